@@ -1,0 +1,437 @@
+#!/usr/bin/env python
+"""bench.py - KITTI-shape frames/s of the Point-GNN message-passing hot path on B200.
+
+    python bench.py --gpus N --steps K --warmup W [--impl reference] [--workload NAME] [--precision P]
+
+A *step* is one pass of the hot path (GPU graph construction + car_auto_T3 forward, real
+trained weights) over one batch of synthetic 20k-point KITTI-crop frames per GPU.  One JSON line is
+printed by rank 0 (contract: project brief, "Measurement").
+
+value      whole-job frames/s, inputs resident in HBM, timed with CUDA events per step (max over ranks)
+e2e        the same metric through the reference-shaped public API with host (pinned) inputs:
+           H2D of points+intensity and D2H of class probabilities + box encodings inside the timing
+roofline   dominant kernel = the fused edge-MLP/segment-max kernel of the GNN iterations, timed live
+           with CUDA events; achieved = algorithmic FLOPs (E1 * 361 800 per launch) / time
+cpu_baseline  the CPU oracle (a port: TF-1.15 cannot be installed) on one frame of the same workload
+--impl reference   times that CPU port alone, all host threads, one frame per step
+"""
+import argparse
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+if ROOT not in sys.path:
+    sys.path.insert(0, ROOT)
+GOLDEN = os.path.join(ROOT, 'tests', 'golden')
+
+WORKLOADS = {
+    # name: (config, points per frame, full_360, frames per step per GPU)
+    'car_auto_T3_20k': ('car_auto_T3_train', 20000, False, 8),
+    'car_auto_T3_120k': ('car_auto_T3_train', 120000, True, 2),
+    'ped_cyl_auto_T3_20k_b8': ('ped_cyl_auto_T3_trainval', 20000, False, 8),
+}
+METRIC = 'KITTI-shape frames/sec (car_auto_T3, graph build + GNN forward)'
+UNIT = 'frames/s'
+
+
+def load_config(name):
+    with open(os.path.join(GOLDEN, 'config_%s.json' % name)) as f:
+        config = json.load(f)
+    weights = dict(np.load(os.path.join(GOLDEN, 'weights_%s.npz' % name)))
+    return config, weights
+
+
+def algorithmic_flops(config, k, e0, e1):
+    """2*M*K*N per fully-connected layer; bias / ReLU / max not counted."""
+    layers = config['model_kwargs']['layer_configs']
+    total = 0
+    edge_flops_per_edge = 0
+    for lc in layers[:-1]:
+        kw = lc['kwargs']
+        if lc['type'] == 'scatter_max_point_set_pooling':
+            dims = [4] + kw['point_MLP_depth_list']
+            total += e0 * sum(2 * a * b for a, b in zip(dims[:-1], dims[1:]))
+            dims = [dims[-1]] + kw['output_MLP_depth_list']
+            total += k * sum(2 * a * b for a, b in zip(dims[:-1], dims[1:]))
+        else:
+            d = kw['edge_MLP_depth_list']
+            dims = [d[0] + 3] + d
+            edge_flops_per_edge = sum(2 * a * b for a, b in zip(dims[:-1], dims[1:]))
+            total += e1 * edge_flops_per_edge
+            dims = [d[-1]] + kw['update_MLP_depth_list']
+            total += k * sum(2 * a * b for a, b in zip(dims[:-1], dims[1:]))
+            if kw.get('auto_offset'):
+                dims = [d[-1]] + kw['auto_offset_MLP_depth_list']
+                total += k * sum(2 * a * b for a, b in zip(dims[:-1], dims[1:]))
+    c = config['num_classes']
+    dlast = layers[-2]['kwargs']['update_MLP_depth_list'][-1]
+    total += k * (2 * dlast * 64 + 2 * 64 * c + c * (2 * dlast * 64 + 2 * 64 * 64 + 2 * 64 * 7))
+    return total, edge_flops_per_edge
+
+
+# ---------------------------------------------------------------------------------------------
+# CPU baseline (oracle port) - also the --impl reference arm
+# ---------------------------------------------------------------------------------------------
+def cpu_frame_seconds(config, weights, frame_idx, num_points, full_360):
+    """One frame through the reference's CPU path: sklearn graph build (graph_gen.py, n_jobs=1 as pinned
+    there) + the torch-CPU restatement of the TF-1.15 forward on all host cores (oracle/cpu_reference.py)."""
+    import warnings
+    from oracle import cpu_reference
+    from oracle import synth
+    xyz, intensity = synth.lidar_frame(frame_idx, num_points, full_360)
+    with warnings.catch_warnings():
+        warnings.simplefilter('ignore')
+        t0 = time.perf_counter()
+        coords, kp, edges = cpu_reference.gen_graph(xyz, **config['runtime_graph_gen_kwargs'])
+        t1 = time.perf_counter()
+        cpu_reference.predict(weights, config['model_kwargs']['layer_configs'], config['num_classes'], 7,
+                              intensity, coords, kp, edges)
+        t2 = time.perf_counter()
+    return t1 - t0, t2 - t1
+
+
+def cpu_model_name():
+    try:
+        with open('/proc/cpuinfo') as f:
+            for line in f:
+                if line.startswith('model name'):
+                    return line.split(':', 1)[1].strip()
+    except OSError:
+        pass
+    return 'unknown'
+
+
+def run_reference(args, rank):
+    """The reference's own CPU path (oracle port of TF-1.15 graph mode + the oracle graph builder)."""
+    if rank != 0:
+        return
+    cfg_name, num_points, full_360, _ = WORKLOADS[args.workload]
+    config, weights = load_config(cfg_name)
+    cores = os.cpu_count() or 1
+    for i in range(args.warmup):
+        cpu_frame_seconds(config, weights, 500 + i, num_points, full_360)
+    t_graph = t_gnn = 0.0
+    for i in range(args.steps):
+        a, b = cpu_frame_seconds(config, weights, 600 + i, num_points, full_360)
+        t_graph += a
+        t_gnn += b
+    total = t_graph + t_gnn
+    value = args.steps / total
+    line = {
+        'impl': 'reference', 'metric': METRIC, 'value': value, 'unit': UNIT, 'n_gpus': args.gpus,
+        'steps': args.steps, 'warmup': args.warmup, 'ms_per_step': 1e3 * total / args.steps,
+        'higher_is_better': True, 'scaling': 'weak', 'vs_baseline': None, 'dtype': 'f32', 'data': 'synthetic',
+        'config': {'workload': args.workload, 'frames_per_step': 1, 'points_per_frame': num_points},
+        'cpu_baseline': {'value': value, 'unit': UNIT, 'cores': cores, 'kind': 'port',
+                         'sample': '1 frame per step of %s; gen graph %.3f s + gnn inference %.3f s per frame; %s' % (
+                             args.workload, t_graph / args.steps, t_gnn / args.steps, cpu_model_name())},
+        'e2e': {'value': value, 'unit': UNIT, 'h2d_bytes_per_step': 0, 'd2h_bytes_per_step': 0},
+        'gpu_launches': 0,
+    }
+    print(json.dumps(line), flush=True)
+
+
+# ---------------------------------------------------------------------------------------------
+# GPU arm
+# ---------------------------------------------------------------------------------------------
+class ClockSampler(object):
+    QUERY = ('index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,'
+             'clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,'
+             'clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap')
+
+    def __init__(self, gpu_index):
+        self.gpu = gpu_index
+        self.rows = []
+        self.proc = None
+        self.thread = None
+
+    def start(self):
+        try:
+            self.proc = subprocess.Popen(
+                ['nvidia-smi', '--query-gpu=' + self.QUERY, '--format=csv,noheader,nounits', '-lms', '100',
+                 '-i', str(self.gpu)], stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+        except OSError:
+            self.proc = None
+            return
+        self.thread = threading.Thread(target=self._read, daemon=True)
+        self.thread.start()
+
+    def _read(self):
+        for line in self.proc.stdout:
+            self.rows.append((time.perf_counter(), [c.strip() for c in line.split(',')]))
+
+    def stop(self, t0, t1):
+        if self.proc is None:
+            return {'sm_mhz': None, 'sm_max_mhz': None, 'reasons': ['nvidia-smi unavailable']}
+        self.proc.terminate()
+        try:
+            self.proc.wait(timeout=5)
+        except subprocess.TimeoutExpired:
+            self.proc.kill()
+        rows = [r for t, r in self.rows if t0 <= t <= t1 and len(r) >= 9] or [r for _, r in self.rows if len(r) >= 9]
+        if not rows:
+            return {'sm_mhz': None, 'sm_max_mhz': None, 'reasons': ['no samples']}
+        sm = sorted(float(r[1]) for r in rows)
+        reasons = set()
+        for r in rows:
+            for name, col in (('hw_slowdown', 5), ('hw_thermal_slowdown', 6), ('sw_thermal_slowdown', 7),
+                              ('sw_power_cap', 8)):
+                if r[col].lower().startswith('active'):
+                    reasons.add(name)
+        return {'sm_mhz': sm[len(sm) // 2], 'sm_max_mhz': float(rows[0][2]), 'reasons': sorted(reasons),
+                'samples': len(rows), 'power_w_max': max(float(r[3]) for r in rows)}
+
+
+def run_gpu(args, rank, world):
+    import torch
+    import torch.distributed as dist
+    import pointgnn_b200
+    from oracle import synth                      # synthetic input generator only
+    from pointgnn_b200 import _lib
+    from pointgnn_b200.models import graph_gen, models
+
+    local_rank = int(os.environ.get('LOCAL_RANK', 0))
+    torch.cuda.set_device(local_rank)
+    dev = torch.device('cuda', local_rank)
+    if world > 1:
+        dist.init_process_group('nccl', device_id=dev)
+    cfg_name, num_points, full_360, frames_per_step = WORKLOADS[args.workload]
+    if args.frames_per_step:
+        frames_per_step = args.frames_per_step
+    config, weights = load_config(cfg_name)
+    precision = args.precision or ('bf16x3' if _lib.tc_available() else 'fp32')
+    pointgnn_b200.set_precision(precision)
+    model = models.get_model(config['model_name'])(num_classes=config['num_classes'], box_encoding_len=7,
+                                                   mode='test', **config['model_kwargs'])
+    model.load_weights(weights)
+    graph_fn = graph_gen.get_graph_generate_fn(config['graph_gen_method'])
+    gkw = config['runtime_graph_gen_kwargs']
+
+    # a pool of distinct frames; every step sees different frames (rank-disjoint), inputs pinned on the host
+    total_steps = args.warmup + args.steps
+    pool = min(total_steps, 6)
+    host_steps = []
+    for s in range(pool):
+        pts, inten = [], []
+        for f in range(frames_per_step):
+            x, it = synth.lidar_frame((rank * 100003 + s * frames_per_step + f) % 100000, num_points, full_360)
+            pts.append(x)
+            inten.append(it)
+        fp = np.arange(frames_per_step + 1, dtype=np.int32) * num_points
+        host_steps.append((torch.from_numpy(np.vstack(pts)).pin_memory(), torch.from_numpy(np.vstack(inten)).pin_memory(),
+                           torch.from_numpy(fp).pin_memory()))
+    dev_steps = [(a.to(dev), b.to(dev), c.to(dev)) for a, b, c in host_steps]
+    flush = torch.empty(256 << 20, dtype=torch.uint8, device=dev)      # > 126 MB L2
+
+    stage_ms = {'gen graph': 0.0, 'gnn inference': 0.0, 'edge kernel': 0.0}
+    counters = {'edges1': 0, 'edges0': 0, 'keypoints': 0, 'edge_launches': 0}
+
+    def step_device(xyz, inten, fp, instrument=False):
+        if instrument:
+            ev = [torch.cuda.Event(enable_timing=True) for _ in range(3)]
+            ev[0].record()
+        coords, kp, edges = graph_fn(xyz, frame_ptr=fp, **gkw)
+        if instrument:
+            ev[1].record()
+        logits, boxes = model.predict(inten, coords, kp, edges, is_training=True)
+        probs = model.postprocess(logits)
+        if instrument:
+            ev[2].record()
+            torch.cuda.synchronize()
+            stage_ms['gen graph'] += ev[0].elapsed_time(ev[1])
+            stage_ms['gnn inference'] += ev[1].elapsed_time(ev[2])
+        return probs, boxes, kp[0].shape[0], edges[0].shape[0], edges[1].shape[0]
+
+    def step_e2e(hx, hi, hfp):
+        xyz = hx.to(dev, non_blocking=True)
+        inten = hi.to(dev, non_blocking=True)
+        fp = hfp.to(dev, non_blocking=True)
+        probs, boxes, k, e0, e1 = step_device(xyz, inten, fp)
+        return probs.cpu(), boxes.cpu()
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    # ---- warm-up ---------------------------------------------------------------------------
+    for s in range(args.warmup):
+        step_device(*dev_steps[s % pool])
+        step_e2e(*host_steps[s % pool])
+    barrier()
+
+    # ---- timed: device-resident inputs -------------------------------------------------------
+    sampler = ClockSampler(local_rank)
+    if rank == 0:
+        sampler.start()
+        time.sleep(0.25)
+    launches0 = _lib.launch_count()
+    barrier()
+    t_wall0 = time.perf_counter()
+    elapsed_ms = 0.0
+    frames = 0
+    for s in range(args.steps):
+        flush.zero_()                                   # L2 flush between timed iterations (untimed)
+        torch.cuda.synchronize()
+        a = torch.cuda.Event(enable_timing=True)
+        b = torch.cuda.Event(enable_timing=True)
+        a.record()
+        probs, boxes, k, e0, e1 = step_device(*dev_steps[(args.warmup + s) % pool])
+        b.record()
+        b.synchronize()
+        elapsed_ms += a.elapsed_time(b)
+        frames += frames_per_step
+        counters['keypoints'] += k
+        counters['edges0'] += e0
+        counters['edges1'] += e1
+    barrier()
+    t_wall1 = time.perf_counter()
+    launches = _lib.launch_count() - launches0
+
+    # ---- timed: end to end through the public API with host buffers ---------------------------
+    barrier()
+    e2e_t0 = time.perf_counter()
+    d2h = 0
+    for s in range(args.steps):
+        p, bx = step_e2e(*host_steps[(args.warmup + s) % pool])
+        d2h = p.numel() * 4 + bx.numel() * 4
+    torch.cuda.synchronize()
+    e2e_s = time.perf_counter() - e2e_t0
+    barrier()
+    clocks = sampler.stop(t_wall0, time.perf_counter()) if rank == 0 else None
+    h2d = sum(t.numel() * t.element_size() for t in host_steps[0])
+
+    # ---- instrumented pass: stage split + the dominant kernel under CUDA events ---------------
+    n_instr = min(args.steps, 3)
+    for s in range(n_instr):
+        step_device(*dev_steps[(args.warmup + s) % pool], instrument=True)
+    edge_ms, edge_flops, edge_launches = time_edge_kernel(model, graph_fn, gkw, dev_steps[args.warmup % pool], config)
+
+    # ---- reduce over ranks ------------------------------------------------------------------
+    t = torch.tensor([elapsed_ms, e2e_s * 1e3], dtype=torch.float64, device=dev)
+    stats = torch.tensor([frames, elapsed_ms, counters['edges1'], counters['edges0'], counters['keypoints']],
+                         dtype=torch.float64, device=dev)
+    if world > 1:
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        gathered = [torch.zeros_like(stats) for _ in range(world)]
+        dist.all_gather(gathered, stats)                 # the only data-path-free collective: counters
+        stats_all = torch.stack(gathered).sum(0)
+    else:
+        stats_all = stats
+    max_ms, max_e2e_ms = float(t[0]), float(t[1])
+    total_frames = float(stats_all[0])
+
+    if rank == 0:
+        peaks = {}
+        try:
+            with open(os.path.join(ROOT, 'MEASURED_PEAKS.json')) as f:
+                peaks = json.load(f)
+        except OSError:
+            pass
+        peak_tf = peaks.get('bf16_tflops_sustained', 1400.0)
+        peak_src = 'measured (MEASURED_PEAKS.json bf16_tflops_sustained)' if peaks else 'fallback 1.4 PFLOP/s sustained'
+        achieved = edge_flops / (edge_ms * 1e-3) / 1e12 if edge_ms > 0 else 0.0
+        k_avg = counters['keypoints'] / args.steps / frames_per_step
+        e0_avg = counters['edges0'] / args.steps / frames_per_step
+        e1_avg = counters['edges1'] / args.steps / frames_per_step
+        flops_frame, _ = algorithmic_flops(config, k_avg, e0_avg, e1_avg)
+        cpu = None
+        if not args.no_cpu_baseline:
+            cpu_frame_seconds(config, weights, 899, num_points, full_360)          # warm-up frame
+            reps = [cpu_frame_seconds(config, weights, 900 + i, num_points, full_360) for i in range(3)]
+            g = sum(r[0] for r in reps) / len(reps)
+            n = sum(r[1] for r in reps) / len(reps)
+            cpu = {'value': 1.0 / (g + n), 'unit': UNIT, 'cores': os.cpu_count() or 1, 'kind': 'port',
+                   'sample': 'mean of 3 frames of %s after 1 warm-up (gen graph %.3f s + gnn inference %.3f s); sklearn graph + torch-CPU fp32 GNN; %s' % (
+                       args.workload, g, n, cpu_model_name())}
+        line = {
+            'metric': METRIC, 'value': total_frames / (max_ms * 1e-3), 'unit': UNIT, 'n_gpus': world,
+            'steps': args.steps, 'warmup': args.warmup, 'ms_per_step': max_ms / args.steps,
+            'higher_is_better': True, 'scaling': 'weak', 'vs_baseline': None,
+            'dtype': 'bf16x3(f32-class)' if precision == 'bf16x3' else 'f32', 'data': 'synthetic',
+            'config': {'workload': args.workload, 'model': cfg_name, 'frames_per_step_per_gpu': frames_per_step,
+                       'points_per_frame': num_points, 'keypoints_per_frame': k_avg, 'edges0_per_frame': e0_avg,
+                       'edges1_per_frame': e1_avg, 'algorithmic_gflop_per_frame': flops_frame / 1e9,
+                       'weights': 'reference checkpoint ' + cfg_name, 'precision': precision,
+                       'l2': 'flushed between timed steps (256 MB write) + distinct frames per step',
+                       'parallelism': 'dp%d (frames sharded, counters all-gathered)' % world},
+            'e2e': {'value': total_frames / (max_e2e_ms * 1e-3), 'unit': UNIT, 'h2d_bytes_per_step': h2d,
+                    'd2h_bytes_per_step': d2h},
+            'gpu_launches': launches,
+            'clocks': clocks,
+            'stages_ms_per_step': {k: v / n_instr for k, v in stage_ms.items() if k != 'edge kernel'},
+            'roofline': {'bound': 'tensor', 'kernel': 'edge_mlp_max (GNN iteration)', 'achieved': achieved,
+                         'peak': peak_tf, 'unit': 'TFLOP/s', 'frac': achieved / peak_tf, 'traffic': None,
+                         'peak_source': peak_src, 'launch_ms': edge_ms / max(edge_launches, 1),
+                         'algorithmic_flops_per_launch': edge_flops / max(edge_launches, 1)},
+            'cpu_baseline': cpu,
+        }
+        print(json.dumps(line), flush=True)
+    if world > 1:
+        dist.destroy_process_group()
+
+
+def time_edge_kernel(model, graph_fn, gkw, dev_step, config):
+    """CUDA-event time of the dominant kernel (fused edge MLP + segment max of one GNN iteration)."""
+    import torch
+    import pointgnn_b200
+    from pointgnn_b200 import _lib
+    from pointgnn_b200.models import gnn
+    xyz, inten, fp = dev_step
+    coords, kp, edges = graph_fn(xyz, frame_ptr=fp, **gkw)
+    lc = [l for l in config['model_kwargs']['layer_configs'] if l['type'] == 'scatter_max_graph_auto_center_net']
+    if not lc:
+        return 0.0, 0.0, 0
+    lc = lc[0]
+    d = lc['kwargs']['edge_MLP_depth_list']
+    k = coords[1].shape[0]
+    feats = torch.rand((k, d[-1]), device=xyz.device) * 0.5
+    store = model._store
+    with gnn.variable_session(store), gnn.variable_scope(lc['scope']), gnn.variable_scope('extract_vertex_features'):
+        ws, bs = gnn._take_mlp_weights(len(d))
+    src, dst = edges[1][:, 0].contiguous(), edges[1][:, 1].contiguous()
+    reps = 5
+    prec = pointgnn_b200.get_precision()
+    for _ in range(2):
+        _lib.edge_mlp_max(1, feats, coords[1], coords[1], None, src, dst, k, ws, bs, precision=prec)
+    torch.cuda.synchronize()
+    a = torch.cuda.Event(enable_timing=True)
+    b = torch.cuda.Event(enable_timing=True)
+    a.record()
+    for _ in range(reps):
+        _lib.edge_mlp_max(1, feats, coords[1], coords[1], None, src, dst, k, ws, bs, precision=prec)
+    b.record()
+    b.synchronize()
+    dims = [d[0] + 3] + d
+    per_edge = sum(2 * x * y for x, y in zip(dims[:-1], dims[1:]))
+    return a.elapsed_time(b), float(src.numel()) * per_edge * reps, reps
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument('--gpus', type=int, default=1)
+    ap.add_argument('--steps', type=int, default=5)
+    ap.add_argument('--warmup', type=int, default=3)
+    ap.add_argument('--impl', default='ours', choices=['ours', 'reference'])
+    ap.add_argument('--workload', default='car_auto_T3_20k', choices=sorted(WORKLOADS))
+    ap.add_argument('--precision', default=None, choices=['fp32', 'bf16x3'])
+    ap.add_argument('--frames-per-step', type=int, default=0)
+    ap.add_argument('--no-cpu-baseline', action='store_true')
+    args = ap.parse_args()
+    args.warmup = max(args.warmup, 3) if args.impl == 'ours' else args.warmup
+    rank = int(os.environ.get('RANK', 0))
+    world = int(os.environ.get('WORLD_SIZE', 1))
+    if args.impl == 'reference':
+        run_reference(args, rank)
+        return
+    run_gpu(args, rank, world)
+
+
+if __name__ == '__main__':
+    main()

@@ -1,0 +1,188 @@
+/*
+ * pointgnn_b200.h - C ABI of libpointgnn_b200.so
+ *
+ * B200 (sm_100a) implementation of Point-GNN's per-frame message-passing hot
+ * path.  Every entry point replaces one piece of the reference's Python/TF path;
+ * the reference interface each one stands in for is cited as
+ * /root/reference/<file>:<line>.
+ *
+ * Conventions
+ *  - All pointers are DEVICE pointers unless the parameter name ends in _host.
+ *  - Row-major, C-contiguous arrays; float = IEEE fp32, indices = int32.
+ *  - `stream` is a cudaStream_t passed as void* (NULL = legacy default stream).
+ *  - Return value: 0 = ok, <0 = error (PG_ERR_*); pg_last_error() gives the
+ *    message of the last failure on the calling thread.  Nothing aborts.
+ *  - Kernels never retain caller pointers after the call returns; temporary
+ *    buffers come from the stream-ordered allocator (cudaMallocAsync).
+ *  - Multi-frame batches follow the reference's batch_data semantics
+ *    (/root/reference/train.py:135-171): frames are concatenated, `frame_ptr`
+ *    [num_frames+1] gives each frame's row range, and all emitted indices are
+ *    GLOBAL (already offset), i.e. exactly what batch_data would produce.
+ */
+#ifndef POINTGNN_B200_H_
+#define POINTGNN_B200_H_
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#if defined(__GNUC__)
+#define PG_API __attribute__((visibility("default")))
+#else
+#define PG_API
+#endif
+
+#define PG_OK 0
+#define PG_ERR_INVALID_ARGUMENT (-1)
+#define PG_ERR_CUDA (-2)
+#define PG_ERR_CAPACITY (-3)   /* caller-provided output buffer too small   */
+#define PG_ERR_RANGE (-4)      /* cloud extent / cell index exceeds key bits */
+#define PG_ERR_UNSUPPORTED (-5)
+
+/* Library ABI version (bumped on any signature change). */
+PG_API int pg_version(void);
+/* Message of the last error on this thread ("" if none). */
+PG_API const char* pg_last_error(void);
+/* 1 if the visible device is sm_100 (B200); the tcgen05 kernels require it. */
+PG_API int pg_device_is_sm100(void);
+/* 1 if the tcgen05 (precision = 1) kernels are built in AND the device can run them. */
+PG_API int pg_tc_available(void);
+
+/* ------------------------------------------------------------------------ *
+ * Graph construction  (reference models/graph_gen.py)
+ * ------------------------------------------------------------------------ */
+
+/*
+ * Voxel keypoint selection = multi_layer_downsampling (open3d.voxel_down_sample,
+ * graph_gen.py:41-45) + the kd-tree 1-NN snap of multi_layer_downsampling_select
+ * (graph_gen.py:84-88), for one voxel scale, over a batch of frames.
+ *
+ *   xyz        [N,3] fp32 points of all frames, concatenated
+ *   frame_ptr  [num_frames+1] int32, frame f owns rows frame_ptr[f]..frame_ptr[f+1)
+ *   voxel_size [3] (host) fp64 voxel edge per axis (= base_voxel_size*graph_scale)
+ *   out_keypoint_idx [capacity] int32: GLOBAL row index of the original point
+ *              nearest to each voxel centroid (fp64 distance, ties -> lowest index);
+ *              per frame in ascending linear-voxel-key order; duplicates kept.
+ *   out_kp_frame_ptr [num_frames+1] int32 keypoint range of each frame
+ *   out_num_keypoints_host  (host) total K.  The call synchronises the stream.
+ * Returns PG_ERR_CAPACITY (and the needed K in *out_num_keypoints_host) if
+ * capacity < K; capacity = N always suffices.
+ */
+PG_API int pg_voxel_keypoints(const float* xyz, const int32_t* frame_ptr, int32_t num_frames,
+                       int64_t num_points, const double* voxel_size_host,
+                       int32_t* out_keypoint_idx, int64_t capacity,
+                       int32_t* out_kp_frame_ptr, int64_t* out_num_keypoints_host,
+                       void* stream);
+
+/*
+ * Radius-neighbour graph = gen_disjointed_rnn_local_graph_v3
+ * (graph_gen.py:197-220; ball_tree radius_neighbors, fp64 predicate
+ * ((dx*dx+dy*dy)+dz*dz) <= r*r on float32-valued coordinates, inclusive), with
+ * num_neighbors <= 0 (no random cap: the inference path, run.py:219-222).
+ * Two passes so the caller owns the edge buffer:
+ *
+ *   pg_radius_graph_count: out_row_ptr [K+1] int32 (CSR by destination/centre),
+ *                          *out_num_edges_host = E (synchronises the stream).
+ *   pg_radius_graph_fill:  out_src [E] int32 source (point) index of every edge,
+ *                          ascending inside a row; out_dst [E] int32 (may be NULL)
+ *                          the expanded destination index, so that
+ *                          stack([out_src,out_dst],1) == the reference's [E,2]
+ *                          `vertices` array after a (dst,src) sort.
+ *
+ *   points  [P,3] fp32 source set,  point_frame_ptr  [num_frames+1]
+ *   centers [K,3] fp32 centre set,  center_frame_ptr [num_frames+1]
+ * Edges only connect points and centres of the same frame.
+ */
+PG_API int pg_radius_graph_count(const float* points, const int32_t* point_frame_ptr,
+                          const float* centers, const int32_t* center_frame_ptr,
+                          int32_t num_frames, int64_t num_points, int64_t num_centers,
+                          double radius, int32_t* out_row_ptr, int64_t* out_num_edges_host,
+                          void* stream);
+PG_API int pg_radius_graph_fill(const float* points, const int32_t* point_frame_ptr,
+                         const float* centers, const int32_t* center_frame_ptr,
+                         int32_t num_frames, int64_t num_points, int64_t num_centers,
+                         double radius, const int32_t* row_ptr, int64_t num_edges,
+                         int32_t* out_src, int32_t* out_dst, void* stream);
+
+/*
+ * Single-call variant (one grid build, count -> scan -> fill) writing into a caller buffer of
+ * `capacity` edges.  Returns PG_ERR_CAPACITY with the needed E in *out_num_edges_host when
+ * the buffer is too small (out_row_ptr is valid in that case).
+ */
+PG_API int pg_radius_graph(const float* points, const int32_t* point_frame_ptr, const float* centers,
+                    const int32_t* center_frame_ptr, int32_t num_frames, int64_t num_points,
+                    int64_t num_centers, double radius, int32_t* out_row_ptr, int32_t* out_src,
+                    int32_t* out_dst, int64_t capacity, int64_t* out_num_edges_host, void* stream);
+
+/* ------------------------------------------------------------------------ *
+ * GNN ops  (reference models/gnn.py)
+ * ------------------------------------------------------------------------ */
+
+/*
+ * graph_scatter_max_fn (gnn.py:106-109) = tf.math.unsorted_segment_max:
+ * out[k,c] = max over edges e with centers[e]==k of features[e,c]; empty segment
+ * -> -FLT_MAX (numeric_limits<float>::lowest()).  `centers` may be in any order.
+ */
+PG_API int pg_scatter_max(const float* features, const int32_t* centers, int64_t num_edges,
+                   int32_t num_channels, int64_t num_centers, float* out, void* stream);
+
+/* tf.gather(params, indices) for [R,C] fp32 rows (gnn.py:256-262,338-348). */
+PG_API int pg_gather_rows(const float* params, int64_t num_rows, int32_t num_channels,
+                   const int32_t* indices, int64_t num_indices, float* out, void* stream);
+
+/*
+ * One slim.fully_connected layer (gnn.py:63-80,93-103), normalizer NONE:
+ *   out[M,N] = act(x[M,K] @ w[K,N] + bias[N]) (+ residual[M,N] if not NULL)
+ * act: 0 = linear (the is_logits last layer), 1 = ReLU.
+ * precision: 0 = fp32 FFMA, 1 = tcgen05 BF16x3 split (fp32-class accuracy).
+ */
+PG_API int pg_fully_connected(const float* x, int64_t m, int32_t k, const float* w, const float* bias,
+                       int32_t n, int32_t act, const float* residual, float* out,
+                       int32_t precision, void* stream);
+
+/*
+ * Fused per-edge MLP + segment max: the body of PointSetPooling.apply_regular
+ * (gnn.py:256-277) and of GraphNetAutoCenter.apply_regular (gnn.py:338-365),
+ * never materialising the [E, D] edge tensors.
+ *
+ *   mode PG_EDGE_POOL : e0 = concat(point_features[src], xyz_src[src] - xyz_dst[kp[dst]])
+ *                       (feature first, then relative xyz; gnn.py:264-267)
+ *   mode PG_EDGE_GNN  : e0 = concat(vertex_features[src], xyz_src[src] - xyz_dst[dst])
+ *                       xyz_src = un-offset coords, xyz_dst = coords + auto-offset
+ *                       (gnn.py:338-352)
+ *   then num_layers x relu(. @ W_l + b_l)      (is_logits=False, gnn.py:99-103)
+ *   then out[k,:] = max over the edges of destination k   (gnn.py:362-365)
+ *
+ *   src, dst     [E] int32; dst must be non-decreasing (CSR order, as produced by
+ *                pg_radius_graph_fill and by the reference generator).
+ *   dst_index    POOL: keypoint_indices [num_dst] int32 (row of xyz_dst per dst);
+ *                GNN: NULL (identity)
+ *   weights_host / biases_host: (host) arrays of num_layers DEVICE pointers,
+ *                W_l is [dims[l], dims[l+1]] row-major, dims[0] = C_in + 3.
+ *   dims_host    (host) [num_layers+1]
+ *   out          [num_dst, dims[num_layers]]; empty segments get -FLT_MAX.
+ *   precision    0 = fp32 FFMA, 1 = tcgen05 BF16x3 for the wide layers.
+ */
+#define PG_EDGE_POOL 0
+#define PG_EDGE_GNN 1
+PG_API int pg_edge_mlp_max(int32_t mode, const float* features, int32_t num_feature_channels,
+                    const float* xyz_src, const float* xyz_dst, const int32_t* dst_index,
+                    const int32_t* src, const int32_t* dst, int64_t num_edges, int64_t num_src,
+                    int64_t num_dst, const float* const* weights_host,
+                    const float* const* biases_host, const int32_t* dims_host,
+                    int32_t num_layers, float* out, int32_t precision, void* stream);
+
+/* Row-wise softmax, MultiLayerFastLocalGraphModelV2.postprocess (models.py:165-168). */
+PG_API int pg_softmax_rows(const float* logits, int64_t num_rows, int32_t num_classes, float* out,
+                    void* stream);
+
+/* Number of kernels this library has launched in the calling process (bench.py). */
+PG_API int64_t pg_launch_count(void);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* POINTGNN_B200_H_ */

@@ -1,0 +1,238 @@
+"""ctypes binding of libpointgnn_b200.so (C ABI: include/pointgnn_b200.h).
+
+The library is loaded on first use and the import fails loudly when it is
+missing or lacks a symbol - there is no CPU or PyTorch fallback behind these
+wrappers.  Arguments are torch CUDA tensors; only their device pointers, sizes
+and the current CUDA stream cross the boundary.
+"""
+import ctypes
+import os
+
+import torch
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+LIB_PATH = os.path.join(_HERE, 'libpointgnn_b200.so')
+
+PG_ERR_CAPACITY = -3
+
+c_i32p = ctypes.c_void_p
+c_f32p = ctypes.c_void_p
+c_i64 = ctypes.c_int64
+c_i32 = ctypes.c_int32
+
+# name -> (restype, argtypes); must list every symbol include/pointgnn_b200.h declares
+SIGNATURES = {
+    'pg_version': (ctypes.c_int, []),
+    'pg_last_error': (ctypes.c_char_p, []),
+    'pg_device_is_sm100': (ctypes.c_int, []),
+    'pg_launch_count': (c_i64, []),
+    'pg_tc_available': (ctypes.c_int, []),
+    'pg_voxel_keypoints': (ctypes.c_int, [c_f32p, c_i32p, c_i32, c_i64, ctypes.POINTER(ctypes.c_double),
+                                          c_i32p, c_i64, c_i32p, ctypes.POINTER(c_i64), ctypes.c_void_p]),
+    'pg_radius_graph_count': (ctypes.c_int, [c_f32p, c_i32p, c_f32p, c_i32p, c_i32, c_i64, c_i64,
+                                             ctypes.c_double, c_i32p, ctypes.POINTER(c_i64), ctypes.c_void_p]),
+    'pg_radius_graph_fill': (ctypes.c_int, [c_f32p, c_i32p, c_f32p, c_i32p, c_i32, c_i64, c_i64,
+                                            ctypes.c_double, c_i32p, c_i64, c_i32p, c_i32p, ctypes.c_void_p]),
+    'pg_radius_graph': (ctypes.c_int, [c_f32p, c_i32p, c_f32p, c_i32p, c_i32, c_i64, c_i64, ctypes.c_double,
+                                       c_i32p, c_i32p, c_i32p, c_i64, ctypes.POINTER(c_i64), ctypes.c_void_p]),
+    'pg_scatter_max': (ctypes.c_int, [c_f32p, c_i32p, c_i64, c_i32, c_i64, c_f32p, ctypes.c_void_p]),
+    'pg_gather_rows': (ctypes.c_int, [c_f32p, c_i64, c_i32, c_i32p, c_i64, c_f32p, ctypes.c_void_p]),
+    'pg_fully_connected': (ctypes.c_int, [c_f32p, c_i64, c_i32, c_f32p, c_f32p, c_i32, c_i32, c_f32p, c_f32p,
+                                          c_i32, ctypes.c_void_p]),
+    'pg_edge_mlp_max': (ctypes.c_int, [c_i32, c_f32p, c_i32, c_f32p, c_f32p, c_i32p, c_i32p, c_i32p, c_i64, c_i64,
+                                       c_i64, ctypes.POINTER(ctypes.c_void_p), ctypes.POINTER(ctypes.c_void_p),
+                                       ctypes.POINTER(c_i32), c_i32, c_f32p, c_i32, ctypes.c_void_p]),
+    'pg_softmax_rows': (ctypes.c_int, [c_f32p, c_i64, c_i32, c_f32p, ctypes.c_void_p]),
+}
+
+_lib = None
+
+
+class PointGNNError(RuntimeError):
+    """A C-ABI call returned a negative status."""
+
+    def __init__(self, code, message):
+        super().__init__('libpointgnn_b200 error %d: %s' % (code, message))
+        self.code = code
+
+
+def load():
+    """Load (once) and type the shared library; raise if it is absent or incomplete."""
+    global _lib
+    if _lib is not None:
+        return _lib
+    if not os.path.isfile(LIB_PATH):
+        raise ImportError(
+            'libpointgnn_b200.so not found at %s - build it with `python -c "import __graft_entry__ as g; '
+            'g.build()"` or `make -C point-gnn_b200/csrc`; there is no CPU fallback' % LIB_PATH)
+    lib = ctypes.CDLL(LIB_PATH)
+    for name, (restype, argtypes) in SIGNATURES.items():
+        fn = getattr(lib, name)      # AttributeError if the symbol is missing
+        fn.restype = restype
+        fn.argtypes = argtypes
+    _lib = lib
+    return lib
+
+
+def _check(code):
+    if code < 0:
+        raise PointGNNError(code, load().pg_last_error().decode())
+    return code
+
+
+def _stream():
+    return ctypes.c_void_p(torch.cuda.current_stream().cuda_stream)
+
+
+def _ptr(t, dtype, name):
+    if t is None:
+        return None
+    if not isinstance(t, torch.Tensor) or not t.is_cuda:
+        raise TypeError('%s must be a CUDA tensor (there is no CPU path)' % name)
+    if t.dtype != dtype:
+        raise TypeError('%s must be %s, got %s' % (name, dtype, t.dtype))
+    if not t.is_contiguous():
+        raise ValueError('%s must be contiguous' % name)
+    return ctypes.c_void_p(t.data_ptr())
+
+
+def launch_count():
+    return int(load().pg_launch_count())
+
+
+def device_is_sm100():
+    return bool(load().pg_device_is_sm100())
+
+
+def tc_available():
+    """True when the tcgen05 (precision=1) kernels are compiled in and the device is sm_100."""
+    return bool(load().pg_tc_available())
+
+
+# ---------------------------------------------------------------------------------------------
+# graph construction
+# ---------------------------------------------------------------------------------------------
+
+def voxel_keypoints(xyz, frame_ptr, voxel_size):
+    """-> (keypoint_idx [K] int32 global point rows, kp_frame_ptr [F+1] int32)."""
+    lib = load()
+    n = xyz.shape[0]
+    num_frames = frame_ptr.numel() - 1
+    out_idx = torch.empty(n, dtype=torch.int32, device=xyz.device)
+    out_fp = torch.empty(num_frames + 1, dtype=torch.int32, device=xyz.device)
+    vs = (ctypes.c_double * 3)(*[float(v) for v in voxel_size])
+    k = c_i64(0)
+    _check(lib.pg_voxel_keypoints(_ptr(xyz, torch.float32, 'xyz'), _ptr(frame_ptr, torch.int32, 'frame_ptr'),
+                                  num_frames, n, vs, _ptr(out_idx, torch.int32, 'out'), n,
+                                  _ptr(out_fp, torch.int32, 'out_fp'), ctypes.byref(k), _stream()))
+    return out_idx[:k.value], out_fp
+
+
+_edge_capacity = {}
+
+
+def radius_graph(points, point_frame_ptr, centers, center_frame_ptr, radius):
+    """-> (row_ptr [K+1] int32, edges [2,E] int32 with row 0 = src, row 1 = dst)."""
+    lib = load()
+    p, k = points.shape[0], centers.shape[0]
+    num_frames = point_frame_ptr.numel() - 1
+    row_ptr = torch.empty(k + 1, dtype=torch.int32, device=points.device)
+    key = (points.device.index, float(radius))
+    cap = max(_edge_capacity.get(key, 0), 64 * k, 1 << 16)
+    e = c_i64(0)
+    while True:
+        buf = torch.empty((2, cap), dtype=torch.int32, device=points.device)
+        code = lib.pg_radius_graph(_ptr(points, torch.float32, 'points'),
+                                   _ptr(point_frame_ptr, torch.int32, 'point_frame_ptr'),
+                                   _ptr(centers, torch.float32, 'centers'),
+                                   _ptr(center_frame_ptr, torch.int32, 'center_frame_ptr'), num_frames, p, k,
+                                   float(radius), _ptr(row_ptr, torch.int32, 'row_ptr'),
+                                   ctypes.c_void_p(buf[0].data_ptr()), ctypes.c_void_p(buf[1].data_ptr()), cap,
+                                   ctypes.byref(e), _stream())
+        if code == PG_ERR_CAPACITY:
+            cap = int(e.value * 1.25) + 1024
+            continue
+        _check(code)
+        break
+    _edge_capacity[key] = max(_edge_capacity.get(key, 0), int(e.value * 1.25) + 1024)
+    # rows of buf are src / dst; the [E,2] transpose view of this slice has contiguous columns
+    return row_ptr, buf[:, :e.value]
+
+
+def radius_graph_two_pass(points, point_frame_ptr, centers, center_frame_ptr, radius):
+    """The count / fill pair of the ABI (caller-allocated exact edge buffer)."""
+    lib = load()
+    p, k = points.shape[0], centers.shape[0]
+    num_frames = point_frame_ptr.numel() - 1
+    row_ptr = torch.empty(k + 1, dtype=torch.int32, device=points.device)
+    e = c_i64(0)
+    args = (_ptr(points, torch.float32, 'points'), _ptr(point_frame_ptr, torch.int32, 'point_frame_ptr'),
+            _ptr(centers, torch.float32, 'centers'), _ptr(center_frame_ptr, torch.int32, 'center_frame_ptr'),
+            num_frames, p, k, float(radius))
+    _check(lib.pg_radius_graph_count(*args, _ptr(row_ptr, torch.int32, 'row_ptr'), ctypes.byref(e), _stream()))
+    out = torch.empty((2, e.value), dtype=torch.int32, device=points.device)
+    _check(lib.pg_radius_graph_fill(*args, _ptr(row_ptr, torch.int32, 'row_ptr'), e.value,
+                                    ctypes.c_void_p(out[0].data_ptr()), ctypes.c_void_p(out[1].data_ptr()),
+                                    _stream()))
+    return row_ptr, out
+
+
+# ---------------------------------------------------------------------------------------------
+# GNN ops
+# ---------------------------------------------------------------------------------------------
+
+def scatter_max(features, centers, num_centers):
+    lib = load()
+    e, c = features.shape
+    out = torch.empty((int(num_centers), c), dtype=torch.float32, device=features.device)
+    _check(lib.pg_scatter_max(_ptr(features, torch.float32, 'features'), _ptr(centers, torch.int32, 'centers'), e, c,
+                              int(num_centers), _ptr(out, torch.float32, 'out'), _stream()))
+    return out
+
+
+def gather_rows(params, indices):
+    lib = load()
+    r, c = params.shape
+    n = indices.numel()
+    out = torch.empty((n, c), dtype=torch.float32, device=params.device)
+    _check(lib.pg_gather_rows(_ptr(params, torch.float32, 'params'), r, c, _ptr(indices, torch.int32, 'indices'), n,
+                              _ptr(out, torch.float32, 'out'), _stream()))
+    return out
+
+
+def fully_connected(x, w, b, relu, residual=None, precision=0):
+    lib = load()
+    m, k = x.shape
+    if w.shape[0] != k:
+        raise ValueError('fully_connected: input width %d != weight rows %d' % (k, w.shape[0]))
+    n = w.shape[1]
+    out = torch.empty((m, n), dtype=torch.float32, device=x.device)
+    _check(lib.pg_fully_connected(_ptr(x, torch.float32, 'x'), m, k, _ptr(w, torch.float32, 'w'),
+                                  _ptr(b, torch.float32, 'b'), n, 1 if relu else 0,
+                                  _ptr(residual, torch.float32, 'residual'), _ptr(out, torch.float32, 'out'),
+                                  int(precision), _stream()))
+    return out
+
+
+def edge_mlp_max(mode, features, xyz_src, xyz_dst, dst_index, src, dst, num_dst, weights, biases, precision=0):
+    lib = load()
+    num_layers = len(weights)
+    dims = [weights[0].shape[0]] + [w.shape[1] for w in weights]
+    wp = (ctypes.c_void_p * num_layers)(*[_ptr(w, torch.float32, 'weight').value for w in weights])
+    bp = (ctypes.c_void_p * num_layers)(*[_ptr(b, torch.float32, 'bias').value for b in biases])
+    dm = (c_i32 * (num_layers + 1))(*dims)
+    out = torch.empty((int(num_dst), dims[-1]), dtype=torch.float32, device=features.device)
+    _check(lib.pg_edge_mlp_max(int(mode), _ptr(features, torch.float32, 'features'), features.shape[1],
+                               _ptr(xyz_src, torch.float32, 'xyz_src'), _ptr(xyz_dst, torch.float32, 'xyz_dst'),
+                               _ptr(dst_index, torch.int32, 'dst_index'), _ptr(src, torch.int32, 'src'),
+                               _ptr(dst, torch.int32, 'dst'), src.numel(), features.shape[0], int(num_dst), wp, bp,
+                               dm, num_layers, _ptr(out, torch.float32, 'out'), int(precision), _stream()))
+    return out
+
+
+def softmax_rows(logits):
+    lib = load()
+    out = torch.empty_like(logits)
+    _check(lib.pg_softmax_rows(_ptr(logits, torch.float32, 'logits'), logits.shape[0], logits.shape[1],
+                               _ptr(out, torch.float32, 'out'), _stream()))
+    return out

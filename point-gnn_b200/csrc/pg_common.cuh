@@ -1,0 +1,70 @@
+// Shared helpers for libpointgnn_b200 (error plumbing, launch accounting, temp buffers).
+#pragma once
+#include <cuda_runtime.h>
+#include <stdint.h>
+#include <stdio.h>
+#include <float.h>
+
+#include "../../include/pointgnn_b200.h"
+
+namespace pg {
+
+void set_error(const char* fmt, ...);
+void count_launch(int n = 1);
+
+#define PG_CUDA_OK(expr)                                                              \
+  do {                                                                                \
+    cudaError_t _e = (expr);                                                          \
+    if (_e != cudaSuccess) {                                                          \
+      pg::set_error("%s:%d %s -> %s", __FILE__, __LINE__, #expr, cudaGetErrorString(_e)); \
+      return PG_ERR_CUDA;                                                             \
+    }                                                                                 \
+  } while (0)
+
+#define PG_REQUIRE(cond, ...)              \
+  do {                                     \
+    if (!(cond)) {                         \
+      pg::set_error(__VA_ARGS__);          \
+      return PG_ERR_INVALID_ARGUMENT;      \
+    }                                      \
+  } while (0)
+
+#define PG_LAUNCH_CHECK()                     \
+  do {                                        \
+    pg::count_launch();                       \
+    PG_CUDA_OK(cudaGetLastError());           \
+  } while (0)
+
+// Stream-ordered temporary buffer; freed (stream-ordered) when it goes out of scope.
+struct Temp {
+  void* ptr = nullptr;
+  cudaStream_t stream = nullptr;
+  Temp() {}
+  Temp(const Temp&) = delete;
+  Temp& operator=(const Temp&) = delete;
+  cudaError_t alloc(size_t bytes, cudaStream_t s) {
+    stream = s;
+    if (bytes == 0) bytes = 16;
+    return cudaMallocAsync(&ptr, bytes, s);
+  }
+  template <typename T>
+  T* as() const { return reinterpret_cast<T*>(ptr); }
+  ~Temp() {
+    if (ptr) cudaFreeAsync(ptr, stream);
+  }
+};
+
+inline int num_sms() {
+  static int sms = 0;
+  if (sms == 0) {
+    int dev = 0;
+    cudaGetDevice(&dev);
+    cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
+    if (sms <= 0) sms = 148;
+  }
+  return sms;
+}
+
+static inline int64_t ceil_div(int64_t a, int64_t b) { return (a + b - 1) / b; }
+
+}  // namespace pg

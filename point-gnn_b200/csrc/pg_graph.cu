@@ -1,0 +1,538 @@
+// Graph construction on the GPU: voxel keypoint selection and radius-neighbour CSR graphs.
+//
+// Replaces /root/reference/models/graph_gen.py:
+//   multi_layer_downsampling (:11-47, open3d.voxel_down_sample branch :41-45)
+//   multi_layer_downsampling_select (:49-90, kd-tree 1-NN snap :84-88)
+//   gen_disjointed_rnn_local_graph_v3 (:197-220, ball-tree radius query)
+//
+// Design: every spatial query runs on a sorted-key uniform grid.  A point's 64-bit key is
+//   frame(16) | iz(16) | iy(16) | ix(16)
+// so one radix sort groups points by (frame, cell) and, because ix is the low field, the three
+// x-adjacent cells of a (frame, iz, iy) row are one contiguous range of the sorted array: a
+// 3x3x3 neighbourhood costs 9 binary searches.  There is no dense grid, so memory is O(N)
+// whatever the extent of the cloud.  All predicates that decide membership (voxel index,
+// nearest point, radius test) are evaluated in fp64 with explicitly rounded mul/add
+// (no FMA contraction), which is what makes the edge lists bit-exact against the reference's
+// scikit-learn float64 trees.
+#include <cub/cub.cuh>
+
+#include "pg_common.cuh"
+
+namespace pg {
+namespace {
+
+constexpr int kAxisBits = 16;
+constexpr int kAxisMax = (1 << kAxisBits) - 1;
+constexpr double kCellSlack = 1.0001;  // cell edge = radius * slack, keeps +-1 cell search exact
+
+__host__ __device__ inline uint64_t make_key(uint32_t frame, uint32_t iz, uint32_t iy, uint32_t ix) {
+  return (uint64_t(frame) << 48) | (uint64_t(iz) << 32) | (uint64_t(iy) << 16) | uint64_t(ix);
+}
+
+// float <-> order-preserving uint (for atomicMin on floats)
+__device__ inline uint32_t float_to_ordered(float f) {
+  uint32_t b = __float_as_uint(f);
+  return (b & 0x80000000u) ? ~b : (b | 0x80000000u);
+}
+__device__ inline float ordered_to_float(uint32_t u) {
+  uint32_t b = (u & 0x80000000u) ? (u & 0x7fffffffu) : ~u;
+  return __uint_as_float(b);
+}
+
+__device__ inline int find_frame(const int32_t* __restrict__ frame_ptr, int num_frames, int64_t row) {
+  int lo = 0, hi = num_frames;  // invariant: frame_ptr[lo] <= row < frame_ptr[hi]
+  while (hi - lo > 1) {
+    int mid = (lo + hi) >> 1;
+    if (frame_ptr[mid] <= row) lo = mid; else hi = mid;
+  }
+  return lo;
+}
+
+// ---- per-frame bounding-box minimum ---------------------------------------------------------
+__global__ void init_bounds_kernel(uint32_t* __restrict__ bounds, int n) {
+  int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i < n) bounds[i] = 0xffffffffu;
+}
+
+__global__ void frame_min_kernel(const float* __restrict__ xyz, const int32_t* __restrict__ frame_ptr,
+                                 uint32_t* __restrict__ bounds) {
+  const int f = blockIdx.y;
+  const int64_t begin = frame_ptr[f], end = frame_ptr[f + 1];
+  float mx = FLT_MAX, my = FLT_MAX, mz = FLT_MAX;
+  for (int64_t i = begin + blockIdx.x * blockDim.x + threadIdx.x; i < end;
+       i += int64_t(gridDim.x) * blockDim.x) {
+    mx = fminf(mx, xyz[3 * i + 0]);
+    my = fminf(my, xyz[3 * i + 1]);
+    mz = fminf(mz, xyz[3 * i + 2]);
+  }
+  for (int o = 16; o > 0; o >>= 1) {
+    mx = fminf(mx, __shfl_xor_sync(0xffffffffu, mx, o));
+    my = fminf(my, __shfl_xor_sync(0xffffffffu, my, o));
+    mz = fminf(mz, __shfl_xor_sync(0xffffffffu, mz, o));
+  }
+  if ((threadIdx.x & 31) == 0 && begin < end) {
+    atomicMin(&bounds[3 * f + 0], float_to_ordered(mx));
+    atomicMin(&bounds[3 * f + 1], float_to_ordered(my));
+    atomicMin(&bounds[3 * f + 2], float_to_ordered(mz));
+  }
+}
+
+// Grid description shared by key generation and queries.
+struct GridSpec {
+  double cell[3];     // cell edge per axis
+  double origin_off;  // origin = frame_min - cell * origin_off   (0.5 for Open3D voxels, 0 for radius grids)
+};
+
+__device__ inline void cell_of(const GridSpec& g, const uint32_t* __restrict__ bounds, int f, float x,
+                               float y, float z, long long* ix, long long* iy, long long* iz) {
+  const double ox = __dsub_rn(double(ordered_to_float(bounds[3 * f + 0])), __dmul_rn(g.cell[0], g.origin_off));
+  const double oy = __dsub_rn(double(ordered_to_float(bounds[3 * f + 1])), __dmul_rn(g.cell[1], g.origin_off));
+  const double oz = __dsub_rn(double(ordered_to_float(bounds[3 * f + 2])), __dmul_rn(g.cell[2], g.origin_off));
+  *ix = (long long)floor(__ddiv_rn(__dsub_rn(double(x), ox), g.cell[0]));
+  *iy = (long long)floor(__ddiv_rn(__dsub_rn(double(y), oy), g.cell[1]));
+  *iz = (long long)floor(__ddiv_rn(__dsub_rn(double(z), oz), g.cell[2]));
+}
+
+__global__ void point_keys_kernel(const float* __restrict__ xyz, const int32_t* __restrict__ frame_ptr,
+                                  int num_frames, int64_t n, GridSpec g,
+                                  const uint32_t* __restrict__ bounds, uint64_t* __restrict__ keys,
+                                  int32_t* __restrict__ vals, int* __restrict__ range_error) {
+  int64_t i = int64_t(blockIdx.x) * blockDim.x + threadIdx.x;
+  if (i >= n) return;
+  const int f = find_frame(frame_ptr, num_frames, i);
+  long long ix, iy, iz;
+  cell_of(g, bounds, f, xyz[3 * i], xyz[3 * i + 1], xyz[3 * i + 2], &ix, &iy, &iz);
+  if (ix < 0 || iy < 0 || iz < 0 || ix > kAxisMax || iy > kAxisMax || iz > kAxisMax) {
+    *range_error = 1;
+    ix = iy = iz = 0;
+  }
+  keys[i] = make_key(uint32_t(f), uint32_t(iz), uint32_t(iy), uint32_t(ix));
+  vals[i] = int32_t(i);
+}
+
+// sorted point record (coalesced candidate reads) + head flag of each run of equal keys
+__global__ void gather_sorted_kernel(const float* __restrict__ xyz, const uint64_t* __restrict__ keys,
+                                     const int32_t* __restrict__ order, int64_t n,
+                                     float4* __restrict__ sorted_pts, int32_t* __restrict__ head) {
+  int64_t i = int64_t(blockIdx.x) * blockDim.x + threadIdx.x;
+  if (i >= n) return;
+  const int32_t j = order[i];
+  sorted_pts[i] = make_float4(xyz[3 * j], xyz[3 * j + 1], xyz[3 * j + 2], __int_as_float(j));
+  head[i] = (i == 0 || keys[i] != keys[i - 1]) ? 1 : 0;
+}
+
+// cell table: cell_key[c], cell_start[c] for every non-empty cell c (ascending key)
+__global__ void cell_table_kernel(const uint64_t* __restrict__ keys, const int32_t* __restrict__ head_scan,
+                                  int64_t n, uint64_t* __restrict__ cell_key,
+                                  int32_t* __restrict__ cell_start) {
+  int64_t i = int64_t(blockIdx.x) * blockDim.x + threadIdx.x;
+  if (i >= n) return;
+  const int32_t c = head_scan[i] - 1;  // inclusive scan of head flags
+  const bool is_head = (i == 0) || (head_scan[i] != head_scan[i - 1]);
+  if (is_head) {
+    cell_key[c] = keys[i];
+    cell_start[c] = int32_t(i);
+  }
+  if (i == n - 1) cell_start[c + 1] = int32_t(n);
+}
+
+__device__ inline int lower_bound_u64(const uint64_t* __restrict__ a, int n, uint64_t v) {
+  int lo = 0, hi = n;
+  while (lo < hi) {
+    int mid = (lo + hi) >> 1;
+    if (a[mid] < v) lo = mid + 1; else hi = mid;
+  }
+  return lo;
+}
+
+struct SortedGrid {
+  const uint64_t* cell_key;   // [num_cells]
+  const int32_t* cell_start;  // [num_cells+1]
+  const float4* pts;          // [n] sorted (x,y,z,orig idx)
+  int num_cells;
+};
+
+// point range covering cells (f, iz, iy, ix_lo..ix_hi); indices already clamped to [0, kAxisMax]
+__device__ inline void row_range(const SortedGrid& g, uint32_t f, uint32_t iz, uint32_t iy, uint32_t ix_lo,
+                                 uint32_t ix_hi, int* begin, int* end) {
+  const int a = lower_bound_u64(g.cell_key, g.num_cells, make_key(f, iz, iy, ix_lo));
+  const int b = lower_bound_u64(g.cell_key, g.num_cells, make_key(f, iz, iy, ix_hi) + 1ull);
+  *begin = g.cell_start[a];
+  *end = g.cell_start[b];
+}
+
+__device__ inline double dist2_rn(double ax, double ay, double az, float bx, float by, float bz) {
+  const double dx = __dsub_rn(ax, double(bx));
+  const double dy = __dsub_rn(ay, double(by));
+  const double dz = __dsub_rn(az, double(bz));
+  return __dadd_rn(__dadd_rn(__dmul_rn(dx, dx), __dmul_rn(dy, dy)), __dmul_rn(dz, dz));
+}
+
+// ---- voxel keypoints: centroid (fp64, ascending point order) + exact nearest original point ----
+__global__ void voxel_keypoint_kernel(SortedGrid g, GridSpec spec, const uint32_t* __restrict__ bounds,
+                                      int32_t* __restrict__ out_idx) {
+  const int v = blockIdx.x * blockDim.x + threadIdx.x;
+  if (v >= g.num_cells) return;
+  const int s = g.cell_start[v], e = g.cell_start[v + 1];
+  double sx = 0.0, sy = 0.0, sz = 0.0;
+  for (int i = s; i < e; ++i) {  // sorted by (key, original index): ascending point order
+    const float4 p = g.pts[i];
+    sx = __dadd_rn(sx, double(p.x));
+    sy = __dadd_rn(sy, double(p.y));
+    sz = __dadd_rn(sz, double(p.z));
+  }
+  const double cnt = double(e - s);
+  const double cx = __ddiv_rn(sx, cnt), cy = __ddiv_rn(sy, cnt), cz = __ddiv_rn(sz, cnt);
+  // best candidate inside the own voxel
+  double best = DBL_MAX;
+  int best_idx = 0x7fffffff;
+  for (int i = s; i < e; ++i) {
+    const float4 p = g.pts[i];
+    const double d = dist2_rn(cx, cy, cz, p.x, p.y, p.z);
+    const int idx = __float_as_int(p.w);
+    if (d < best || (d == best && idx < best_idx)) { best = d; best_idx = idx; }
+  }
+  // every point closer than sqrt(best) lies in a cell overlapping the box centroid +- reach
+  const uint64_t key = g.cell_key[v];
+  const uint32_t f = uint32_t(key >> 48);
+  const double reach = sqrt(best) * (1.0 + 1e-9) + 1e-12;
+  const double ox = double(ordered_to_float(bounds[3 * f + 0])) - spec.cell[0] * spec.origin_off;
+  const double oy = double(ordered_to_float(bounds[3 * f + 1])) - spec.cell[1] * spec.origin_off;
+  const double oz = double(ordered_to_float(bounds[3 * f + 2])) - spec.cell[2] * spec.origin_off;
+  // reach is inflated by 1e-9 relative, far above the fp64 rounding of the corner cells
+  long long x0 = (long long)floor((cx - reach - ox) / spec.cell[0]), x1 = (long long)floor((cx + reach - ox) / spec.cell[0]);
+  long long y0 = (long long)floor((cy - reach - oy) / spec.cell[1]), y1 = (long long)floor((cy + reach - oy) / spec.cell[1]);
+  long long z0 = (long long)floor((cz - reach - oz) / spec.cell[2]), z1 = (long long)floor((cz + reach - oz) / spec.cell[2]);
+  x0 = max(x0, 0ll); y0 = max(y0, 0ll); z0 = max(z0, 0ll);
+  x1 = min(x1, (long long)kAxisMax); y1 = min(y1, (long long)kAxisMax); z1 = min(z1, (long long)kAxisMax);
+  for (long long iz = z0; iz <= z1; ++iz) {
+    for (long long iy = y0; iy <= y1; ++iy) {
+      int b, en;
+      row_range(g, f, uint32_t(iz), uint32_t(iy), uint32_t(x0), uint32_t(x1), &b, &en);
+      for (int i = b; i < en; ++i) {
+        const float4 p = g.pts[i];
+        const double d = dist2_rn(cx, cy, cz, p.x, p.y, p.z);
+        const int idx = __float_as_int(p.w);
+        if (d < best || (d == best && idx < best_idx)) { best = d; best_idx = idx; }
+      }
+    }
+  }
+  out_idx[v] = best_idx;
+}
+
+__global__ void frame_ranges_kernel(const uint64_t* __restrict__ cell_key, int num_cells, int num_frames,
+                                    int32_t* __restrict__ out_frame_ptr) {
+  const int f = blockIdx.x * blockDim.x + threadIdx.x;
+  if (f > num_frames) return;
+  out_frame_ptr[f] = lower_bound_u64(cell_key, num_cells, uint64_t(f) << 48);
+}
+
+// ---- radius graph ----------------------------------------------------------------------------
+struct CenterCell {
+  uint32_t f;
+  long long ix, iy, iz;
+};
+
+// One warp per centre.  kFill=false: count neighbours.  kFill=true: write source indices at
+// row_ptr[c] + rank (rank from a warp ballot prefix, traversal order; rows are sorted afterwards).
+template <bool kFill>
+__global__ void __launch_bounds__(256) radius_query_kernel(
+    SortedGrid g, GridSpec spec, const uint32_t* __restrict__ bounds, const float* __restrict__ centers,
+    const int32_t* __restrict__ center_frame_ptr, int num_frames, int64_t num_centers, double r2,
+    int32_t* __restrict__ counts, const int32_t* __restrict__ row_ptr, int32_t* __restrict__ out_src) {
+  const int lane = threadIdx.x & 31;
+  const int64_t c = (int64_t(blockIdx.x) * blockDim.x + threadIdx.x) >> 5;
+  if (c >= num_centers) return;
+  const int f = find_frame(center_frame_ptr, num_frames, c);
+  const float cxf = centers[3 * c], cyf = centers[3 * c + 1], czf = centers[3 * c + 2];
+  const double cx = double(cxf), cy = double(cyf), cz = double(czf);
+  long long ix, iy, iz;
+  cell_of(spec, bounds, f, cxf, cyf, czf, &ix, &iy, &iz);
+  const long long x0 = max(ix - 1, 0ll), x1 = min(ix + 1, (long long)kAxisMax);
+  int total = 0;
+  int base = kFill ? row_ptr[c] : 0;
+  if (x0 <= x1) {
+    for (long long zz = iz - 1; zz <= iz + 1; ++zz) {
+      if (zz < 0 || zz > kAxisMax) continue;
+      for (long long yy = iy - 1; yy <= iy + 1; ++yy) {
+        if (yy < 0 || yy > kAxisMax) continue;
+        int b, e;
+        row_range(g, uint32_t(f), uint32_t(zz), uint32_t(yy), uint32_t(x0), uint32_t(x1), &b, &e);
+        for (int i0 = b; i0 < e; i0 += 32) {
+          const int i = i0 + lane;
+          bool hit = false;
+          int idx = 0;
+          if (i < e) {
+            const float4 p = g.pts[i];
+            hit = dist2_rn(cx, cy, cz, p.x, p.y, p.z) <= r2;
+            idx = __float_as_int(p.w);
+          }
+          const uint32_t m = __ballot_sync(0xffffffffu, hit);
+          if (kFill && hit) out_src[base + total + __popc(m & ((1u << lane) - 1u))] = idx;
+          total += __popc(m);
+        }
+      }
+    }
+  }
+  if (!kFill && lane == 0) counts[c] = total;
+}
+
+// Sort every CSR row ascending (canonical order) and expand the destination index.
+// Bitonic network in its "all comparators ascending" form (flip stage i^(k-1), then half-cleaners
+// i^j): with every comparator ascending, virtual +inf padding at the tail never moves, so rows of
+// any length sort in place.
+constexpr int kRowSortMax = 8192;
+__global__ void __launch_bounds__(256) sort_rows_kernel(const int32_t* __restrict__ row_ptr, int64_t num_rows,
+                                                         int32_t* __restrict__ src, int32_t* __restrict__ dst) {
+  extern __shared__ int32_t srow[];
+  for (int64_t r = blockIdx.x; r < num_rows; r += gridDim.x) {
+    const int b = row_ptr[r], e = row_ptr[r + 1];
+    const int len = e - b;
+    if (dst != nullptr)
+      for (int i = threadIdx.x; i < len; i += blockDim.x) dst[b + i] = int32_t(r);
+    if (len <= 1) continue;
+    int n = 1;
+    while (n < len) n <<= 1;
+    const bool in_smem = len <= kRowSortMax;
+    int32_t* a = in_smem ? srow : src + b;
+    if (in_smem) {
+      for (int i = threadIdx.x; i < len; i += blockDim.x) srow[i] = src[b + i];
+    }
+    __syncthreads();
+    for (int k = 2; k <= n; k <<= 1) {
+      for (int j = k >> 1; j > 0; j >>= 1) {
+        const bool flip = (j == (k >> 1));
+        for (int i = threadIdx.x; i < len; i += blockDim.x) {
+          const int p = flip ? (i ^ (k - 1)) : (i ^ j);
+          if (p > i && p < len) {
+            const int x = a[i], y = a[p];
+            if (x > y) { a[i] = y; a[p] = x; }
+          }
+        }
+        __syncthreads();
+      }
+    }
+    if (in_smem) {
+      for (int i = threadIdx.x; i < len; i += blockDim.x) src[b + i] = srow[i];
+    }
+    __syncthreads();
+  }
+}
+
+// ---- host-side building blocks ----------------------------------------------------------------
+struct BuiltGrid {
+  Temp bounds, keys_a, keys_b, vals_a, vals_b, sorted_pts, head, head_scan, cell_key, cell_start, cub_tmp, err;
+  int num_cells = 0;
+  SortedGrid view{};
+};
+
+int build_grid(const float* xyz, const int32_t* frame_ptr, int num_frames, int64_t n, const GridSpec& spec,
+               cudaStream_t s, BuiltGrid* out) {
+  PG_REQUIRE(num_frames >= 1 && num_frames <= 65535, "num_frames=%d out of range [1,65535]", num_frames);
+  PG_REQUIRE(n >= 1 && n < (int64_t(1) << 31), "num_points=%lld out of range", (long long)n);
+  PG_CUDA_OK(out->bounds.alloc(sizeof(uint32_t) * 3 * num_frames, s));
+  PG_CUDA_OK(out->keys_a.alloc(sizeof(uint64_t) * n, s));
+  PG_CUDA_OK(out->keys_b.alloc(sizeof(uint64_t) * n, s));
+  PG_CUDA_OK(out->vals_a.alloc(sizeof(int32_t) * n, s));
+  PG_CUDA_OK(out->vals_b.alloc(sizeof(int32_t) * n, s));
+  PG_CUDA_OK(out->sorted_pts.alloc(sizeof(float4) * n, s));
+  PG_CUDA_OK(out->head.alloc(sizeof(int32_t) * n, s));
+  PG_CUDA_OK(out->head_scan.alloc(sizeof(int32_t) * n, s));
+  PG_CUDA_OK(out->cell_key.alloc(sizeof(uint64_t) * n, s));
+  PG_CUDA_OK(out->cell_start.alloc(sizeof(int32_t) * (n + 1), s));
+  PG_CUDA_OK(out->err.alloc(sizeof(int), s));
+  PG_CUDA_OK(cudaMemsetAsync(out->err.ptr, 0, sizeof(int), s));
+
+  uint32_t* bounds = out->bounds.as<uint32_t>();
+  init_bounds_kernel<<<ceil_div(3 * num_frames, 256), 256, 0, s>>>(bounds, 3 * num_frames);
+  PG_LAUNCH_CHECK();
+  const int blocks_per_frame = int(std::min<int64_t>(std::max<int64_t>(1, ceil_div(n / num_frames, 1024)), 64));
+  frame_min_kernel<<<dim3(blocks_per_frame, num_frames), 256, 0, s>>>(xyz, frame_ptr, bounds);
+  PG_LAUNCH_CHECK();
+  point_keys_kernel<<<ceil_div(n, 256), 256, 0, s>>>(xyz, frame_ptr, num_frames, n, spec, bounds,
+                                                      out->keys_a.as<uint64_t>(), out->vals_a.as<int32_t>(),
+                                                      out->err.as<int>());
+  PG_LAUNCH_CHECK();
+  // radix sort (key, original index); stable, so equal keys keep ascending point index
+  int frame_bits = 1;
+  while ((1 << frame_bits) < num_frames) ++frame_bits;
+  const int end_bit = 48 + frame_bits;
+  size_t tmp_bytes = 0;
+  PG_CUDA_OK(cub::DeviceRadixSort::SortPairs(nullptr, tmp_bytes, out->keys_a.as<uint64_t>(), out->keys_b.as<uint64_t>(),
+                                             out->vals_a.as<int32_t>(), out->vals_b.as<int32_t>(), int(n), 0, end_bit, s));
+  size_t scan_bytes = 0;
+  PG_CUDA_OK(cub::DeviceScan::InclusiveSum(nullptr, scan_bytes, out->head.as<int32_t>(), out->head_scan.as<int32_t>(), int(n), s));
+  PG_CUDA_OK(out->cub_tmp.alloc(std::max(tmp_bytes, scan_bytes), s));
+  PG_CUDA_OK(cub::DeviceRadixSort::SortPairs(out->cub_tmp.ptr, tmp_bytes, out->keys_a.as<uint64_t>(), out->keys_b.as<uint64_t>(),
+                                             out->vals_a.as<int32_t>(), out->vals_b.as<int32_t>(), int(n), 0, end_bit, s));
+  count_launch(4);
+  gather_sorted_kernel<<<ceil_div(n, 256), 256, 0, s>>>(xyz, out->keys_b.as<uint64_t>(), out->vals_b.as<int32_t>(), n,
+                                                         out->sorted_pts.as<float4>(), out->head.as<int32_t>());
+  PG_LAUNCH_CHECK();
+  PG_CUDA_OK(cub::DeviceScan::InclusiveSum(out->cub_tmp.ptr, scan_bytes, out->head.as<int32_t>(), out->head_scan.as<int32_t>(), int(n), s));
+  count_launch(2);
+  cell_table_kernel<<<ceil_div(n, 256), 256, 0, s>>>(out->keys_b.as<uint64_t>(), out->head_scan.as<int32_t>(), n,
+                                                      out->cell_key.as<uint64_t>(), out->cell_start.as<int32_t>());
+  PG_LAUNCH_CHECK();
+  int h_cells = 0, h_err = 0;
+  PG_CUDA_OK(cudaMemcpyAsync(&h_cells, out->head_scan.as<int32_t>() + (n - 1), sizeof(int), cudaMemcpyDeviceToHost, s));
+  PG_CUDA_OK(cudaMemcpyAsync(&h_err, out->err.ptr, sizeof(int), cudaMemcpyDeviceToHost, s));
+  PG_CUDA_OK(cudaStreamSynchronize(s));
+  if (h_err) {
+    set_error("point cloud extent exceeds %d grid cells per axis", kAxisMax + 1);
+    return PG_ERR_RANGE;
+  }
+  out->num_cells = h_cells;
+  out->view.cell_key = out->cell_key.as<uint64_t>();
+  out->view.cell_start = out->cell_start.as<int32_t>();
+  out->view.pts = out->sorted_pts.as<float4>();
+  out->view.num_cells = h_cells;
+  return PG_OK;
+}
+
+int check_frames_host(const int32_t* frame_ptr_dev, int num_frames, int64_t n, cudaStream_t s, const char* what) {
+  // cheap sanity check of the caller's frame_ptr (first/last entries)
+  int32_t ends[2] = {0, 0};
+  PG_CUDA_OK(cudaMemcpyAsync(&ends[0], frame_ptr_dev, sizeof(int32_t), cudaMemcpyDeviceToHost, s));
+  PG_CUDA_OK(cudaMemcpyAsync(&ends[1], frame_ptr_dev + num_frames, sizeof(int32_t), cudaMemcpyDeviceToHost, s));
+  PG_CUDA_OK(cudaStreamSynchronize(s));
+  PG_REQUIRE(ends[0] == 0 && ends[1] == n, "%s frame_ptr must run from 0 to %lld (got %d..%d)", what,
+             (long long)n, ends[0], ends[1]);
+  return PG_OK;
+}
+
+struct RadiusPlan {
+  BuiltGrid grid;
+  GridSpec spec;
+  double r2;
+};
+
+int radius_prepare(const float* points, const int32_t* point_frame_ptr, int num_frames, int64_t num_points,
+                   double radius, cudaStream_t s, RadiusPlan* plan) {
+  PG_REQUIRE(radius > 0.0, "radius must be positive");
+  plan->spec.cell[0] = plan->spec.cell[1] = plan->spec.cell[2] = radius * kCellSlack;
+  plan->spec.origin_off = 0.0;
+  plan->r2 = radius * radius;
+  return build_grid(points, point_frame_ptr, num_frames, num_points, plan->spec, s, &plan->grid);
+}
+
+}  // namespace
+}  // namespace pg
+
+using namespace pg;
+
+extern "C" int pg_voxel_keypoints(const float* xyz, const int32_t* frame_ptr, int32_t num_frames, int64_t num_points,
+                                  const double* voxel_size_host, int32_t* out_keypoint_idx, int64_t capacity,
+                                  int32_t* out_kp_frame_ptr, int64_t* out_num_keypoints_host, void* stream) {
+  cudaStream_t s = static_cast<cudaStream_t>(stream);
+  PG_REQUIRE(xyz && frame_ptr && voxel_size_host && out_keypoint_idx && out_kp_frame_ptr && out_num_keypoints_host,
+             "pg_voxel_keypoints: null argument");
+  PG_REQUIRE(voxel_size_host[0] > 0 && voxel_size_host[1] > 0 && voxel_size_host[2] > 0, "voxel size must be positive");
+  if (int rc = check_frames_host(frame_ptr, num_frames, num_points, s, "point")) return rc;
+  GridSpec spec;
+  spec.cell[0] = voxel_size_host[0];
+  spec.cell[1] = voxel_size_host[1];
+  spec.cell[2] = voxel_size_host[2];
+  spec.origin_off = 0.5;  // Open3D: voxel_min_bound = min_bound - voxel_size * 0.5
+  BuiltGrid grid;
+  if (int rc = build_grid(xyz, frame_ptr, num_frames, num_points, spec, s, &grid)) return rc;
+  *out_num_keypoints_host = grid.num_cells;
+  if (grid.num_cells > capacity) {
+    set_error("keypoint buffer too small: need %d, capacity %lld", grid.num_cells, (long long)capacity);
+    return PG_ERR_CAPACITY;
+  }
+  voxel_keypoint_kernel<<<ceil_div(grid.num_cells, 128), 128, 0, s>>>(grid.view, spec, grid.bounds.as<uint32_t>(),
+                                                                        out_keypoint_idx);
+  PG_LAUNCH_CHECK();
+  frame_ranges_kernel<<<ceil_div(num_frames + 1, 128), 128, 0, s>>>(grid.view.cell_key, grid.num_cells, num_frames,
+                                                                     out_kp_frame_ptr);
+  PG_LAUNCH_CHECK();
+  PG_CUDA_OK(cudaStreamSynchronize(s));
+  return PG_OK;
+}
+
+static int radius_count_impl(RadiusPlan& plan, const float* centers, const int32_t* center_frame_ptr, int num_frames,
+                             int64_t num_centers, int32_t* out_row_ptr, int64_t* out_num_edges_host, cudaStream_t s) {
+  Temp counts, tmp;
+  PG_CUDA_OK(counts.alloc(sizeof(int32_t) * (num_centers + 1), s));
+  PG_CUDA_OK(cudaMemsetAsync(counts.ptr, 0, sizeof(int32_t) * (num_centers + 1), s));
+  radius_query_kernel<false><<<ceil_div(num_centers * 32, 256), 256, 0, s>>>(
+      plan.grid.view, plan.spec, plan.grid.bounds.as<uint32_t>(), centers, center_frame_ptr, num_frames, num_centers,
+      plan.r2, counts.as<int32_t>(), nullptr, nullptr);
+  PG_LAUNCH_CHECK();
+  size_t bytes = 0;
+  PG_CUDA_OK(cub::DeviceScan::ExclusiveSum(nullptr, bytes, counts.as<int32_t>(), out_row_ptr, int(num_centers + 1), s));
+  PG_CUDA_OK(tmp.alloc(bytes, s));
+  PG_CUDA_OK(cub::DeviceScan::ExclusiveSum(tmp.ptr, bytes, counts.as<int32_t>(), out_row_ptr, int(num_centers + 1), s));
+  count_launch(2);
+  int32_t e = 0;
+  PG_CUDA_OK(cudaMemcpyAsync(&e, out_row_ptr + num_centers, sizeof(int32_t), cudaMemcpyDeviceToHost, s));
+  PG_CUDA_OK(cudaStreamSynchronize(s));
+  *out_num_edges_host = e;
+  return PG_OK;
+}
+
+static int radius_fill_impl(RadiusPlan& plan, const float* centers, const int32_t* center_frame_ptr, int num_frames,
+                            int64_t num_centers, const int32_t* row_ptr, int32_t* out_src, int32_t* out_dst,
+                            cudaStream_t s) {
+  radius_query_kernel<true><<<ceil_div(num_centers * 32, 256), 256, 0, s>>>(
+      plan.grid.view, plan.spec, plan.grid.bounds.as<uint32_t>(), centers, center_frame_ptr, num_frames, num_centers,
+      plan.r2, nullptr, row_ptr, out_src);
+  PG_LAUNCH_CHECK();
+  const int blocks = int(std::min<int64_t>(num_centers, int64_t(num_sms()) * 16));
+  sort_rows_kernel<<<blocks, 256, kRowSortMax * sizeof(int32_t), s>>>(row_ptr, num_centers, out_src, out_dst);
+  PG_LAUNCH_CHECK();
+  return PG_OK;
+}
+
+extern "C" int pg_radius_graph_count(const float* points, const int32_t* point_frame_ptr, const float* centers,
+                                     const int32_t* center_frame_ptr, int32_t num_frames, int64_t num_points,
+                                     int64_t num_centers, double radius, int32_t* out_row_ptr,
+                                     int64_t* out_num_edges_host, void* stream) {
+  cudaStream_t s = static_cast<cudaStream_t>(stream);
+  PG_REQUIRE(points && point_frame_ptr && centers && center_frame_ptr && out_row_ptr && out_num_edges_host,
+             "pg_radius_graph_count: null argument");
+  PG_REQUIRE(num_centers >= 1 && num_centers < (int64_t(1) << 31) - 1, "num_centers out of range");
+  if (int rc = check_frames_host(point_frame_ptr, num_frames, num_points, s, "point")) return rc;
+  if (int rc = check_frames_host(center_frame_ptr, num_frames, num_centers, s, "center")) return rc;
+  RadiusPlan plan;
+  if (int rc = radius_prepare(points, point_frame_ptr, num_frames, num_points, radius, s, &plan)) return rc;
+  return radius_count_impl(plan, centers, center_frame_ptr, num_frames, num_centers, out_row_ptr, out_num_edges_host, s);
+}
+
+extern "C" int pg_radius_graph_fill(const float* points, const int32_t* point_frame_ptr, const float* centers,
+                                    const int32_t* center_frame_ptr, int32_t num_frames, int64_t num_points,
+                                    int64_t num_centers, double radius, const int32_t* row_ptr, int64_t num_edges,
+                                    int32_t* out_src, int32_t* out_dst, void* stream) {
+  cudaStream_t s = static_cast<cudaStream_t>(stream);
+  PG_REQUIRE(points && point_frame_ptr && centers && center_frame_ptr && row_ptr && (out_src || num_edges == 0),
+             "pg_radius_graph_fill: null argument");
+  if (num_edges == 0) return PG_OK;
+  RadiusPlan plan;
+  if (int rc = radius_prepare(points, point_frame_ptr, num_frames, num_points, radius, s, &plan)) return rc;
+  return radius_fill_impl(plan, centers, center_frame_ptr, num_frames, num_centers, row_ptr, out_src, out_dst, s);
+}
+
+extern "C" int pg_radius_graph(const float* points, const int32_t* point_frame_ptr, const float* centers,
+                               const int32_t* center_frame_ptr, int32_t num_frames, int64_t num_points,
+                               int64_t num_centers, double radius, int32_t* out_row_ptr, int32_t* out_src,
+                               int32_t* out_dst, int64_t capacity, int64_t* out_num_edges_host, void* stream) {
+  cudaStream_t s = static_cast<cudaStream_t>(stream);
+  PG_REQUIRE(points && point_frame_ptr && centers && center_frame_ptr && out_row_ptr && out_num_edges_host,
+             "pg_radius_graph: null argument");
+  PG_REQUIRE(num_centers >= 1 && num_centers < (int64_t(1) << 31) - 1, "num_centers out of range");
+  if (int rc = check_frames_host(point_frame_ptr, num_frames, num_points, s, "point")) return rc;
+  if (int rc = check_frames_host(center_frame_ptr, num_frames, num_centers, s, "center")) return rc;
+  RadiusPlan plan;
+  if (int rc = radius_prepare(points, point_frame_ptr, num_frames, num_points, radius, s, &plan)) return rc;
+  if (int rc = radius_count_impl(plan, centers, center_frame_ptr, num_frames, num_centers, out_row_ptr,
+                                 out_num_edges_host, s))
+    return rc;
+  if (*out_num_edges_host > capacity) {
+    set_error("edge buffer too small: need %lld, capacity %lld", (long long)*out_num_edges_host, (long long)capacity);
+    return PG_ERR_CAPACITY;
+  }
+  if (*out_num_edges_host == 0) return PG_OK;
+  PG_REQUIRE(out_src != nullptr, "pg_radius_graph: out_src is null");
+  return radius_fill_impl(plan, centers, center_frame_ptr, num_frames, num_centers, out_row_ptr, out_src, out_dst, s);
+}

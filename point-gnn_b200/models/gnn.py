@@ -1,0 +1,314 @@
+"""GNN layers and ops - same classes / functions / argument lists as the reference's
+``models/gnn.py`` (/root/reference/models/gnn.py), executing on hand-written sm_100a kernels.
+
+The reference builds a TF-1 graph whose variables are created by ``slim.fully_connected``
+inside nested ``tf.variable_scope``s; here the same scoping is reproduced eagerly so that the
+reference's checkpoints load by variable name: ``variable_scope(name)`` pushes a scope,
+every fully-connected layer draws the next ``fully_connected[_i]`` name of its scope, and
+weights are looked up in the active ``VariableStore`` (name -> CUDA tensor).
+
+When a layer is built from the default plugins (``multi_layer_neural_network_fn`` +
+``graph_scatter_max_fn``, i.e. every layer type models.py:49-74 registers) its gather /
+concat / edge-MLP / segment-max chain runs as ONE fused kernel (``pg_edge_mlp_max``); any
+other plugin combination runs the same chain op by op, still on the GPU.
+"""
+import contextlib
+import threading
+from functools import partial  # noqa: F401  (re-exported for config code written against the reference)
+
+import torch
+
+from .. import _lib
+from .. import get_precision
+
+_PG_EDGE_POOL = 0
+_PG_EDGE_GNN = 1
+
+
+# ---------------------------------------------------------------------------------------------
+# variable scoping (stand-in for tf.variable_scope + slim's layer naming)
+# ---------------------------------------------------------------------------------------------
+class VariableStore(object):
+    """name -> CUDA tensor, e.g. 'layer2/extract_vertex_features/fully_connected_1/weights'."""
+
+    def __init__(self, variables=None, device=None):
+        self.vars = {}
+        if variables:
+            self.load(variables, device)
+
+    def load(self, variables, device=None):
+        device = device or torch.device('cuda', torch.cuda.current_device())
+        for name, value in variables.items():
+            if not (name.endswith('/weights') or name.endswith('/biases')):
+                continue
+            t = torch.as_tensor(value)
+            if t.dtype != torch.float32:
+                continue
+            self.vars[name] = t.to(device).contiguous()
+
+    def get(self, name):
+        if name not in self.vars:
+            raise KeyError('variable %r not found in the checkpoint' % name)   # TF: NotFoundError
+        return self.vars[name]
+
+
+class _Ctx(threading.local):
+    def __init__(self):
+        self.store = None
+        self.scope = []
+        self.counters = {}
+
+
+_ctx = _Ctx()
+
+
+@contextlib.contextmanager
+def variable_session(store):
+    """One model build: binds the weight store and resets slim's per-scope layer counters."""
+    prev = (_ctx.store, _ctx.scope, _ctx.counters)
+    _ctx.store, _ctx.scope, _ctx.counters = store, [], {}
+    try:
+        yield store
+    finally:
+        _ctx.store, _ctx.scope, _ctx.counters = prev
+
+
+@contextlib.contextmanager
+def variable_scope(name):
+    _ctx.scope.append(name)
+    try:
+        yield
+    finally:
+        _ctx.scope.pop()
+
+
+def _next_fully_connected():
+    if _ctx.store is None:
+        raise RuntimeError('no VariableStore bound: call inside model.predict / variable_session')
+    scope = '/'.join(_ctx.scope)
+    i = _ctx.counters.get(scope, 0)
+    _ctx.counters[scope] = i + 1
+    base = (scope + '/' if scope else '') + ('fully_connected' if i == 0 else 'fully_connected_%d' % i)
+    return _ctx.store.get(base + '/weights'), _ctx.store.get(base + '/biases')
+
+
+# the reference's tables (gnn.py:17-32); only the entries its shipped configs use are executable
+normalization_fn_dict = {'fused_BN_center': 'fused_BN_center', 'BN': 'BN', 'BN_center': 'BN_center',
+                         'IN': 'IN', 'NONE': None}
+activation_fn_dict = {'ReLU': 'ReLU', 'ReLU6': 'ReLU6', 'LeakyReLU': 'LeakyReLU', 'ELU': 'ELU',
+                      'NONE': None, 'Sigmoid': 'Sigmoid', 'Tanh': 'Tanh'}
+
+
+def _check_types(normalization_type, activation_type):
+    if normalization_fn_dict[normalization_type] is not None:
+        raise NotImplementedError('normalization %r: every shipped config uses "NONE" '
+                                  '(SURVEY fact 3); batch/instance norm are not built' % normalization_type)
+    if activation_fn_dict[activation_type] not in ('ReLU',):
+        raise NotImplementedError('activation %r: every shipped config uses "ReLU"' % activation_type)
+
+
+def _fully_connected(features, relu, residual=None):
+    w, b = _next_fully_connected()
+    return _lib.fully_connected(features, w, b, relu, residual=residual, precision=get_precision())
+
+
+def multi_layer_fc_fn(sv, mask=None, Ks=(64, 32, 64), num_classes=4, is_logits=False, num_layer=4,
+                      normalization_type="fused_BN_center", activation_type='ReLU'):
+    """gnn.py:34-84."""
+    assert len(sv.shape) == 2
+    assert len(Ks) == num_layer - 1
+    _check_types(normalization_type, activation_type)
+    features = sv
+    for i in range(num_layer - 1):
+        features = _fully_connected(features, relu=True)
+        assert features.shape[1] == Ks[i]
+    features = _fully_connected(features, relu=not is_logits)
+    assert features.shape[1] == num_classes
+    if mask is not None:
+        features = features * mask
+    return features
+
+
+def multi_layer_neural_network_fn(features, Ks=(64, 32, 64), is_logits=False,
+                                  normalization_type="fused_BN_center", activation_type='ReLU',
+                                  residual=None):
+    """gnn.py:86-104.  ``residual`` (extension): added to the last layer's output in-kernel."""
+    assert len(features.shape) == 2
+    _check_types(normalization_type, activation_type)
+    for i in range(len(Ks)):
+        last = i == len(Ks) - 1
+        features = _fully_connected(features, relu=not (is_logits and last),
+                                    residual=residual if last else None)
+        assert features.shape[1] == Ks[i]
+    return features
+
+
+def _take_mlp_weights(num_layers):
+    ws, bs = [], []
+    for _ in range(num_layers):
+        w, b = _next_fully_connected()
+        ws.append(w)
+        bs.append(b)
+    return ws, bs
+
+
+def graph_scatter_max_fn(point_features, point_centers, num_centers):
+    """gnn.py:106-109 (tf.math.unsorted_segment_max; empty segment -> float lowest)."""
+    centers = point_centers.reshape(-1).to(torch.int32).contiguous()
+    return _lib.scatter_max(point_features.contiguous(), centers, int(num_centers))
+
+
+def graph_scatter_sum_fn(point_features, point_centers, num_centers):
+    """gnn.py:111-114 - not used by any shipped config."""
+    raise NotImplementedError('scatter_sum aggregation is unused by the shipped configs')
+
+
+def graph_scatter_mean_fn(point_features, point_centers, num_centers):
+    """gnn.py:116-119 - not used by any shipped config."""
+    raise NotImplementedError('scatter_mean aggregation is unused by the shipped configs')
+
+
+def _i32(t):
+    return t.to(torch.int32).contiguous() if (t.dtype != torch.int32 or not t.is_contiguous()) else t
+
+
+class ClassAwarePredictor(object):
+    """gnn.py:121-163."""
+
+    def __init__(self, cls_fn, loc_fn):
+        self._cls_fn = cls_fn
+        self._loc_fn = loc_fn
+
+    def apply_regular(self, features, num_classes, box_encoding_len,
+                      normalization_type='fused_BN_center', activation_type='ReLU'):
+        box_encodings_list = []
+        with variable_scope('predictor'):
+            with variable_scope('cls'):
+                logits = self._cls_fn(features, num_classes=num_classes, is_logits=True,
+                                      normalization_type=normalization_type,
+                                      activation_type=activation_type)
+            with variable_scope('loc'):
+                for class_idx in range(num_classes):
+                    with variable_scope('cls_%d' % class_idx):
+                        box_encodings = self._loc_fn(features, num_classes=box_encoding_len, is_logits=True,
+                                                     normalization_type=normalization_type,
+                                                     activation_type=activation_type)
+                        box_encodings_list.append(box_encodings.unsqueeze(1))
+            box_encodings = torch.cat(box_encodings_list, dim=1)
+        return logits, box_encodings
+
+
+class PointSetPooling(object):
+    """gnn.py:211-283."""
+
+    def __init__(self, point_feature_fn=multi_layer_neural_network_fn,
+                 aggregation_fn=graph_scatter_max_fn, output_fn=multi_layer_neural_network_fn):
+        self._point_feature_fn = point_feature_fn
+        self._aggregation_fn = aggregation_fn
+        self._output_fn = output_fn
+
+    def _fusable(self, normalization_type, activation_type):
+        return (self._point_feature_fn is multi_layer_neural_network_fn
+                and self._aggregation_fn is graph_scatter_max_fn
+                and normalization_type == 'NONE' and activation_type == 'ReLU')
+
+    def apply_regular(self, point_features, point_coordinates, keypoint_indices, set_indices,
+                      point_MLP_depth_list=None, point_MLP_normalization_type='fused_BN_center',
+                      point_MLP_activation_type='ReLU', output_MLP_depth_list=None,
+                      output_MLP_normalization_type='fused_BN_center', output_MLP_activation_type='ReLU'):
+        num_keypoints = keypoint_indices.shape[0]
+        src, dst = set_indices[:, 0], set_indices[:, 1]
+        with variable_scope('extract_vertex_features'):
+            if self._fusable(point_MLP_normalization_type, point_MLP_activation_type):
+                ws, bs = _take_mlp_weights(len(point_MLP_depth_list))
+                set_features = _lib.edge_mlp_max(
+                    _PG_EDGE_POOL, point_features.contiguous(), point_coordinates.contiguous(),
+                    point_coordinates.contiguous(), _i32(keypoint_indices.reshape(-1)), _i32(src), _i32(dst),
+                    num_keypoints, ws, bs, precision=get_precision())
+            else:
+                # op-by-op composition, gnn.py:256-277
+                psf = _lib.gather_rows(point_features.contiguous(), _i32(src))
+                psc = _lib.gather_rows(point_coordinates.contiguous(), _i32(src))
+                kidx = _i32(keypoint_indices.reshape(-1))[dst.long()]
+                kc = _lib.gather_rows(point_coordinates.contiguous(), _i32(kidx))
+                x = torch.cat([psf, psc - kc], dim=-1).contiguous()
+                x = self._point_feature_fn(x, Ks=point_MLP_depth_list, is_logits=False,
+                                           normalization_type=point_MLP_normalization_type,
+                                           activation_type=point_MLP_activation_type)
+                set_features = self._aggregation_fn(x, dst, num_keypoints)
+        with variable_scope('combined_features'):
+            set_features = self._output_fn(set_features, Ks=output_MLP_depth_list, is_logits=False,
+                                           normalization_type=output_MLP_normalization_type,
+                                           activation_type=output_MLP_activation_type)
+        return set_features
+
+
+class GraphNetAutoCenter(object):
+    """gnn.py:285-373."""
+
+    def __init__(self, edge_feature_fn=multi_layer_neural_network_fn, aggregation_fn=graph_scatter_max_fn,
+                 update_fn=multi_layer_neural_network_fn, auto_offset_fn=multi_layer_neural_network_fn):
+        self._edge_feature_fn = edge_feature_fn
+        self._aggregation_fn = aggregation_fn
+        self._update_fn = update_fn
+        self._auto_offset_fn = auto_offset_fn
+
+    def _fusable(self, normalization_type, activation_type):
+        return (self._edge_feature_fn is multi_layer_neural_network_fn
+                and self._aggregation_fn is graph_scatter_max_fn
+                and normalization_type == 'NONE' and activation_type == 'ReLU')
+
+    def apply_regular(self, input_vertex_features, input_vertex_coordinates, NOT_USED, edges,
+                      edge_MLP_depth_list=None, edge_MLP_normalization_type='fused_BN_center',
+                      edge_MLP_activation_type='ReLU', update_MLP_depth_list=None,
+                      update_MLP_normalization_type='fused_BN_center', update_MLP_activation_type='ReLU',
+                      auto_offset=False, auto_offset_MLP_depth_list=None,
+                      auto_offset_MLP_normalization_type='fused_BN_center',
+                      auto_offset_MLP_feature_activation_type='ReLU'):
+        num_vertices = input_vertex_features.shape[0]
+        src, dst = edges[:, 0], edges[:, 1]
+        source_coordinates = input_vertex_coordinates.contiguous()          # gnn.py:339: un-offset
+        dest_coordinates = source_coordinates
+        if auto_offset:                                                     # gnn.py:341-346
+            if self._auto_offset_fn is multi_layer_neural_network_fn:
+                dest_coordinates = self._auto_offset_fn(
+                    input_vertex_features, Ks=auto_offset_MLP_depth_list, is_logits=True,
+                    normalization_type=auto_offset_MLP_normalization_type,
+                    activation_type=auto_offset_MLP_feature_activation_type,
+                    residual=source_coordinates)                            # coords + offset, fused
+            else:
+                offset = self._auto_offset_fn(
+                    input_vertex_features, Ks=auto_offset_MLP_depth_list, is_logits=True,
+                    normalization_type=auto_offset_MLP_normalization_type,
+                    activation_type=auto_offset_MLP_feature_activation_type)
+                dest_coordinates = (source_coordinates + offset).contiguous()
+        with variable_scope('extract_vertex_features'):
+            if self._fusable(edge_MLP_normalization_type, edge_MLP_activation_type):
+                ws, bs = _take_mlp_weights(len(edge_MLP_depth_list))
+                aggregated_edge_features = _lib.edge_mlp_max(
+                    _PG_EDGE_GNN, input_vertex_features.contiguous(), source_coordinates, dest_coordinates,
+                    None, _i32(src), _i32(dst), num_vertices, ws, bs, precision=get_precision())
+            else:
+                # op-by-op composition, gnn.py:338-365
+                s_feat = _lib.gather_rows(input_vertex_features.contiguous(), _i32(src))
+                s_coord = _lib.gather_rows(source_coordinates, _i32(src))
+                d_coord = _lib.gather_rows(dest_coordinates, _i32(dst))
+                x = torch.cat([s_feat, s_coord - d_coord], dim=-1).contiguous()
+                x = self._edge_feature_fn(x, Ks=edge_MLP_depth_list, is_logits=False,
+                                          normalization_type=edge_MLP_normalization_type,
+                                          activation_type=edge_MLP_activation_type)
+                aggregated_edge_features = self._aggregation_fn(x, dst, num_vertices)
+        with variable_scope('combined_features'):
+            if self._update_fn is multi_layer_neural_network_fn:
+                output_vertex_features = self._update_fn(
+                    aggregated_edge_features, Ks=update_MLP_depth_list, is_logits=True,
+                    normalization_type=update_MLP_normalization_type,
+                    activation_type=update_MLP_activation_type,
+                    residual=input_vertex_features.contiguous())            # gnn.py:372, fused
+            else:
+                update_features = self._update_fn(
+                    aggregated_edge_features, Ks=update_MLP_depth_list, is_logits=True,
+                    normalization_type=update_MLP_normalization_type,
+                    activation_type=update_MLP_activation_type)
+                output_vertex_features = update_features + input_vertex_features
+        return output_vertex_features

@@ -1,0 +1,160 @@
+"""Graph generation on the GPU - same names / signatures / return layout as the reference's
+``models/graph_gen.py`` (/root/reference/models/graph_gen.py).
+
+* ``get_graph_generate_fn``              graph_gen.py:222-227
+* ``gen_multi_level_local_graph_v3``     graph_gen.py:155-195
+* ``gen_disjointed_rnn_local_graph_v3``  graph_gen.py:197-220
+* ``multi_layer_downsampling_select``    graph_gen.py:49-90  (+ :11-47 voxel centroids)
+
+Inputs may be NumPy arrays (the reference's calling convention, run.py:219-222: arrays are
+copied to the GPU, results copied back as NumPy) or torch CUDA tensors (results stay on the
+device).  The deterministic inference path is implemented (``add_rnd3d=False``,
+``downsample_method='center'``, ``num_neighbors <= 0``); the training-time random variants
+(graph_gen.py:24-39, 92-153, 210-214) draw from Python's RNG and are out of scope.
+
+Extra, backwards-compatible keyword ``frame_ptr``: a [F+1] int array batching F frames in one
+call; the result is then exactly what the reference's ``batch_data`` (train.py:135-171) builds
+from F per-frame graphs (indices offset per level).
+
+Canonical orders (the reference leaves both unspecified): keypoints in
+ascending linear voxel key, edges grouped by destination with ascending source inside a group.
+"""
+import numpy as np
+import torch
+
+from .. import _lib
+
+
+def _device():
+    if not torch.cuda.is_available():
+        raise RuntimeError('point-gnn_b200 needs a CUDA device (no CPU fallback)')
+    return torch.device('cuda', torch.cuda.current_device())
+
+
+class _Cloud(object):
+    """points + frame partition on the device, remembering the caller's array type."""
+
+    def __init__(self, points_xyz, frame_ptr=None):
+        self.numpy_io = not isinstance(points_xyz, torch.Tensor)
+        dev = _device()
+        if self.numpy_io:
+            pts = torch.from_numpy(np.ascontiguousarray(points_xyz, dtype=np.float32)).to(dev)
+        else:
+            pts = points_xyz.to(device=dev, dtype=torch.float32).contiguous()
+        assert pts.dim() == 2 and pts.shape[1] == 3, 'points_xyz must be [N, 3]'
+        if frame_ptr is None:
+            fp = torch.tensor([0, pts.shape[0]], dtype=torch.int32, device=dev)
+        elif isinstance(frame_ptr, torch.Tensor):
+            fp = frame_ptr.to(device=dev, dtype=torch.int32).contiguous()
+        else:
+            fp = torch.from_numpy(np.asarray(frame_ptr, dtype=np.int32)).to(dev)
+        self.xyz = pts
+        self.frame_ptr = fp
+
+
+def _voxel_vector(base_voxel_size, level):
+    v = np.asarray(base_voxel_size, dtype=np.float64) * level      # graph_gen.py:44
+    return np.broadcast_to(v, (3,)).astype(np.float64)
+
+
+def multi_layer_downsampling_select(points_xyz, base_voxel_size, levels=[1], add_rnd3d=False):
+    """graph_gen.py:49-90.  -> (vertex_coord_list, keypoint_indices_list)."""
+    cloud = _Cloud(points_xyz)
+    vertex_coord_list, keypoint_indices_list, _ = _downsampling_select(cloud, base_voxel_size, levels, add_rnd3d)
+    if cloud.numpy_io:
+        vertex_coord_list = [v.cpu().numpy() for v in vertex_coord_list]
+        keypoint_indices_list = [k.cpu().numpy().astype(np.int64) for k in keypoint_indices_list]
+    return vertex_coord_list, keypoint_indices_list
+
+
+def _downsampling_select(cloud, base_voxel_size, levels, add_rnd3d):
+    """Device-side body of multi_layer_downsampling_select, also tracking each level's frame_ptr."""
+    if add_rnd3d:
+        raise NotImplementedError('add_rnd3d=True is the training-time random grid shift '
+                                  '(graph_gen.py:24-39); only the inference path is built')
+    vertex_coord_list = [cloud.xyz]
+    frame_ptr_list = [cloud.frame_ptr]
+    keypoint_indices_list = []
+    last_level = 0
+    for level in levels:
+        base_points = vertex_coord_list[-1]
+        if np.isclose(level, last_level):
+            # same scale (a gnn layer): identity, graph_gen.py:76-81
+            vertex_coord_list.append(base_points)
+            frame_ptr_list.append(frame_ptr_list[-1])
+            keypoint_indices_list.append(
+                torch.arange(base_points.shape[0], dtype=torch.int32, device=base_points.device)[:, None])
+        else:
+            # graph_gen.py:41-45 voxelises the ORIGINAL cloud, :84-88 snaps to the previous level.
+            # All shipped configs have one distinct scale, where previous level == original cloud.
+            if base_points is not cloud.xyz:
+                raise NotImplementedError('more than one distinct downsampling scale')
+            idx, kp_fp = _lib.voxel_keypoints(cloud.xyz, cloud.frame_ptr, _voxel_vector(base_voxel_size, level))
+            vertex_coord_list.append(_lib.gather_rows(cloud.xyz, idx))
+            frame_ptr_list.append(kp_fp)
+            keypoint_indices_list.append(idx[:, None])
+        last_level = level
+    return vertex_coord_list, keypoint_indices_list, frame_ptr_list
+
+
+def _radius_edges(points, point_fp, centers, center_fp, radius, num_neighbors,
+                  neighbors_downsample_method='random', scale=None):
+    if num_neighbors > 0:
+        raise NotImplementedError('num_neighbors > 0 is the training-time random neighbour cap '
+                                  '(graph_gen.py:210-214); inference configs use -1')
+    if scale is not None:
+        s = torch.as_tensor(np.asarray(scale, dtype=np.float32), device=points.device)
+        points = (points / s).contiguous()          # graph_gen.py:203-206
+        centers = (centers / s).contiguous()
+    _, edges = _lib.radius_graph(points, point_fp, centers, center_fp, radius)
+    return edges.t()      # [E,2] view whose columns (src, dst) are contiguous
+
+
+def gen_disjointed_rnn_local_graph_v3(points_xyz, center_xyz, radius, num_neighbors,
+                                      neighbors_downsample_method='random', scale=None):
+    """graph_gen.py:197-220.  -> [E,2] (point_idx, center_idx)."""
+    pc = _Cloud(points_xyz)
+    cc = _Cloud(center_xyz)
+    edges = _radius_edges(pc.xyz, pc.frame_ptr, cc.xyz, cc.frame_ptr, radius, num_neighbors,
+                          neighbors_downsample_method, scale)
+    if pc.numpy_io:
+        return np.ascontiguousarray(edges.cpu().numpy()).astype(np.int64)
+    return edges
+
+
+def gen_multi_level_local_graph_v3(points_xyz, base_voxel_size, level_configs, add_rnd3d=False,
+                                   downsample_method='center', frame_ptr=None, return_frame_ptr=False):
+    """graph_gen.py:155-195.  -> (vertex_coord_list, keypoint_indices_list, edges_list)."""
+    if isinstance(base_voxel_size, list):
+        base_voxel_size = np.array(base_voxel_size)
+    if downsample_method != 'center':
+        raise NotImplementedError("downsample_method='random' is training-only (graph_gen.py:92-153)")
+    cloud = _Cloud(points_xyz, frame_ptr)
+    scales = [config['graph_scale'] for config in level_configs]
+    vertex_coord_list, keypoint_indices_list, frame_ptr_list = _downsampling_select(
+        cloud, base_voxel_size, scales, add_rnd3d)
+    edges_list = []
+    for config in level_configs:
+        graph_level = config['graph_level']
+        if config['graph_gen_method'] != 'disjointed_rnn_local_graph_v3':
+            raise KeyError(config['graph_gen_method'])
+        edges_list.append(_radius_edges(vertex_coord_list[graph_level], frame_ptr_list[graph_level],
+                                        vertex_coord_list[graph_level + 1], frame_ptr_list[graph_level + 1],
+                                        **config['graph_gen_kwargs']))
+    if cloud.numpy_io:
+        vertex_coord_list = [v.cpu().numpy() for v in vertex_coord_list]
+        keypoint_indices_list = [k.cpu().numpy().astype(np.int64) for k in keypoint_indices_list]
+        edges_list = [np.ascontiguousarray(e.cpu().numpy()).astype(np.int64) for e in edges_list]
+        frame_ptr_list = [f.cpu().numpy() for f in frame_ptr_list]
+    if return_frame_ptr:
+        return vertex_coord_list, keypoint_indices_list, edges_list, frame_ptr_list
+    return vertex_coord_list, keypoint_indices_list, edges_list
+
+
+def get_graph_generate_fn(method_name):
+    """graph_gen.py:222-227."""
+    method_map = {
+        'disjointed_rnn_local_graph_v3': gen_disjointed_rnn_local_graph_v3,
+        'multi_level_local_graph_v3': gen_multi_level_local_graph_v3,
+    }
+    return method_map[method_name]

@@ -1,0 +1,238 @@
+"""GPU parity tests for the GNN half: CUDA kernels (through the C ABI / the reference-shaped
+Python layer API) vs the fp32 CPU oracle, with the reference's trained weights.
+
+Tolerance (BASELINE.json north_star): vertex features / logits / box encodings within 1e-3
+absolute of the fp32 CPU path.  The fp32 FFMA kernels are expected ~1e-5; the tcgen05 BF16x3
+kernels ~1e-4 (three-term split)."""
+import numpy as np
+import pytest
+import torch
+
+from oracle import gnn as ognn
+from oracle import graph as ograph
+from oracle import synth
+
+pytestmark = pytest.mark.gpu
+TOL = 1e-3
+
+
+def _cuda(a, dtype=None):
+    t = torch.from_numpy(np.ascontiguousarray(a)).cuda()
+    return t if dtype is None else t.to(dtype)
+
+
+def test_scatter_max_vs_oracle():
+    from pointgnn_b200.models import gnn
+    rng = np.random.default_rng(0)
+    for e, c, k, sorted_ids in ((1000, 300, 37, True), (5000, 7, 600, False), (64, 1, 3, True), (3, 513, 5, False)):
+        f = rng.standard_normal((e, c)).astype(np.float32)
+        ids = rng.integers(0, k, e)
+        if sorted_ids:
+            ids = np.sort(ids)
+        out = gnn.graph_scatter_max_fn(_cuda(f), _cuda(ids.astype(np.int32)), k).cpu().numpy()
+        assert np.array_equal(out, ognn.graph_scatter_max_fn(f, ids, k))      # max is exact
+    # empty input, every segment empty -> float lowest
+    out = gnn.graph_scatter_max_fn(torch.zeros((0, 4), device='cuda'), torch.zeros(0, dtype=torch.int32, device='cuda'), 3)
+    assert np.array_equal(out.cpu().numpy(), np.full((3, 4), np.finfo(np.float32).min, np.float32))
+    # int64 [E,1] ids as the reference passes them
+    f = rng.standard_normal((10, 2)).astype(np.float32)
+    ids = np.array([0, 0, 1, 1, 1, 4, 4, 4, 4, 4])
+    out = gnn.graph_scatter_max_fn(_cuda(f), _cuda(ids[:, None]), 5).cpu().numpy()
+    assert np.array_equal(out, ognn.graph_scatter_max_fn(f, ids, 5))
+
+
+@pytest.mark.parametrize('precision', ['fp32'])
+def test_fully_connected_vs_oracle(precision):
+    import pointgnn_b200
+    from pointgnn_b200 import _lib
+    pointgnn_b200.set_precision(precision)
+    rng = np.random.default_rng(1)
+    for m, k, n in ((1, 1, 1), (257, 300, 300), (1000, 303, 300), (77, 64, 3), (513, 4, 32), (130, 512, 256),
+                    (64, 300, 7)):
+        x = rng.standard_normal((m, k)).astype(np.float32)
+        w = (rng.standard_normal((k, n)) / np.sqrt(k)).astype(np.float32)
+        b = rng.standard_normal(n).astype(np.float32)
+        r = rng.standard_normal((m, n)).astype(np.float32)
+        for relu in (True, False):
+            for res in (None, r):
+                want = x @ w + b
+                if relu:
+                    want = np.maximum(want, 0)
+                if res is not None:
+                    want = want + res
+                got = _lib.fully_connected(_cuda(x), _cuda(w), _cuda(b), relu, residual=None if res is None else _cuda(res),
+                                           precision=pointgnn_b200.get_precision()).cpu().numpy()
+                assert np.abs(got - want).max() < 1e-4, (m, k, n, relu)
+    pointgnn_b200.set_precision('fp32')
+
+
+def _edge_case(g, scope, mode):
+    coords, keypoints, edges = g.graph_tuple()
+    rng = np.random.default_rng(5)
+    w = g.weights
+    if mode == 'pool':
+        lc = g.layer_configs[0]
+        feats = g.graph['intensity']
+        return lc, feats, coords[0], keypoints[0], edges[0]
+    lc = [l for l in g.layer_configs if l['scope'] == scope][0]
+    k = coords[1].shape[0]
+    d = w[scope + '/combined_features/fully_connected_1/weights'].shape[1]
+    feats = np.abs(rng.standard_normal((k, d))).astype(np.float32) * 0.3
+    return lc, feats, coords[1], keypoints[1], edges[1]
+
+
+@pytest.mark.parametrize('name', ['car', 'ped'])
+@pytest.mark.parametrize('precision', ['fp32'])
+def test_layers_vs_oracle(name, precision, request):
+    """PointSetPooling.apply_regular and GraphNetAutoCenter.apply_regular, layer by layer."""
+    import pointgnn_b200
+    from pointgnn_b200.models import gnn
+    g = request.getfixturevalue(name)
+    pointgnn_b200.set_precision(precision)
+    store = gnn.VariableStore(g.weights)
+    try:
+        lc, feats, xyz, kp, ed = _edge_case(g, 'layer1', 'pool')
+        want = ognn.point_set_pooling(g.weights, 'layer1', feats, xyz, kp, ed, **lc['kwargs'])
+        with gnn.variable_session(store), gnn.variable_scope('layer1'):
+            got = gnn.PointSetPooling().apply_regular(_cuda(feats), _cuda(xyz), _cuda(kp, torch.int32),
+                                                      _cuda(ed, torch.int32), **lc['kwargs'])
+        assert got.shape == want.shape and np.abs(got.cpu().numpy() - want).max() < TOL
+        for scope in ('layer2', 'layer4'):
+            lc, feats, xyz, kp, ed = _edge_case(g, scope, 'gnn')
+            want = ognn.graph_net_auto_center(g.weights, scope, feats, xyz, kp, ed, **lc['kwargs'])
+            with gnn.variable_session(store), gnn.variable_scope(scope):
+                got = gnn.GraphNetAutoCenter().apply_regular(_cuda(feats), _cuda(xyz), None, _cuda(ed, torch.int32),
+                                                             **lc['kwargs'])
+            err = np.abs(got.cpu().numpy() - want).max()
+            assert err < TOL, (scope, err)
+            # auto_offset=False path (configs/car_fixed_T3_train_config:64)
+            kw = dict(lc['kwargs'], auto_offset=False)
+            want = ognn.graph_net_auto_center(g.weights, scope, feats, xyz, kp, ed, **kw)
+            with gnn.variable_session(store), gnn.variable_scope(scope):
+                # the un-offset layer does not create the offset MLP variables, scope counters differ
+                got = gnn.GraphNetAutoCenter().apply_regular(_cuda(feats), _cuda(xyz), None, _cuda(ed, torch.int32), **kw)
+            assert np.abs(got.cpu().numpy() - want).max() < TOL
+    finally:
+        pointgnn_b200.set_precision('fp32')
+
+
+def test_fused_equals_op_by_op(car):
+    """Custom plugin functions take the op-by-op route; results must equal the fused kernel."""
+    from pointgnn_b200.models import gnn
+
+    def my_mlp(features, Ks, is_logits, normalization_type, activation_type):
+        return gnn.multi_layer_neural_network_fn(features, Ks, is_logits, normalization_type, activation_type)
+
+    def my_max(f, c, n):
+        return gnn.graph_scatter_max_fn(f, c, n)
+
+    store = gnn.VariableStore(car.weights)
+    lc, feats, xyz, kp, ed = _edge_case(car, 'layer3', 'gnn')
+    args = (_cuda(feats), _cuda(xyz), None, _cuda(ed, torch.int32))
+    with gnn.variable_session(store), gnn.variable_scope('layer3'):
+        fused = gnn.GraphNetAutoCenter().apply_regular(*args, **lc['kwargs'])
+    with gnn.variable_session(store), gnn.variable_scope('layer3'):
+        plain = gnn.GraphNetAutoCenter(edge_feature_fn=my_mlp, aggregation_fn=my_max, update_fn=my_mlp,
+                                       auto_offset_fn=my_mlp).apply_regular(*args, **lc['kwargs'])
+    assert np.abs(fused.cpu().numpy() - plain.cpu().numpy()).max() < 1e-4
+    lc, feats, xyz, kp, ed = _edge_case(car, 'layer1', 'pool')
+    args = (_cuda(feats), _cuda(xyz), _cuda(kp, torch.int32), _cuda(ed, torch.int32))
+    with gnn.variable_session(store), gnn.variable_scope('layer1'):
+        fused = gnn.PointSetPooling().apply_regular(*args, **lc['kwargs'])
+    with gnn.variable_session(store), gnn.variable_scope('layer1'):
+        plain = gnn.PointSetPooling(point_feature_fn=my_mlp, aggregation_fn=my_max,
+                                    output_fn=my_mlp).apply_regular(*args, **lc['kwargs'])
+    assert np.abs(fused.cpu().numpy() - plain.cpu().numpy()).max() < 1e-4
+
+
+def _predict(g, layer_configs, precision, inputs):
+    import pointgnn_b200
+    from pointgnn_b200.models import models
+    pointgnn_b200.set_precision(precision)
+    try:
+        model = models.get_model(g.config['model_name'])(
+            num_classes=g.config['num_classes'], box_encoding_len=7, mode='test',
+            **dict(g.config['model_kwargs'], layer_configs=layer_configs))
+        model.load_weights(g.weights)
+        logits, boxes = model.predict(*inputs, is_training=True)       # run.py:254 feeds True
+        probs = model.postprocess(logits)
+    finally:
+        pointgnn_b200.set_precision('fp32')
+    return logits, boxes, probs
+
+
+@pytest.mark.parametrize('name', ['car', 'ped'])
+@pytest.mark.parametrize('precision', ['fp32'])
+def test_predict_matches_golden(name, precision, request):
+    """Whole model (pool + 3 GNN iterations + predictor) on the pinned graph vs the golden logits."""
+    g = request.getfixturevalue(name)
+    coords, keypoints, edges = g.graph_tuple()
+    logits, boxes, probs = _predict(g, g.layer_configs, precision, (g.graph['intensity'], coords, keypoints, edges))
+    assert isinstance(logits, np.ndarray) and logits.shape == g.gnn['logits'].shape
+    assert boxes.shape == g.gnn['boxes'].shape
+    assert np.abs(logits - g.gnn['logits']).max() < TOL
+    assert np.abs(boxes - g.gnn['boxes']).max() < TOL
+    assert np.abs(probs - ognn.postprocess(g.gnn['logits'])).max() < 1e-4
+    assert np.array_equal(probs.argmax(1), ognn.postprocess(g.gnn['logits']).argmax(1))
+
+
+@pytest.mark.parametrize('precision', ['fp32'])
+def test_car_auto_T1_end_to_end(car, precision):
+    """BASELINE config 1: car_auto_T1 (pool + 1 GNN iteration + predictor), graph built on the GPU,
+    20k-point synthetic cloud, vs the CPU oracle on the oracle's own graph."""
+    from pointgnn_b200.models import graph_gen
+    t1_layers = car.layer_configs[:2] + car.layer_configs[-1:]
+    xyz, intensity = synth.lidar_frame(0, 20000)
+    graph_np = graph_gen.get_graph_generate_fn('multi_level_local_graph_v3')(xyz, **car.graph_kwargs)
+    co, kp, ed = ograph.gen_multi_level_local_graph_v3(xyz, **car.graph_kwargs)
+    for a, b in zip(graph_np[2], ed):
+        assert np.array_equal(a, b)
+    logits, boxes, _ = _predict(car, t1_layers, precision, (intensity,) + tuple(graph_np))
+    want_l, want_b = ognn.predict(car.weights, t1_layers, 4, 7, intensity, co, kp, ed)
+    assert np.abs(logits - want_l).max() < TOL and np.abs(boxes - want_b).max() < TOL
+
+
+def test_device_resident_predict_and_batch(car):
+    """CUDA-tensor inputs stay on the device; a 2-frame batch (batch_data layout) equals per-frame results."""
+    from pointgnn_b200.models import graph_gen
+    clouds = [synth.lidar_frame(i, 4000) for i in (30, 31)]
+    xyz = torch.from_numpy(np.vstack([c[0] for c in clouds])).cuda()
+    inten = torch.from_numpy(np.vstack([c[1] for c in clouds])).cuda()
+    fp = torch.tensor([0, 4000, 8000], dtype=torch.int32, device='cuda')
+    coords, kp, edges, fps = graph_gen.gen_multi_level_local_graph_v3(xyz, frame_ptr=fp, return_frame_ptr=True,
+                                                                     **car.graph_kwargs)
+    logits, boxes, _ = _predict(car, car.layer_configs, 'fp32', (inten, coords, kp, edges))
+    assert logits.is_cuda and boxes.is_cuda
+    k0 = int(fps[1][1])
+    for i, (c, it) in enumerate(clouds):
+        g1 = graph_gen.gen_multi_level_local_graph_v3(c, **car.graph_kwargs)
+        l1, b1, _ = _predict(car, car.layer_configs, 'fp32', (it,) + tuple(g1))
+        sl = slice(0, k0) if i == 0 else slice(k0, None)
+        assert np.abs(logits[sl].cpu().numpy() - l1).max() < 1e-4
+        assert np.abs(boxes[sl].cpu().numpy() - b1).max() < 1e-4
+
+
+def test_errors_are_python_exceptions(car):
+    from pointgnn_b200 import _lib
+    from pointgnn_b200.models import gnn, models
+    m = models.get_model('multi_layer_fast_local_graph_model_v2')(num_classes=4, box_encoding_len=7, mode='test',
+                                                                  **car.config['model_kwargs'])
+    with pytest.raises(RuntimeError):
+        m.predict(np.zeros((1, 1), np.float32), [], [], [])
+    # out-of-range edge index (TF: InvalidArgumentError at sess.run)
+    w = torch.zeros((4, 8), device='cuda')
+    b = torch.zeros(8, device='cuda')
+    f = torch.zeros((5, 1), device='cuda')
+    x = torch.zeros((5, 3), device='cuda')
+    src = torch.tensor([0, 9], dtype=torch.int32, device='cuda')
+    dst = torch.tensor([0, 0], dtype=torch.int32, device='cuda')
+    with pytest.raises(_lib.PointGNNError):
+        _lib.edge_mlp_max(1, f, x, x, None, src, dst, 5, [w], [b])
+    with pytest.raises(ValueError):
+        _lib.fully_connected(torch.zeros((2, 3), device='cuda'), w, b, True)
+    store = gnn.VariableStore({})
+    with gnn.variable_session(store), gnn.variable_scope('layer9'):
+        with pytest.raises(KeyError):
+            gnn.multi_layer_neural_network_fn(torch.zeros((2, 3), device='cuda'), Ks=(4,), normalization_type='NONE')
+    with pytest.raises(NotImplementedError):
+        gnn.multi_layer_neural_network_fn(torch.zeros((2, 3), device='cuda'), Ks=(4,))   # default BN: not built

@@ -1,0 +1,162 @@
+"""GPU parity tests for graph construction: CUDA kernels (through the C ABI) vs the CPU oracle
+and vs the golden edge lists produced by the reference's own graph_gen.py.  Bit-exact."""
+import numpy as np
+import pytest
+import torch
+
+from oracle import graph, synth
+
+pytestmark = pytest.mark.gpu
+
+
+def _np(t):
+    return t.cpu().numpy()
+
+
+def _check_graph(xyz, kwargs, got):
+    coords_o, kp_o, edges_o = graph.gen_multi_level_local_graph_v3(xyz, **kwargs)
+    coords, kp, edges = got
+    assert len(coords) == len(coords_o) and len(edges) == len(edges_o)
+    for a, b in zip(coords, coords_o):
+        assert np.array_equal(np.asarray(a), np.asarray(b, dtype=np.float32))
+    for a, b in zip(kp, kp_o):
+        assert a.shape == b.shape and np.array_equal(a, b)
+    for a, b in zip(edges, edges_o):
+        assert a.shape == b.shape and np.array_equal(a, b)      # already canonical: no re-sort needed
+
+
+@pytest.mark.parametrize('name', ['car', 'ped'])
+def test_numpy_api_matches_reference_golden(name, request):
+    from pointgnn_b200.models import graph_gen
+    g = request.getfixturevalue(name)
+    fn = graph_gen.get_graph_generate_fn(g.config['graph_gen_method'])
+    coords, kp, edges = fn(g.graph['xyz'], **g.graph_kwargs)
+    assert isinstance(edges[0], np.ndarray) and edges[0].dtype == np.int64 and edges[0].shape[1] == 2
+    assert np.array_equal(kp[0][:, 0], g.graph['keypoint_idx'])
+    assert np.array_equal(edges[0], g.graph['edges0'])          # reference's sklearn output, canonical order
+    assert np.array_equal(edges[1], g.graph['edges1'])
+    assert np.array_equal(coords[1], g.graph['xyz'][g.graph['keypoint_idx']])
+
+
+@pytest.mark.parametrize('n,frame', [(20000, 0), (6000, 3)])
+def test_full_frame_vs_oracle(car, n, frame):
+    from pointgnn_b200.models import graph_gen
+    xyz, _ = synth.lidar_frame(frame, n)
+    got = graph_gen.gen_multi_level_local_graph_v3(xyz, **car.graph_kwargs)
+    _check_graph(xyz, car.graph_kwargs, got)
+
+
+def test_ped_radii_vs_oracle(ped):
+    from pointgnn_b200.models import graph_gen
+    xyz, _ = synth.lidar_frame(2, 12000)
+    got = graph_gen.gen_multi_level_local_graph_v3(xyz, **ped.graph_kwargs)
+    _check_graph(xyz, ped.graph_kwargs, got)
+
+
+def test_device_tensor_api_and_two_pass_abi(car):
+    from pointgnn_b200 import _lib
+    from pointgnn_b200.models import graph_gen
+    xyz, _ = synth.lidar_frame(4, 5000)
+    t = torch.from_numpy(xyz).cuda()
+    coords, kp, edges = graph_gen.gen_multi_level_local_graph_v3(t, **car.graph_kwargs)
+    assert all(c.is_cuda for c in coords) and edges[0].is_cuda and edges[0].dtype == torch.int32
+    assert edges[0][:, 0].is_contiguous() and edges[0][:, 1].is_contiguous()
+    _check_graph(xyz, car.graph_kwargs, ([_np(c) for c in coords], [_np(k).astype(np.int64) for k in kp],
+                                        [_np(e).astype(np.int64) for e in edges]))
+    fp = torch.tensor([0, 5000], dtype=torch.int32, device='cuda')
+    kfp = torch.tensor([0, coords[1].shape[0]], dtype=torch.int32, device='cuda')
+    row_ptr, e2 = _lib.radius_graph_two_pass(t, fp, coords[1], kfp, 1.0)
+    assert np.array_equal(_np(e2.t()), _np(edges[0]))
+    rp = _np(row_ptr)
+    assert rp[0] == 0 and rp[-1] == e2.shape[1]
+    assert np.array_equal(np.diff(rp), np.bincount(_np(e2[1]), minlength=coords[1].shape[0]))
+
+
+def test_batched_frames_equal_batch_data(car):
+    """frame_ptr batching == reference batch_data (train.py:135-171) of per-frame graphs."""
+    from pointgnn_b200.models import graph_gen
+    clouds = [synth.lidar_frame(i, n)[0] for i, n in ((20, 3000), (21, 4500), (22, 2000))]
+    frames = []
+    for c in clouds:
+        co, kp, ed = graph.gen_multi_level_local_graph_v3(c, **car.graph_kwargs)
+        frames.append((np.zeros((c.shape[0], 1), np.float32), co, kp, ed))
+    _, bc, bk, be = graph.batch_graphs(frames)
+    fp = np.cumsum([0] + [c.shape[0] for c in clouds]).astype(np.int32)
+    coords, kp, edges, fps = graph_gen.gen_multi_level_local_graph_v3(
+        np.vstack(clouds), frame_ptr=fp, return_frame_ptr=True, **car.graph_kwargs)
+    for a, b in zip(coords, bc):
+        assert np.array_equal(a, b.astype(np.float32))
+    for a, b in zip(kp, bk):
+        assert np.array_equal(a, b)
+    for a, b in zip(edges, be):
+        assert np.array_equal(a, b)
+    assert np.array_equal(fps[1], np.cumsum([0] + [f[1][1].shape[0] for f in frames]))
+
+
+def test_edge_cases():
+    from pointgnn_b200.models import graph_gen
+    # single point: one keypoint, one self loop at every level
+    one = np.array([[1.5, -0.25, 7.0]], np.float32)
+    cfg = [dict(graph_level=0, graph_scale=0.5, graph_gen_method='disjointed_rnn_local_graph_v3',
+                graph_gen_kwargs=dict(radius=1.0, num_neighbors=-1)),
+           dict(graph_level=1, graph_scale=0.5, graph_gen_method='disjointed_rnn_local_graph_v3',
+                graph_gen_kwargs=dict(radius=4.0, num_neighbors=-1))]
+    coords, kp, edges = graph_gen.gen_multi_level_local_graph_v3(one, 0.8, cfg)
+    assert np.array_equal(kp[0], [[0]]) and np.array_equal(edges[0], [[0, 0]]) and np.array_equal(edges[1], [[0, 0]])
+    # exact boundary: points at distance exactly r are included (d <= r), just outside are not
+    pts = np.array([[0, 0, 0], [1, 0, 0], [0, 1, 0], [0, 0, np.nextafter(np.float32(1), np.float32(2))],
+                    [0.6, 0.8, 0]], np.float32)
+    e = graph_gen.gen_disjointed_rnn_local_graph_v3(pts, pts[:1], 1.0, -1)
+    assert np.array_equal(e, graph.radius_graph(pts, pts[:1], 1.0))
+    assert e[:, 0].tolist() == [0, 1, 2] or e[:, 0].tolist() == [0, 1, 2, 4]   # 0.36+0.64 rounds either way in fp32->fp64
+    # dense blob: every point within the radius of every centre -> one very long row per centre
+    rng = np.random.default_rng(0)
+    blob = (rng.random((9000, 3), dtype=np.float32) * 0.3).astype(np.float32)
+    e = graph_gen.gen_disjointed_rnn_local_graph_v3(blob, blob[:3], 1.0, -1)
+    assert e.shape == (27000, 2) and np.array_equal(e, graph.radius_graph(blob, blob[:3], 1.0))
+    # centres outside the bounding box of the points, negative coordinates, empty rows
+    pts = (rng.random((500, 3), dtype=np.float32) * 10 - 5).astype(np.float32)
+    ctr = np.array([[-30, 0, 0], [0, 0, 0], [4.9, 4.9, 4.9], [100, 100, 100]], np.float32)
+    e = graph_gen.gen_disjointed_rnn_local_graph_v3(pts, ctr, 2.0, -1)
+    assert np.array_equal(e, graph.radius_graph(pts, ctr, 2.0))
+    # duplicate points: ties in the 1-NN snap resolve to the lowest index, duplicates are kept
+    dup = np.repeat(np.array([[0.1, 0.1, 5.0], [3.0, 0.2, 9.0]], np.float32), 3, axis=0)
+    coords, kp, edges = graph_gen.gen_multi_level_local_graph_v3(dup, 0.8, cfg)
+    co, ko, eo = graph.gen_multi_level_local_graph_v3(dup, 0.8, cfg)
+    assert np.array_equal(kp[0], ko[0]) and np.array_equal(edges[0], eo[0]) and np.array_equal(edges[1], eo[1])
+
+
+def test_per_axis_voxel_and_training_paths_raise(car):
+    from pointgnn_b200.models import graph_gen
+    xyz, _ = synth.lidar_frame(9, 3000)
+    kw = dict(car.graph_kwargs)
+    kw['base_voxel_size'] = [0.8, 0.6, 1.0]                   # graph_gen.py:172-173
+    got = graph_gen.gen_multi_level_local_graph_v3(xyz, **kw)
+    _check_graph(xyz, kw, got)
+    with pytest.raises(NotImplementedError):
+        graph_gen.gen_multi_level_local_graph_v3(xyz, 0.8, car.graph_kwargs['level_configs'], add_rnd3d=True)
+    with pytest.raises(NotImplementedError):
+        graph_gen.gen_multi_level_local_graph_v3(xyz, 0.8, car.graph_kwargs['level_configs'],
+                                                 downsample_method='random')
+    with pytest.raises(NotImplementedError):
+        graph_gen.gen_disjointed_rnn_local_graph_v3(xyz, xyz[:10], 1.0, 256)
+
+
+def test_large_cloud_properties(car):
+    """120k-point 360-degree frame (BASELINE config 3): size-independent properties + oracle."""
+    from pointgnn_b200.models import graph_gen
+    xyz, _ = synth.lidar_frame(1, 120000, full_360=True)
+    coords, kp, edges = graph_gen.gen_multi_level_local_graph_v3(xyz, **car.graph_kwargs)
+    k = kp[0].shape[0]
+    for e, nsrc in ((edges[0], xyz.shape[0]), (edges[1], k)):
+        assert np.all(np.diff(e[:, 1]) >= 0)
+        same = e[1:, 1] == e[:-1, 1]
+        assert np.all(e[1:, 0][same] > e[:-1, 0][same])
+        assert e[:, 0].min() >= 0 and e[:, 0].max() < nsrc and e[:, 1].max() == k - 1
+    e1 = edges[1]
+    assert np.count_nonzero(e1[:, 0] == e1[:, 1]) == k                        # self loops
+    # symmetry of the keypoint graph: (a,b) in E <=> (b,a) in E
+    fwd = e1[:, 0] * k + e1[:, 1]
+    bwd = e1[:, 1] * k + e1[:, 0]
+    assert np.array_equal(np.sort(fwd), np.sort(bwd))
+    _check_graph(xyz, car.graph_kwargs, (coords, kp, edges))
