@@ -82,7 +82,7 @@ constexpr int kTM = 64, kTN = 64, kTK = 16;
 __global__ void __launch_bounds__(256) fc_fp32_kernel(const float* __restrict__ x, int64_t m, int k,
                                                        const float* __restrict__ w, const float* __restrict__ bias,
                                                        int n, int act, const float* __restrict__ residual,
-                                                       float* __restrict__ out) {
+                                                       float* __restrict__ out, int ldo) {
   __shared__ float xs[kTK][kTM + 4];
   __shared__ float ws[kTK][kTN + 4];
   const int tx = threadIdx.x & 15, ty = threadIdx.x >> 4;
@@ -126,11 +126,12 @@ __global__ void __launch_bounds__(256) fc_fp32_kernel(const float* __restrict__ 
 #pragma unroll
     for (int j = 0; j < 4; ++j) {
       const int gc = col0 + tx * 4 + j;
-      if (gc >= n) continue;
+      if (gc >= ldo) continue;
+      if (gc >= n) { out[gr * ldo + gc] = 0.0f; continue; }   // zero padding columns [n, ldo)
       float v = acc[i][j] + bias[gc];
       if (act == 1) v = fmaxf(v, 0.0f);
       if (residual != nullptr) v += residual[gr * n + gc];
-      out[gr * n + gc] = v;
+      out[gr * ldo + gc] = v;
     }
   }
 }
@@ -148,6 +149,16 @@ __global__ void softmax_rows_kernel(const float* __restrict__ logits, int64_t nu
 }
 
 }  // namespace
+
+// out has row stride ldo >= n; columns [n, ldo) are written as zeros (ldo <= n rounded up to 64)
+int fc_fp32_launch(const float* x, int64_t m, int k, const float* w, const float* bias, int n, int act,
+                   const float* residual, float* out, int ldo, cudaStream_t s) {
+  PG_REQUIRE(ldo >= n && ldo <= (n + kTN - 1) / kTN * kTN, "fc: bad output stride %d for n=%d", ldo, n);
+  dim3 grid(ceil_div(n, kTN), ceil_div(m, kTM));
+  fc_fp32_kernel<<<grid, 256, 0, s>>>(x, m, k, w, bias, n, act, residual, out, ldo);
+  PG_LAUNCH_CHECK();
+  return PG_OK;
+}
 
 int fc_tc_bf16x3(const float* x, int64_t m, int k, const float* w, const float* bias, int n, int act,
                  const float* residual, float* out, cudaStream_t s);  // pg_tc.cu
@@ -200,10 +211,7 @@ extern "C" int pg_fully_connected(const float* x, int64_t m, int32_t k, const fl
   PG_REQUIRE(x && w && bias && out, "pg_fully_connected: null argument");
   if (precision == 1) return fc_tc_bf16x3(x, m, k, w, bias, n, act, residual, out, s);
   PG_REQUIRE(precision == 0, "pg_fully_connected: unknown precision %d", precision);
-  dim3 grid(ceil_div(n, kTN), ceil_div(m, kTM));
-  fc_fp32_kernel<<<grid, 256, 0, s>>>(x, m, k, w, bias, n, act, residual, out);
-  PG_LAUNCH_CHECK();
-  return PG_OK;
+  return fc_fp32_launch(x, m, k, w, bias, n, act, residual, out, n, s);
 }
 
 extern "C" int pg_softmax_rows(const float* logits, int64_t num_rows, int32_t num_classes, float* out, void* stream) {

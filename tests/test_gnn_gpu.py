@@ -14,6 +14,13 @@ from oracle import synth
 
 pytestmark = pytest.mark.gpu
 TOL = 1e-3
+PRECISIONS = ['fp32', 'bf16x3']
+
+
+def _need(precision):
+    from pointgnn_b200 import _lib
+    if precision == 'bf16x3' and not _lib.tc_available():
+        pytest.skip('tcgen05 path needs an sm_100 device')
 
 
 def _cuda(a, dtype=None):
@@ -82,9 +89,10 @@ def _edge_case(g, scope, mode):
 
 
 @pytest.mark.parametrize('name', ['car', 'ped'])
-@pytest.mark.parametrize('precision', ['fp32'])
+@pytest.mark.parametrize('precision', PRECISIONS)
 def test_layers_vs_oracle(name, precision, request):
     """PointSetPooling.apply_regular and GraphNetAutoCenter.apply_regular, layer by layer."""
+    _need(precision)
     import pointgnn_b200
     from pointgnn_b200.models import gnn
     g = request.getfixturevalue(name)
@@ -162,9 +170,10 @@ def _predict(g, layer_configs, precision, inputs):
 
 
 @pytest.mark.parametrize('name', ['car', 'ped'])
-@pytest.mark.parametrize('precision', ['fp32'])
+@pytest.mark.parametrize('precision', PRECISIONS)
 def test_predict_matches_golden(name, precision, request):
     """Whole model (pool + 3 GNN iterations + predictor) on the pinned graph vs the golden logits."""
+    _need(precision)
     g = request.getfixturevalue(name)
     coords, keypoints, edges = g.graph_tuple()
     logits, boxes, probs = _predict(g, g.layer_configs, precision, (g.graph['intensity'], coords, keypoints, edges))
@@ -176,10 +185,11 @@ def test_predict_matches_golden(name, precision, request):
     assert np.array_equal(probs.argmax(1), ognn.postprocess(g.gnn['logits']).argmax(1))
 
 
-@pytest.mark.parametrize('precision', ['fp32'])
+@pytest.mark.parametrize('precision', PRECISIONS)
 def test_car_auto_T1_end_to_end(car, precision):
     """BASELINE config 1: car_auto_T1 (pool + 1 GNN iteration + predictor), graph built on the GPU,
     20k-point synthetic cloud, vs the CPU oracle on the oracle's own graph."""
+    _need(precision)
     from pointgnn_b200.models import graph_gen
     t1_layers = car.layer_configs[:2] + car.layer_configs[-1:]
     xyz, intensity = synth.lidar_frame(0, 20000)
@@ -236,3 +246,41 @@ def test_errors_are_python_exceptions(car):
             gnn.multi_layer_neural_network_fn(torch.zeros((2, 3), device='cuda'), Ks=(4,), normalization_type='NONE')
     with pytest.raises(NotImplementedError):
         gnn.multi_layer_neural_network_fn(torch.zeros((2, 3), device='cuda'), Ks=(4,))   # default BN: not built
+
+
+@pytest.mark.parametrize('d,c_in', [(300, 300), (256, 256), (64, 32), (128, 300)])
+def test_tc_edge_kernel_shapes_and_tails(d, c_in):
+    """The tcgen05 edge kernel on its own: odd widths, tails, tiny / huge / empty segments."""
+    _need('bf16x3')
+    from pointgnn_b200 import _lib
+    rng = np.random.default_rng(d)
+    nv = 700
+    for case, (e, pattern) in enumerate(((1, 'one'), (255, 'long'), (256, 'long'), (257, 'short'), (5000, 'mixed'),
+                                         (33000, 'mixed'))):
+        if pattern == 'one':
+            dst = np.array([3])
+        elif pattern == 'long':
+            dst = np.sort(rng.integers(0, 3, e))                      # segments spanning tiles
+        elif pattern == 'short':
+            dst = np.sort(rng.integers(0, nv, e))                     # ~1 edge per segment, many empty
+        else:
+            dst = np.sort(np.concatenate([rng.integers(0, nv, e // 2), rng.integers(10, 14, e - e // 2)]))
+        src = rng.integers(0, nv, e)
+        f = (rng.standard_normal((nv, c_in)) * 0.5).astype(np.float32)
+        x = (rng.standard_normal((nv, 3)) * 20).astype(np.float32)
+        xd = x + (rng.standard_normal((nv, 3)) * 0.1).astype(np.float32)
+        w1 = (rng.standard_normal((c_in + 3, d)) / np.sqrt(c_in)).astype(np.float32)
+        b1 = (rng.standard_normal(d) * 0.1).astype(np.float32)
+        w2 = (rng.standard_normal((d, d)) / np.sqrt(d)).astype(np.float32)
+        b2 = (rng.standard_normal(d) * 0.1).astype(np.float32)
+        e0 = np.concatenate([f[src], x[src] - xd[dst]], axis=1)
+        h = np.maximum(np.maximum(e0 @ w1 + b1, 0) @ w2 + b2, 0)
+        want = ognn.graph_scatter_max_fn(h, dst, nv)
+        for prec in (0, 1):
+            got = _lib.edge_mlp_max(1, _cuda(f), _cuda(x), _cuda(xd), None, _cuda(src.astype(np.int32)),
+                                    _cuda(dst.astype(np.int32)), nv, [_cuda(w1), _cuda(w2)], [_cuda(b1), _cuda(b2)],
+                                    precision=prec).cpu().numpy()
+            empty = want == np.finfo(np.float32).min
+            assert np.array_equal(got == np.finfo(np.float32).min, empty), (case, prec)
+            err = np.abs(got - want)[~empty].max() if (~empty).any() else 0.0
+            assert err < (2e-4 if prec == 0 else 1e-3), (d, case, prec, err)

@@ -1,0 +1,222 @@
+// umma_lab: stand-alone hardware checks of the tcgen05 building blocks used by pg_tc.cu.
+// Each test runs in its own process (a faulting kernel poisons the CUDA context):
+//   umma_lab 1cta <swap>      D[128xN] = A[128xK] * B[NxK]^T, cta_group::1, no-swizzle K-major operands
+//   umma_lab 2cta <swap>      D[256xN], cta_group::2 (A split by rows, B split by N across the CTA pair)
+//   umma_lab redux            redux.sync.max.f32 with full and partial member masks
+// <swap> = 0: descriptor LBO = K-adjacent core stride, SBO = row-group stride (CUTLASS reading);
+//          1: the two swapped.  Exactly one of them must reproduce the CPU result.
+#include <cstdio>
+#include <cstdlib>
+#include <cstring>
+#include <vector>
+
+#include "../point-gnn_b200/csrc/pg_umma.cuh"
+
+using namespace pg::umma;
+
+#define CK(x)                                                                     \
+  do {                                                                            \
+    cudaError_t e = (x);                                                          \
+    if (e != cudaSuccess) {                                                       \
+      printf("CUDA error %s at %s:%d\n", cudaGetErrorString(e), __FILE__, __LINE__); \
+      exit(2);                                                                    \
+    }                                                                             \
+  } while (0)
+
+static uint16_t f2bf(float f) {
+  uint32_t u;
+  memcpy(&u, &f, 4);
+  return uint16_t(u >> 16);  // exact for the small integers used here
+}
+
+// K-major no-swizzle image of a [rows x k] matrix: core (rg, kc) at rg*rgs + kc*kcs
+static void pack(const std::vector<float>& m, int rows, int k, int kcs, int rgs, std::vector<uint16_t>& img) {
+  img.assign(size_t(rows / 8) * rgs / 2, 0);
+  for (int r = 0; r < rows; ++r)
+    for (int c = 0; c < k; ++c) {
+      size_t off = size_t(r / 8) * rgs + size_t(c / 8) * kcs + (r % 8) * 16 + (c % 8) * 2;
+      img[off / 2] = f2bf(m[size_t(r) * k + c]);
+    }
+}
+
+template <int kCtaGroup>
+__global__ void __launch_bounds__(128) gemm_kernel(const uint16_t* __restrict__ a_img, const uint16_t* __restrict__ b_img,
+                                                   int a_bytes, int b_bytes, int n, int k, int kcs, int lbo, int sbo,
+                                                   float* __restrict__ out) {
+  extern __shared__ __align__(1024) uint8_t smem[];
+  __shared__ uint64_t bar;
+  __shared__ uint32_t tmem_base;
+  const uint32_t rank = kCtaGroup == 2 ? cluster_ctarank() : 0;
+  uint8_t* sa = smem;
+  uint8_t* sb = smem + ((a_bytes + 1023) / 1024) * 1024;
+  const uint16_t* ga = a_img + size_t(rank) * a_bytes / 2;
+  const uint16_t* gb = b_img + size_t(rank) * b_bytes / 2;
+  for (int i = threadIdx.x; i < a_bytes / 4; i += blockDim.x) reinterpret_cast<uint32_t*>(sa)[i] = reinterpret_cast<const uint32_t*>(ga)[i];
+  for (int i = threadIdx.x; i < b_bytes / 4; i += blockDim.x) reinterpret_cast<uint32_t*>(sb)[i] = reinterpret_cast<const uint32_t*>(gb)[i];
+  fence_proxy_async_smem();
+  if (threadIdx.x == 0) {
+    mbar_init(&bar, 1);
+    fence_barrier_init();
+  }
+  if (threadIdx.x < 32) {
+    tmem_alloc<kCtaGroup>(&tmem_base, 256);
+    tmem_relinquish<kCtaGroup>();
+  }
+  tc_fence_before();
+  __syncthreads();
+  if (kCtaGroup == 2) cluster_sync();
+  tc_fence_after();
+  const uint32_t tmem = tmem_base;
+  if (threadIdx.x == 0 && rank == 0) {
+    const uint32_t idesc = make_idesc_bf16(128 * kCtaGroup, n);
+    for (int s = 0; s < k / 16; ++s) {
+      const uint64_t da = make_smem_desc(smem_u32(sa) + s * 2 * kcs, lbo, sbo);
+      const uint64_t db = make_smem_desc(smem_u32(sb) + s * 2 * kcs, lbo, sbo);
+      mma_bf16<kCtaGroup>(tmem, da, db, idesc, s > 0);
+    }
+    if (kCtaGroup == 1)
+      mma_commit_1cta(&bar);
+    else
+      mma_commit_2cta(&bar, 0x3);
+  }
+  mbar_wait(&bar, 0);
+  tc_fence_after();
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int row = warp * 32 + lane;
+  for (int c0 = 0; c0 < n; c0 += 16) {
+    uint32_t v[16];
+    tmem_ld16(tmem + (uint32_t(warp * 32) << 16) + c0, v);
+    tmem_ld_wait();
+    for (int j = 0; j < 16; ++j) out[(size_t(rank) * 128 + row) * n + c0 + j] = __uint_as_float(v[j]);
+  }
+  tc_fence_before();
+  __syncthreads();
+  if (kCtaGroup == 2) cluster_sync();
+  if (threadIdx.x < 32) tmem_dealloc<kCtaGroup>(tmem, 256);
+}
+
+static int run_gemm(int cta_group, int swap) {
+  const int k = 64, n = 160, m = 128 * cta_group;
+  const int kcs = 128, rgs = (k / 8) * 128;
+  std::vector<float> a(size_t(m) * k), b(size_t(n) * k);
+  srand(1);
+  for (auto& x : a) x = float(rand() % 7 - 3);
+  for (auto& x : b) x = float(rand() % 7 - 3);
+  // per-CTA images: A rows [128*rank, +128); B rows: cta_group 1 -> all n; 2 -> [n/2*rank, +n/2)
+  const int a_rows = 128, b_rows = n / cta_group;
+  std::vector<uint16_t> a_img, b_img, tmp;
+  for (int r = 0; r < cta_group; ++r) {
+    std::vector<float> sub(a.begin() + size_t(r) * a_rows * k, a.begin() + size_t(r + 1) * a_rows * k);
+    pack(sub, a_rows, k, kcs, rgs, tmp);
+    a_img.insert(a_img.end(), tmp.begin(), tmp.end());
+    std::vector<float> subb(b.begin() + size_t(r) * b_rows * k, b.begin() + size_t(r + 1) * b_rows * k);
+    pack(subb, b_rows, k, kcs, rgs, tmp);
+    b_img.insert(b_img.end(), tmp.begin(), tmp.end());
+  }
+  const int a_bytes = a_rows / 8 * rgs, b_bytes = b_rows / 8 * rgs;
+  uint16_t *da, *db;
+  float* dout;
+  CK(cudaMalloc(&da, a_img.size() * 2));
+  CK(cudaMalloc(&db, b_img.size() * 2));
+  CK(cudaMalloc(&dout, size_t(m) * n * 4));
+  CK(cudaMemcpy(da, a_img.data(), a_img.size() * 2, cudaMemcpyHostToDevice));
+  CK(cudaMemcpy(db, b_img.data(), b_img.size() * 2, cudaMemcpyHostToDevice));
+  CK(cudaMemset(dout, 0xff, size_t(m) * n * 4));
+  const int lbo = swap ? rgs : kcs, sbo = swap ? kcs : rgs;
+  const size_t smem = ((a_bytes + 1023) / 1024) * 1024 + b_bytes + 1024;
+  if (cta_group == 1) {
+    CK(cudaFuncSetAttribute(gemm_kernel<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, int(smem)));
+    gemm_kernel<1><<<1, 128, smem>>>(da, db, a_bytes, b_bytes, n, k, kcs, lbo, sbo, dout);
+  } else {
+    CK(cudaFuncSetAttribute(gemm_kernel<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, int(smem)));
+    cudaLaunchConfig_t cfg{};
+    cfg.gridDim = dim3(2);
+    cfg.blockDim = dim3(128);
+    cfg.dynamicSmemBytes = smem;
+    cudaLaunchAttribute at[1];
+    at[0].id = cudaLaunchAttributeClusterDimension;
+    at[0].val.clusterDim.x = 2;
+    at[0].val.clusterDim.y = 1;
+    at[0].val.clusterDim.z = 1;
+    cfg.attrs = at;
+    cfg.numAttrs = 1;
+    CK(cudaLaunchKernelEx(&cfg, gemm_kernel<2>, (const uint16_t*)da, (const uint16_t*)db, a_bytes, b_bytes, n, k, kcs,
+                          lbo, sbo, dout));
+  }
+  CK(cudaGetLastError());
+  CK(cudaDeviceSynchronize());
+  std::vector<float> out(size_t(m) * n);
+  CK(cudaMemcpy(out.data(), dout, out.size() * 4, cudaMemcpyDeviceToHost));
+  double maxerr = 0;
+  int bad = 0;
+  for (int i = 0; i < m; ++i)
+    for (int j = 0; j < n; ++j) {
+      float ref = 0;
+      for (int c = 0; c < k; ++c) ref += a[size_t(i) * k + c] * b[size_t(j) * k + c];
+      const double e = fabs(double(ref) - out[size_t(i) * n + j]);
+      if (!(e <= 1e-3)) ++bad;
+      if (e > maxerr || e != e) maxerr = e;
+    }
+  printf("gemm cta_group=%d swap=%d: maxerr=%g bad=%d/%d -> %s\n", cta_group, swap, maxerr, bad, m * n,
+         bad == 0 ? "MATCH" : "mismatch");
+  return bad == 0 ? 0 : 1;
+}
+
+__global__ void redux_kernel(float* out, long long* cycles) {
+  const int lane = threadIdx.x & 31;
+  float v = float((lane * 37) % 32) - 7.5f;
+  float r_full, r_part = -1.f;
+  asm volatile("redux.sync.max.f32 %0, %1, %2;" : "=f"(r_full) : "f"(v), "r"(0xffffffffu));
+  const unsigned mask = lane < 11 ? 0x7ffu : 0xfffff800u;  // two segments
+  asm volatile("redux.sync.max.f32 %0, %1, %2;" : "=f"(r_part) : "f"(v), "r"(mask));
+  out[threadIdx.x] = r_full;
+  out[32 + threadIdx.x] = r_part;
+  // throughput: 256 dependent-free redux per warp
+  float acc = 0.f;
+  long long t0 = clock64();
+#pragma unroll 16
+  for (int i = 0; i < 256; ++i) {
+    float r;
+    asm volatile("redux.sync.max.f32 %0, %1, %2;" : "=f"(r) : "f"(v + float(i)), "r"(0xffffffffu));
+    acc += r;
+  }
+  long long t1 = clock64();
+  if (threadIdx.x == 0) cycles[0] = t1 - t0;
+  out[64 + threadIdx.x] = acc;
+}
+
+static int run_redux() {
+  float* d;
+  long long* c;
+  CK(cudaMalloc(&d, 96 * 4));
+  CK(cudaMalloc(&c, 8));
+  redux_kernel<<<1, 32>>>(d, c);
+  CK(cudaDeviceSynchronize());
+  float h[96];
+  long long hc;
+  CK(cudaMemcpy(h, d, sizeof(h), cudaMemcpyDeviceToHost));
+  CK(cudaMemcpy(&hc, c, 8, cudaMemcpyDeviceToHost));
+  float v[32], mfull = -1e9f, m0 = -1e9f, m1 = -1e9f;
+  for (int l = 0; l < 32; ++l) {
+    v[l] = float((l * 37) % 32) - 7.5f;
+    mfull = fmaxf(mfull, v[l]);
+    if (l < 11) m0 = fmaxf(m0, v[l]); else m1 = fmaxf(m1, v[l]);
+  }
+  int bad = 0;
+  for (int l = 0; l < 32; ++l) {
+    if (h[l] != mfull) ++bad;
+    if (h[32 + l] != (l < 11 ? m0 : m1)) ++bad;
+  }
+  printf("redux.sync.max.f32: bad=%d  (256 redux in %lld cycles = %.2f cyc/op, one warp)\n", bad, hc, hc / 256.0);
+  return bad;
+}
+
+int main(int argc, char** argv) {
+  if (argc < 2) return 1;
+  cudaDeviceProp prop;
+  CK(cudaGetDeviceProperties(&prop, 0));
+  if (!strcmp(argv[1], "1cta")) return run_gemm(1, argc > 2 ? atoi(argv[2]) : 0);
+  if (!strcmp(argv[1], "2cta")) return run_gemm(2, argc > 2 ? atoi(argv[2]) : 0);
+  if (!strcmp(argv[1], "redux")) return run_redux();
+  return 1;
+}
