@@ -179,6 +179,10 @@ PG_API int pg_edge_mlp_max(int32_t mode, const float* features, int32_t num_feat
 PG_API int pg_softmax_rows(const float* logits, int64_t num_rows, int32_t num_classes, float* out,
                     void* stream);
 
+/* tcgen05 kernel launches so far (which: 0 = fused edge MLP + segment max, 1 = dense layer);
+ * lets callers and tests verify that the tensor-core path, not the FFMA path, actually ran. */
+PG_API int64_t pg_tc_launch_count(int32_t which);
+
 /* Number of kernels this library has launched in the calling process (bench.py). */
 PG_API int64_t pg_launch_count(void);
 

@@ -27,6 +27,7 @@ SIGNATURES = {
     'pg_device_is_sm100': (ctypes.c_int, []),
     'pg_launch_count': (c_i64, []),
     'pg_tc_available': (ctypes.c_int, []),
+    'pg_tc_launch_count': (c_i64, [c_i32]),
     'pg_voxel_keypoints': (ctypes.c_int, [c_f32p, c_i32p, c_i32, c_i64, ctypes.POINTER(ctypes.c_double),
                                           c_i32p, c_i64, c_i32p, ctypes.POINTER(c_i64), ctypes.c_void_p]),
     'pg_radius_graph_count': (ctypes.c_int, [c_f32p, c_i32p, c_f32p, c_i32p, c_i32, c_i64, c_i64,
@@ -102,6 +103,11 @@ def launch_count():
 
 def device_is_sm100():
     return bool(load().pg_device_is_sm100())
+
+
+def tc_launch_count(which=0):
+    """tcgen05 launches so far: which=0 fused edge kernel, 1 dense-layer kernel."""
+    return int(load().pg_tc_launch_count(int(which)))
 
 
 def tc_available():

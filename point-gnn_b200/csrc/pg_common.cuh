@@ -45,7 +45,21 @@ struct Temp {
   cudaError_t alloc(size_t bytes, cudaStream_t s) {
     stream = s;
     if (bytes == 0) bytes = 16;
+    keep_pool_warm();
     return cudaMallocAsync(&ptr, bytes, s);
+  }
+  // By default the stream-ordered pool returns freed memory to the OS at every synchronisation,
+  // which turns each temporary into a driver allocation (measured: graph build 2.8 -> 26 ms/step).
+  static void keep_pool_warm() {
+    static bool done = false;
+    if (done) return;
+    done = true;
+    int dev = 0;
+    cudaMemPool_t pool;
+    if (cudaGetDevice(&dev) == cudaSuccess && cudaDeviceGetDefaultMemPool(&pool, dev) == cudaSuccess) {
+      unsigned long long threshold = ~0ull;
+      cudaMemPoolSetAttribute(pool, cudaMemPoolAttrReleaseThreshold, &threshold);
+    }
   }
   template <typename T>
   T* as() const { return reinterpret_cast<T*>(ptr); }

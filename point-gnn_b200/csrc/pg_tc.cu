@@ -24,8 +24,26 @@
 //
 // Operand layout (no swizzle, K-major): 8-row x 16-byte core matrices, 128 contiguous bytes each;
 // A stage: core(rg, kc) at rg*256 + kc*128; resident B: core(g, kc) at g*(KP/8)*128 + kc*128.
+#include <atomic>
+
 #include "pg_common.cuh"
 #include "pg_umma.cuh"
+
+extern "C" int pg_tc_available(void) {
+  int dev = 0, major = 0;
+  if (cudaGetDevice(&dev) != cudaSuccess) return 0;
+  if (cudaDeviceGetAttribute(&major, cudaDevAttrComputeCapabilityMajor, dev) != cudaSuccess) return 0;
+  return major == 10 ? 1 : 0;
+}
+
+namespace pg {
+static std::atomic<long long> g_tc_launches[2];   // [0] fused edge kernel, [1] dense-layer kernel
+}
+
+// tcgen05 kernel launches so far: which = 0 fused edge (segment-max) kernel, 1 dense-layer kernel
+extern "C" int64_t pg_tc_launch_count(int32_t which) {
+  return (which == 0 || which == 1) ? pg::g_tc_launches[which].load(std::memory_order_relaxed) : -1;
+}
 
 namespace pg {
 
@@ -40,38 +58,55 @@ int edge_mlp_max_fp32(int mode, const float* features, int c_in, const float* xy
 namespace {
 using namespace umma;
 
-constexpr int kStages = 4;
-constexpr int kEpiWarps = 4;
-constexpr int kProdWarps = 8;
-constexpr int kThreads = (kEpiWarps + 1 + kProdWarps) * 32;  // 416
+constexpr int kStages = 3;
+constexpr int kEpiWarps = 8;     // warps 0-7: warp w drains TMEM lane quarter (w & 3), column chunks of parity (w >> 2)
+constexpr int kMmaWarp = 8;
+constexpr int kProdWarps = 8;    // warps 9-16
+constexpr int kThreads = (kEpiWarps + 1 + kProdWarps) * 32;  // 544
 constexpr int kStageBytes = 8192;                            // A hi (4096) + A lo (4096): 128 rows x 16 k
-constexpr int kTileRows = 128;                               // edges per CTA per pair-tile
+constexpr int kTileRows = 128;                               // rows (edges) per CTA per pair-tile
+constexpr int kScratchFloats = 16 * 33;                      // per epilogue warp: 16 columns x 32 rows (+1 pad)
 
-struct TcEdgeParams {
-  const float* P;         // [num_src, ldp] = F @ W1[:C] + b1, zero padded to ldp = KP
+enum { PROD_GNN = 0, PROD_ROWS = 1, PROD_POOL = 2 };
+constexpr int kPoolC1 = 32, kPoolC2 = 64, kPoolC3 = 128;   // point MLP widths the pooling producer is built for
+constexpr int kPoolWFloats = 4 * kPoolC1 + kPoolC1 + kPoolC1 * kPoolC2 + kPoolC2 + kPoolC2 * kPoolC3 + kPoolC3;
+enum { EPI_SEGMAX = 0, EPI_STORE = 1 };
+
+struct TcParams {
+  // A-operand producer
+  const float* P;         // GNN: [num_src, ldp] = F @ W1[:C] + b1 (zero padded to ldp = kp);  ROWS: x [num_rows, ldp]
   int ldp;
+  int k_real;             // ROWS: true K (multiple of 4)
   const float* xyz_src;   // [num_src, 3]
-  const float* xyz_dst;   // [num_dst', 3] (already offset)
+  const float* xyz_dst;   // [*, 3] (already offset)
   const int32_t* dst_index;  // optional indirection dst -> row of xyz_dst
   const int32_t* src;
   const int32_t* dst;
-  int64_t num_edges, num_src, num_dst;
-  const float* w1x;       // [3, kp] zero padded
-  const float* b2;        // [np] zero padded
+  int64_t num_rows;       // edges (GNN) or matrix rows (ROWS)
+  int64_t num_src, num_dst;
+  const float* w1x;       // [3, kp] zero padded (GNN)
+  const float* pool_w;    // POOL: packed [W1 4x32 | b1 | W2 32x64 | b2 | W3 64x128 | b3] (fp32)
+  const float* pool_feat; // POOL: point features [num_src, 1]
+  // GEMM shape
+  const float* bias;      // [np] zero padded
   int kp, ks;             // padded K, k-steps (kp / 16)
   int n, np, n1, n2;      // real N, padded N, instruction split
   const uint8_t* wimg;    // per rank: [hi part | lo part], each part_bytes
   uint32_t part_bytes;
   uint32_t tmem_cols;
-  float* out;             // [num_dst, n], pre-filled with -FLT_MAX
+  // epilogue
+  float* out;             // SEGMAX: [num_dst, n] pre-filled with -FLT_MAX;  STORE: [num_rows, ldo]
+  int ldo;
+  int act;                // STORE: 0 linear, 1 relu
+  const float* residual;  // STORE: optional [num_rows, n]
   int* err;
   int64_t num_pair_tiles;
 };
 
-// ---- W2 -> resident B image -------------------------------------------------------------------
-// w2 is [K, N] row-major fp32.  B operand rows are OUTPUT features (N), K-major.  Rank r of the
-// pair holds rows [r*N1/2, (r+1)*N1/2) of instruction 1 followed by [N1 + r*N2/2, ...) of
-// instruction 2, as 8-row groups g: core(g, kc) at g*sbo + kc*128, element (row%8)*16 + (k%8)*2.
+// ---- W [K, N] -> resident B image ---------------------------------------------------------------
+// B operand rows are OUTPUT features (N), K-major.  Rank r of the pair holds rows
+// [r*N1/2, (r+1)*N1/2) of instruction 1 followed by [N1 + r*N2/2, ...) of instruction 2, as 8-row
+// groups g: core(g, kc) at g*sbo + kc*128, element (row%8)*16 + (k%8)*2.  hi / lo = BF16 split.
 __global__ void pack_w2_kernel(const float* __restrict__ w2, int k, int n, int kp, int n1, int n2,
                                uint8_t* __restrict__ img, uint32_t part_bytes) {
   const int rows_per_rank = (n1 + n2) / 2;
@@ -103,27 +138,130 @@ __global__ void pad_rows_kernel(const float* __restrict__ in, int rows, int cols
   }
 }
 
-__device__ __forceinline__ float redux_max_f32(float v, uint32_t mask) {
-  float r;
-  asm volatile("redux.sync.max.f32 %0, %1, %2;" : "=f"(r) : "f"(v), "r"(mask));
-  return r;
+struct SmemMap {
+  uint8_t* bres;
+  uint8_t* a;
+  float* w1x;
+  float* bias;
+  float* scratch;
+  int* dstw;
+  uint64_t* bar_full;      // [kStages]   (leader)
+  uint64_t* bar_empty;     // [kStages]
+  uint64_t* bar_tmem_full;
+  uint64_t* bar_i1_empty;  // [2]         (leader)
+  uint64_t* bar_i2_empty;  //             (leader)
+  uint64_t* bar_wres;
+  uint32_t* tmem;
+};
+
+__host__ __device__ inline size_t smem_layout(uint8_t* base, int kp, int np, uint32_t part_bytes, SmemMap* m,
+                                              int prod = PROD_GNN) {
+  size_t off = 0;
+  auto take = [&](size_t bytes) { size_t o = off; off += (bytes + 15) & ~size_t(15); return o; };
+  const size_t o_bres = take(2 * size_t(part_bytes));
+  const size_t o_a = take(size_t(kStages) * kStageBytes);
+  const size_t o_w1x = take((prod == PROD_POOL ? size_t(kPoolWFloats) : size_t(3) * kp) * sizeof(float));
+  const size_t o_bias = take(size_t(np) * sizeof(float));
+  const size_t o_scr = take(size_t(kEpiWarps) * kScratchFloats * sizeof(float));
+  const size_t o_dst = take(size_t(kEpiWarps) * 32 * sizeof(int));
+  const size_t o_bar = take((2 * kStages + 5) * sizeof(uint64_t));
+  const size_t o_tmem = take(16);
+  if (m != nullptr) {
+    m->bres = base + o_bres;
+    m->a = base + o_a;
+    m->w1x = reinterpret_cast<float*>(base + o_w1x);
+    m->bias = reinterpret_cast<float*>(base + o_bias);
+    m->scratch = reinterpret_cast<float*>(base + o_scr);
+    m->dstw = reinterpret_cast<int*>(base + o_dst);
+    uint64_t* bars = reinterpret_cast<uint64_t*>(base + o_bar);
+    m->bar_full = bars;
+    m->bar_empty = bars + kStages;
+    m->bar_tmem_full = bars + 2 * kStages;
+    m->bar_i1_empty = bars + 2 * kStages + 1;
+    m->bar_i2_empty = bars + 2 * kStages + 3;
+    m->bar_wres = bars + 2 * kStages + 4;
+    m->tmem = reinterpret_cast<uint32_t*>(base + o_tmem);
+  }
+  return off;
 }
 
-__global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kThreads, 1) edge_gnn_tc_kernel(TcEdgeParams p) {
-  extern __shared__ __align__(1024) uint8_t smem_raw[];
-  // carve-up (all offsets identical in both CTAs of the pair: cta_group::2 requires it)
-  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
-  uint8_t* s_bres = smem;                                   // 2 * part_bytes
-  uint8_t* s_a = s_bres + 2 * size_t(p.part_bytes);         // kStages * kStageBytes
-  float* s_w1x = reinterpret_cast<float*>(s_a + kStages * kStageBytes);   // 3 * kp
-  float* s_b2 = s_w1x + 3 * p.kp;                                         // np
-  uint64_t* bars = reinterpret_cast<uint64_t*>(s_b2 + p.np + (p.np & 1));
-  uint64_t* bar_full = bars;                 // [kStages]  (used in the leader CTA)
-  uint64_t* bar_empty = bars + kStages;      // [kStages]
-  uint64_t* bar_tmem_full = bars + 2 * kStages;
-  uint64_t* bar_tmem_empty = bars + 2 * kStages + 1;   // (leader)
-  uint64_t* bar_wres = bars + 2 * kStages + 2;
-  uint32_t* s_tmem = reinterpret_cast<uint32_t*>(bars + 2 * kStages + 3);
+// One 16-column chunk of the accumulator, segment-max flavour.  Thread = TMEM lane = tile row.
+// The chunk is transposed through a warp-private shared-memory scratch so that each lane then owns
+// one COLUMN and walks 16 rows with a running max (half-warp h covers rows 16h..16h+15); a max is
+// flushed (bias + relu + atomicMax) only where the destination changes (bm = boundary bit mask).
+__device__ __forceinline__ void epi_chunk_segmax(const TcParams& p, const SmemMap& sm, uint32_t taddr, int c_out,
+                                                  float* scratch, const int* sd, uint32_t bm, int lane) {
+  uint32_t v[16];
+  tmem_ld16(taddr, v);
+  tmem_ld_wait();
+#pragma unroll
+  for (int j = 0; j < 16; ++j) scratch[j * 33 + lane] = __uint_as_float(v[j]);
+  __syncwarp();
+  const int jj = lane & 15, h = lane >> 4;
+  const float* col = scratch + jj * 33 + 16 * h;
+  const int c = c_out + jj;
+  const bool col_ok = c < p.n;
+  const float bias = col_ok ? sm.bias[c] : 0.0f;
+  int cur = sd[16 * h];
+  float m = -FLT_MAX;
+#pragma unroll
+  for (int i = 0; i < 16; ++i) {
+    if (i > 0 && ((bm >> i) & 1u)) {
+      if (cur >= 0 && col_ok)
+        atomicMax(reinterpret_cast<int*>(p.out + int64_t(cur) * p.n + c), __float_as_int(fmaxf(m + bias, 0.0f)));
+      cur = sd[16 * h + i];
+      m = -FLT_MAX;
+    }
+    m = fmaxf(m, col[i]);
+  }
+  if (cur >= 0 && col_ok)
+    atomicMax(reinterpret_cast<int*>(p.out + int64_t(cur) * p.n + c), __float_as_int(fmaxf(m + bias, 0.0f)));
+  __syncwarp();
+}
+
+// Plain GEMM epilogue: out[row, c] = act(acc + bias[c]) (+ residual[row, c]).
+__device__ __forceinline__ void epi_chunk_store(const TcParams& p, const SmemMap& sm, uint32_t taddr, int c_out,
+                                                 int64_t row, bool row_ok) {
+  uint32_t v[16];
+  tmem_ld16(taddr, v);
+  tmem_ld_wait();
+  if (!row_ok) return;
+  float* o = p.out + row * p.ldo + c_out;
+  const float* res = p.residual ? p.residual + row * p.n + c_out : nullptr;
+  const bool vec = ((p.n & 3) == 0) && ((p.ldo & 3) == 0);
+#pragma unroll
+  for (int j4 = 0; j4 < 16; j4 += 4) {
+    float r[4];
+#pragma unroll
+    for (int j = 0; j < 4; ++j) {
+      const int c = c_out + j4 + j;
+      float t = __uint_as_float(v[j4 + j]) + (c < p.np ? sm.bias[c] : 0.0f);
+      if (p.act == 1) t = fmaxf(t, 0.0f);
+      r[j] = t;
+    }
+    if (vec) {
+      if (c_out + j4 + 3 < p.n) {
+        if (res) {
+          const float4 q = *reinterpret_cast<const float4*>(res + j4);
+          r[0] += q.x; r[1] += q.y; r[2] += q.z; r[3] += q.w;
+        }
+        *reinterpret_cast<float4*>(o + j4) = make_float4(r[0], r[1], r[2], r[3]);
+      }
+    } else {
+#pragma unroll
+      for (int j = 0; j < 4; ++j)
+        if (c_out + j4 + j < p.n) o[j4 + j] = r[j] + (res ? res[j4 + j] : 0.0f);
+    }
+  }
+}
+
+template <int kProd, int kEpi>
+__global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kThreads, 1) row_gemm_tc_kernel(TcParams p) {
+  // No-swizzle operands, bulk copies and mbarriers only need 16-byte alignment; the carve-up is
+  // identical in both CTAs of the pair (cta_group::2 addresses the peer's operands by offset).
+  extern __shared__ __align__(128) uint8_t smem_raw[];
+  SmemMap sm;
+  smem_layout(smem_raw, p.kp, p.np, p.part_bytes, &sm, kProd);
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const uint32_t rank = cluster_ctarank();
@@ -131,37 +269,45 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kThreads, 1) edge_gn
   const int64_t num_clusters = gridDim.x >> 1;
 
   // ---- prologue ------------------------------------------------------------------------------
-  for (int i = threadIdx.x; i < 3 * p.kp; i += kThreads) s_w1x[i] = p.w1x[i];
-  for (int i = threadIdx.x; i < p.np; i += kThreads) s_b2[i] = p.b2[i];
+  if (kProd == PROD_GNN)
+    for (int i = threadIdx.x; i < 3 * p.kp; i += kThreads) sm.w1x[i] = p.w1x[i];
+  if (kProd == PROD_POOL)
+    for (int i = threadIdx.x; i < kPoolWFloats; i += kThreads) sm.w1x[i] = p.pool_w[i];
+  for (int i = threadIdx.x; i < p.np; i += kThreads) sm.bias[i] = p.bias[i];
   if (threadIdx.x == 0) {
     for (int i = 0; i < kStages; ++i) {
-      mbar_init(&bar_full[i], 2 * kProdWarps);
-      mbar_init(&bar_empty[i], 1);
+      mbar_init(&sm.bar_full[i], 2 * kProdWarps);
+      mbar_init(&sm.bar_empty[i], 1);
     }
-    mbar_init(bar_tmem_full, 1);
-    mbar_init(bar_tmem_empty, 2 * kEpiWarps);
-    mbar_init(bar_wres, 1);
+    mbar_init(sm.bar_tmem_full, 1);
+    mbar_init(&sm.bar_i1_empty[0], 2 * kEpiWarps);
+    mbar_init(&sm.bar_i1_empty[1], 2 * kEpiWarps);
+    mbar_init(sm.bar_i2_empty, 2 * kEpiWarps);
+    mbar_init(sm.bar_wres, 1);
     fence_barrier_init();
   }
-  if (warp == kEpiWarps) {
-    tmem_alloc<2>(s_tmem, p.tmem_cols);
+  if (warp == kMmaWarp) {
+    tmem_alloc<2>(sm.tmem, p.tmem_cols);
     tmem_relinquish<2>();
   }
   tc_fence_before();
   __syncthreads();
   cluster_sync();
   tc_fence_after();
-  const uint32_t tmem = *s_tmem;
+  const uint32_t tmem = *sm.tmem;
+  // accumulator columns: instruction 1 is double buffered (a / b), instruction 2 single
+  const uint32_t col_i1[2] = {0u, uint32_t(p.n1 + p.n2)};
+  const uint32_t col_i2 = uint32_t(p.n1);
 
-  if (warp == kEpiWarps) {
+  if (warp == kMmaWarp) {
     // =================================== MMA warp =============================================
     if (lane == 0) {
       // resident weights: one bulk copy per part into this CTA's shared memory
-      mbar_arrive_expect_tx(bar_wres, 2 * p.part_bytes);
+      mbar_arrive_expect_tx(sm.bar_wres, 2 * p.part_bytes);
       const uint8_t* g = p.wimg + size_t(rank) * 2 * p.part_bytes;
-      bulk_g2s(s_bres, g, p.part_bytes, bar_wres);
-      bulk_g2s(s_bres + p.part_bytes, g + p.part_bytes, p.part_bytes, bar_wres);
-      mbar_wait(bar_wres, 0);
+      bulk_g2s(sm.bres, g, p.part_bytes, sm.bar_wres);
+      bulk_g2s(sm.bres + p.part_bytes, g + p.part_bytes, p.part_bytes, sm.bar_wres);
+      mbar_wait(sm.bar_wres, 0);
     }
     __syncwarp();
     cluster_sync();   // both CTAs' weights are resident before the leader issues any MMA   [sync A]
@@ -169,87 +315,90 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kThreads, 1) edge_gn
       const uint32_t idesc1 = make_idesc_bf16(256, p.n1);
       const uint32_t idesc2 = make_idesc_bf16(256, p.n2 > 0 ? p.n2 : 16);
       const uint32_t sbo_b = uint32_t(p.kp / 8) * 128u;
-      const uint32_t b_hi = smem_u32(s_bres), b_lo = b_hi + p.part_bytes;
+      const uint32_t b_hi = smem_u32(sm.bres), b_lo = b_hi + p.part_bytes;
       const uint32_t b2_off = uint32_t(p.n1 / 16) * sbo_b;   // first row group of instruction 2
       uint32_t it = 0;
       uint32_t tile_iter = 0;
       for (int64_t tile = cluster_id; tile < p.num_pair_tiles; tile += num_clusters, ++tile_iter) {
-        mbar_wait_cluster(bar_tmem_empty, (tile_iter & 1) ^ 1);
+        const uint32_t buf = tile_iter & 1u;
+        mbar_wait(&sm.bar_i1_empty[buf], ((tile_iter >> 1) & 1u) ^ 1u);
+        if (p.n2 > 0) mbar_wait(sm.bar_i2_empty, (tile_iter & 1u) ^ 1u);
         tc_fence_after();
+        const uint32_t d1 = tmem + col_i1[buf], d2 = tmem + col_i2;
         for (int s = 0; s < p.ks; ++s, ++it) {
           const uint32_t stage = it % kStages;
-          mbar_wait_cluster(&bar_full[stage], (it / kStages) & 1);
+          mbar_wait(&sm.bar_full[stage], (it / kStages) & 1u);
           tc_fence_after();
-          const uint32_t a_hi = smem_u32(s_a + stage * kStageBytes), a_lo = a_hi + kStageBytes / 2;
+          const uint32_t a_hi = smem_u32(sm.a + stage * kStageBytes), a_lo = a_hi + kStageBytes / 2;
           const uint64_t da_hi = make_smem_desc(a_hi, 128, 256);
           const uint64_t da_lo = make_smem_desc(a_lo, 128, 256);
           const uint32_t koff = uint32_t(s) * 256u;   // two K-adjacent cores per k-step
           {
             const uint64_t db_hi = make_smem_desc(b_hi + koff, 128, sbo_b);
             const uint64_t db_lo = make_smem_desc(b_lo + koff, 128, sbo_b);
-            mma_bf16<2>(tmem, da_hi, db_hi, idesc1, s > 0);
-            mma_bf16<2>(tmem, da_lo, db_hi, idesc1, true);
-            mma_bf16<2>(tmem, da_hi, db_lo, idesc1, true);
+            mma_bf16<2>(d1, da_hi, db_hi, idesc1, s > 0);
+            mma_bf16<2>(d1, da_lo, db_hi, idesc1, true);
+            mma_bf16<2>(d1, da_hi, db_lo, idesc1, true);
           }
           if (p.n2 > 0) {
             const uint64_t db_hi = make_smem_desc(b_hi + b2_off + koff, 128, sbo_b);
             const uint64_t db_lo = make_smem_desc(b_lo + b2_off + koff, 128, sbo_b);
-            mma_bf16<2>(tmem + p.n1, da_hi, db_hi, idesc2, s > 0);
-            mma_bf16<2>(tmem + p.n1, da_lo, db_hi, idesc2, true);
-            mma_bf16<2>(tmem + p.n1, da_hi, db_lo, idesc2, true);
+            mma_bf16<2>(d2, da_hi, db_hi, idesc2, s > 0);
+            mma_bf16<2>(d2, da_lo, db_hi, idesc2, true);
+            mma_bf16<2>(d2, da_hi, db_lo, idesc2, true);
           }
-          mma_commit_2cta(&bar_empty[stage], 0x3);    // frees this A stage in both CTAs
+          mma_commit_2cta(&sm.bar_empty[stage], 0x3);    // frees this A stage in both CTAs
         }
-        mma_commit_2cta(bar_tmem_full, 0x3);          // accumulators of this tile are complete
+        mma_commit_2cta(sm.bar_tmem_full, 0x3);          // accumulators of this tile are complete
       }
     }
     __syncwarp();
   } else if (warp < kEpiWarps) {
     // =================================== epilogue warps =======================================
     cluster_sync();   // [sync A]
+    const int quarter = warp & 3, par = warp >> 2;
+    float* scratch = sm.scratch + warp * kScratchFloats;
+    int* sd = sm.dstw + warp * 32;
+    const uint32_t lane_base = uint32_t(quarter * 32) << 16;
     uint32_t tile_iter = 0;
     for (int64_t tile = cluster_id; tile < p.num_pair_tiles; tile += num_clusters, ++tile_iter) {
-      const int64_t row = tile * 256 + int64_t(rank) * kTileRows + warp * 32 + lane;
-      int d = -1;
-      if (row < p.num_edges) {
-        d = p.dst[row];
-        if (d < 0 || d >= p.num_dst) { *p.err = 1; d = -1; }
-      }
-      const uint32_t my_mask = __match_any_sync(0xffffffffu, d);
-      const int my_rank = __popc(my_mask & ((1u << lane) - 1u));
-      const int my_count = __popc(my_mask);
-      mbar_wait(bar_tmem_full, tile_iter & 1);
-      tc_fence_after();
-      const uint32_t taddr = tmem + (uint32_t(warp * 32) << 16);
-      for (int c0 = 0; c0 < p.np; c0 += 16) {
-        uint32_t v[16];
-        tmem_ld16(taddr + c0, v);
-        tmem_ld_wait();
-        // segments of this warp: iterate distinct match masks (warp-uniform loop)
-        uint32_t remaining = 0xffffffffu;
-        while (remaining) {
-          const int leader = __ffs(remaining) - 1;
-          const uint32_t m = __shfl_sync(0xffffffffu, my_mask, leader);
-          const int seg_dst = __shfl_sync(0xffffffffu, d, leader);
-          remaining &= ~m;
-          if (seg_dst < 0) continue;
-          if (my_mask == m) {
-            float* orow = p.out + int64_t(seg_dst) * p.n;
-#pragma unroll
-            for (int j = 0; j < 16; ++j) {
-              const float r = redux_max_f32(__uint_as_float(v[j]), m);
-              const int c = c0 + j;
-              if ((j % my_count) == my_rank && c < p.n) {
-                const float val = fmaxf(r + s_b2[c], 0.0f);
-                atomicMax(reinterpret_cast<int*>(orow + c), __float_as_int(val));
-              }
-            }
-          }
+      const uint32_t buf = tile_iter & 1u;
+      const int64_t row = tile * 256 + int64_t(rank) * kTileRows + quarter * 32 + lane;
+      const bool row_ok = row < p.num_rows;
+      uint32_t bm = 0;
+      if (kEpi == EPI_SEGMAX) {
+        int d = -1;
+        if (row_ok) {
+          d = p.dst[row];
+          if (d < 0 || d >= p.num_dst) { *p.err = 1; d = -1; }
         }
+        sd[lane] = d;
+        __syncwarp();
+        const int h = lane >> 4;
+#pragma unroll
+        for (int i = 1; i < 16; ++i) bm |= (sd[16 * h + i] != sd[16 * h + i - 1]) ? (1u << i) : 0u;
+      }
+      mbar_wait(sm.bar_tmem_full, tile_iter & 1u);
+      tc_fence_after();
+      // ---- instruction-2 columns first: they are single buffered, free them as early as possible
+      if (p.n2 > 0) {
+        for (int ci = par; ci * 16 < p.n2; ci += 2) {
+          const uint32_t taddr = tmem + lane_base + col_i2 + ci * 16;
+          if (kEpi == EPI_SEGMAX) epi_chunk_segmax(p, sm, taddr, p.n1 + ci * 16, scratch, sd, bm, lane);
+          else epi_chunk_store(p, sm, taddr, p.n1 + ci * 16, row, row_ok);
+        }
+        tc_fence_before();
+        __syncwarp();
+        if (lane == 0) mbar_arrive_cluster(sm.bar_i2_empty, 0);
+      }
+      for (int ci = par; ci * 16 < p.n1; ci += 2) {
+        const uint32_t taddr = tmem + lane_base + col_i1[buf] + ci * 16;
+        if (kEpi == EPI_SEGMAX) epi_chunk_segmax(p, sm, taddr, ci * 16, scratch, sd, bm, lane);
+        else epi_chunk_store(p, sm, taddr, ci * 16, row, row_ok);
       }
       tc_fence_before();
       __syncwarp();
-      if (lane == 0) mbar_arrive_cluster(bar_tmem_empty, 0);
+      if (lane == 0) mbar_arrive_cluster(&sm.bar_i1_empty[buf], 0);
     }
   } else {
     // =================================== producer warps =======================================
@@ -261,52 +410,133 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kThreads, 1) edge_gn
     uint32_t it = 0;
     for (int64_t tile = cluster_id; tile < p.num_pair_tiles; tile += num_clusters) {
       const int64_t row = tile * 256 + int64_t(rank) * kTileRows + r;
-      bool valid = row < p.num_edges;
+      bool valid = row < p.num_rows;
+      float rx = 0.f, ry = 0.f, rz = 0.f;
+      const float* prow = p.P;
       int sidx = 0, didx = 0;
-      if (valid) {
-        sidx = p.src[row];
-        didx = p.dst[row];
-        if (sidx < 0 || sidx >= p.num_src || didx < 0 || didx >= p.num_dst) { *p.err = 1; valid = false; sidx = 0; didx = 0; }
+      if (kProd != PROD_ROWS) {
+        if (valid) {
+          sidx = p.src[row];
+          didx = p.dst[row];
+          if (sidx < 0 || sidx >= p.num_src || didx < 0 || didx >= p.num_dst) { *p.err = 1; valid = false; sidx = 0; didx = 0; }
+        }
+        const int64_t drow = p.dst_index ? int64_t(p.dst_index[didx]) : int64_t(didx);
+        rx = p.xyz_src[int64_t(sidx) * 3 + 0] - p.xyz_dst[drow * 3 + 0];
+        ry = p.xyz_src[int64_t(sidx) * 3 + 1] - p.xyz_dst[drow * 3 + 1];
+        rz = p.xyz_src[int64_t(sidx) * 3 + 2] - p.xyz_dst[drow * 3 + 2];
+        if (kProd == PROD_GNN) prow = p.P + int64_t(sidx) * p.ldp + kc * 8;
+      } else {
+        prow = p.P + (valid ? row : 0) * int64_t(p.ldp) + kc * 8;
       }
-      const int64_t drow = p.dst_index ? int64_t(p.dst_index[didx]) : int64_t(didx);
-      const float rx = p.xyz_src[int64_t(sidx) * 3 + 0] - p.xyz_dst[drow * 3 + 0];
-      const float ry = p.xyz_src[int64_t(sidx) * 3 + 1] - p.xyz_dst[drow * 3 + 1];
-      const float rz = p.xyz_src[int64_t(sidx) * 3 + 2] - p.xyz_dst[drow * 3 + 2];
-      const float* prow = p.P + int64_t(sidx) * p.ldp + kc * 8;
-      float4 n0 = *reinterpret_cast<const float4*>(prow);
-      float4 n1 = *reinterpret_cast<const float4*>(prow + 4);
-      for (int s = 0; s < p.ks; ++s, ++it) {
-        const float4 c0 = n0, c1 = n1;
-        if (s + 1 < p.ks) {   // prefetch the next k-step's slice of P[src]
-          n0 = *reinterpret_cast<const float4*>(prow + (s + 1) * 16);
-          n1 = *reinterpret_cast<const float4*>(prow + (s + 1) * 16 + 4);
-        }
-        const int k0 = s * 16 + kc * 8;
-        const float* wx = s_w1x + k0;
-        const float* wy = s_w1x + p.kp + k0;
-        const float* wz = s_w1x + 2 * p.kp + k0;
-        float h[8];
-        const float pv[8] = {c0.x, c0.y, c0.z, c0.w, c1.x, c1.y, c1.z, c1.w};
-#pragma unroll
-        for (int j = 0; j < 8; ++j) {
-          float t = fmaf(rx, wx[j], pv[j]);
-          t = fmaf(ry, wy[j], t);
-          t = fmaf(rz, wz[j], t);
-          h[j] = valid ? fmaxf(t, 0.0f) : 0.0f;
-        }
+      // hand one k-step (8 values of this thread's row) to the tensor core
+      auto publish = [&](const float (&h)[8]) {
         uint4 hi, lo;
         split_bf16x2(h[0], h[1], &hi.x, &lo.x);
         split_bf16x2(h[2], h[3], &hi.y, &lo.y);
         split_bf16x2(h[4], h[5], &hi.z, &lo.z);
         split_bf16x2(h[6], h[7], &hi.w, &lo.w);
         const uint32_t stage = it % kStages;
-        mbar_wait(&bar_empty[stage], ((it / kStages) & 1) ^ 1);
-        uint8_t* st = s_a + stage * kStageBytes + a_off;
+        mbar_wait(&sm.bar_empty[stage], ((it / kStages) & 1u) ^ 1u);
+        uint8_t* st = sm.a + stage * kStageBytes + a_off;
         *reinterpret_cast<uint4*>(st) = hi;
         *reinterpret_cast<uint4*>(st + kStageBytes / 2) = lo;
         fence_proxy_async_smem();
         __syncwarp();
-        if (lane == 0) mbar_arrive_cluster(&bar_full[stage], 0);
+        if (lane == 0) mbar_arrive_cluster(&sm.bar_full[stage], 0);
+        ++it;
+      };
+      if (kProd == PROD_POOL) {
+        // per-edge point MLP 4 -> 32 -> 64 (registers), then 64 -> 128 eight outputs per k-step;
+        // weights are warp-uniform shared-memory broadcasts.  gnn.py:264-274 (layers 1-3 of 4).
+        const float* w1 = sm.w1x;
+        const float* b1 = w1 + 4 * kPoolC1;
+        const float* w2 = b1 + kPoolC1;
+        const float* b2 = w2 + kPoolC1 * kPoolC2;
+        const float* w3 = b2 + kPoolC2;
+        const float* b3 = w3 + kPoolC2 * kPoolC3;
+        const float f0 = p.pool_feat[sidx];
+        float h2[kPoolC2];
+#pragma unroll
+        for (int j = 0; j < kPoolC2; ++j) h2[j] = b2[j];
+#pragma unroll 4
+        for (int i = 0; i < kPoolC1; ++i) {
+          float t = b1[i];
+          t = fmaf(f0, w1[i], t);
+          t = fmaf(rx, w1[kPoolC1 + i], t);
+          t = fmaf(ry, w1[2 * kPoolC1 + i], t);
+          t = fmaf(rz, w1[3 * kPoolC1 + i], t);
+          t = fmaxf(t, 0.0f);
+          const float4* wr = reinterpret_cast<const float4*>(w2 + i * kPoolC2);
+#pragma unroll
+          for (int j4 = 0; j4 < kPoolC2 / 4; ++j4) {
+            const float4 q = wr[j4];
+            h2[4 * j4 + 0] = fmaf(t, q.x, h2[4 * j4 + 0]);
+            h2[4 * j4 + 1] = fmaf(t, q.y, h2[4 * j4 + 1]);
+            h2[4 * j4 + 2] = fmaf(t, q.z, h2[4 * j4 + 2]);
+            h2[4 * j4 + 3] = fmaf(t, q.w, h2[4 * j4 + 3]);
+          }
+        }
+#pragma unroll
+        for (int j = 0; j < kPoolC2; ++j) h2[j] = fmaxf(h2[j], 0.0f);
+        for (int s = 0; s < p.ks; ++s) {
+          const int k0 = s * 16 + kc * 8;
+          float acc[8];
+#pragma unroll
+          for (int j = 0; j < 8; ++j) acc[j] = b3[k0 + j];
+#pragma unroll
+          for (int i = 0; i < kPoolC2; ++i) {
+            const float4 q0 = *reinterpret_cast<const float4*>(w3 + i * kPoolC3 + k0);
+            const float4 q1 = *reinterpret_cast<const float4*>(w3 + i * kPoolC3 + k0 + 4);
+            acc[0] = fmaf(h2[i], q0.x, acc[0]);
+            acc[1] = fmaf(h2[i], q0.y, acc[1]);
+            acc[2] = fmaf(h2[i], q0.z, acc[2]);
+            acc[3] = fmaf(h2[i], q0.w, acc[3]);
+            acc[4] = fmaf(h2[i], q1.x, acc[4]);
+            acc[5] = fmaf(h2[i], q1.y, acc[5]);
+            acc[6] = fmaf(h2[i], q1.z, acc[6]);
+            acc[7] = fmaf(h2[i], q1.w, acc[7]);
+          }
+          float h[8];
+#pragma unroll
+          for (int j = 0; j < 8; ++j) h[j] = valid ? fmaxf(acc[j], 0.0f) : 0.0f;
+          publish(h);
+        }
+      } else {
+        auto load_chunk = [&](int s, float4& q0, float4& q1) {
+          if (kProd == PROD_GNN) {
+            q0 = *reinterpret_cast<const float4*>(prow + s * 16);
+            q1 = *reinterpret_cast<const float4*>(prow + s * 16 + 4);
+          } else {
+            const int k0 = s * 16 + kc * 8;
+            q0 = (k0 + 4 <= p.k_real) ? *reinterpret_cast<const float4*>(prow + s * 16) : make_float4(0.f, 0.f, 0.f, 0.f);
+            q1 = (k0 + 8 <= p.k_real) ? *reinterpret_cast<const float4*>(prow + s * 16 + 4) : make_float4(0.f, 0.f, 0.f, 0.f);
+          }
+        };
+        float4 n0, n1;
+        load_chunk(0, n0, n1);
+        for (int s = 0; s < p.ks; ++s) {
+          const float4 c0 = n0, c1 = n1;
+          if (s + 1 < p.ks) load_chunk(s + 1, n0, n1);   // prefetch the next k-step's slice
+          float h[8];
+          const float pv[8] = {c0.x, c0.y, c0.z, c0.w, c1.x, c1.y, c1.z, c1.w};
+          if (kProd == PROD_GNN) {
+            const int k0 = s * 16 + kc * 8;
+            const float* wx = sm.w1x + k0;
+            const float* wy = sm.w1x + p.kp + k0;
+            const float* wz = sm.w1x + 2 * p.kp + k0;
+#pragma unroll
+            for (int j = 0; j < 8; ++j) {
+              float t = fmaf(rx, wx[j], pv[j]);
+              t = fmaf(ry, wy[j], t);
+              t = fmaf(rz, wz[j], t);
+              h[j] = valid ? fmaxf(t, 0.0f) : 0.0f;
+            }
+          } else {
+#pragma unroll
+            for (int j = 0; j < 8; ++j) h[j] = valid ? pv[j] : 0.0f;
+          }
+          publish(h);
+        }
       }
     }
   }
@@ -315,99 +545,195 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kThreads, 1) edge_gn
   tc_fence_before();
   __syncthreads();
   cluster_sync();
-  if (warp == kEpiWarps) tmem_dealloc<2>(tmem, p.tmem_cols);
+  if (warp == kMmaWarp) tmem_dealloc<2>(tmem, p.tmem_cols);
 }
 
-size_t tc_edge_smem_bytes(int kp, int np) {
-  const size_t part = size_t(np / 16) * size_t(kp / 8) * 128;
-  return 1024 + 2 * part + kStages * kStageBytes + (3 * kp + np + (np & 1)) * sizeof(float) + (2 * kStages + 3) * 8 + 16;
+size_t tc_smem_bytes(int kp, int np, int prod = PROD_GNN) {
+  const uint32_t part = uint32_t(np / 16) * uint32_t(kp / 8) * 128u;
+  return smem_layout(nullptr, kp, np, part, nullptr, prod);
+}
+
+struct TcShape {
+  int kp, np, n1, n2;
+  uint32_t part, tmem_cols;
+  bool ok;
+};
+
+TcShape tc_shape(int k, int n) {
+  TcShape t{};
+  t.kp = (k + 15) / 16 * 16;
+  t.np = (n + 15) / 16 * 16;
+  if (t.np <= 256) { t.n1 = t.np; t.n2 = 0; }
+  else { t.n1 = ((t.np / 2) + 15) / 16 * 16; t.n2 = t.np - t.n1; }
+  t.part = uint32_t(t.np / 16) * uint32_t(t.kp / 8) * 128u;
+  const int cols_needed = 2 * t.n1 + t.n2;
+  uint32_t cols = 32;
+  while (cols < uint32_t(cols_needed)) cols <<= 1;
+  t.tmem_cols = cols;
+  t.ok = pg_tc_available() && cols_needed <= 512 && t.n1 <= 256 && t.n2 <= 256 && t.kp / 16 > kStages && n >= 8 &&
+         tc_smem_bytes(t.kp, t.np) <= 227 * 1024;
+  return t;
+}
+
+template <int kProd, int kEpi>
+int launch_row_gemm(TcParams& p, const TcShape& t, const float* w, int k, int n, const float* bias, Temp& t_img,
+                    Temp& t_bias, cudaStream_t s) {
+  PG_CUDA_OK(t_bias.alloc(sizeof(float) * t.np, s));
+  pad_rows_kernel<<<2, 256, 0, s>>>(bias, 1, n, t.np, t_bias.as<float>());
+  PG_LAUNCH_CHECK();
+  PG_CUDA_OK(t_img.alloc(size_t(4) * t.part, s));
+  pack_w2_kernel<<<std::min(num_sms(), 64), 256, 0, s>>>(w, k, n, t.kp, t.n1, t.n2, t_img.as<uint8_t>(), t.part);
+  PG_LAUNCH_CHECK();
+  p.bias = t_bias.as<float>();
+  p.kp = t.kp;
+  p.ks = t.kp / 16;
+  p.n = n;
+  p.np = t.np;
+  p.n1 = t.n1;
+  p.n2 = t.n2;
+  p.wimg = t_img.as<uint8_t>();
+  p.part_bytes = t.part;
+  p.tmem_cols = t.tmem_cols;
+  p.num_pair_tiles = ceil_div(p.num_rows, 2 * kTileRows);
+  const size_t smem = tc_smem_bytes(t.kp, t.np, kProd);
+  PG_REQUIRE(smem <= 227 * 1024, "tcgen05 kernel needs %zu B of shared memory", smem);
+  PG_CUDA_OK(cudaFuncSetAttribute(row_gemm_tc_kernel<kProd, kEpi>, cudaFuncAttributeMaxDynamicSharedMemorySize, int(smem)));
+  const int clusters = int(std::min<int64_t>(p.num_pair_tiles, num_sms() / 2));
+  row_gemm_tc_kernel<kProd, kEpi><<<2 * clusters, kThreads, smem, s>>>(p);
+  PG_LAUNCH_CHECK();
+  g_tc_launches[kEpi == EPI_SEGMAX ? 0 : 1].fetch_add(1, std::memory_order_relaxed);
+  return PG_OK;
 }
 
 }  // namespace
 
-extern "C" int pg_tc_available(void) {
-  int dev = 0, major = 0;
-  if (cudaGetDevice(&dev) != cudaSuccess) return 0;
-  if (cudaDeviceGetAttribute(&major, cudaDevAttrComputeCapabilityMajor, dev) != cudaSuccess) return 0;
-  return major == 10 ? 1 : 0;
-}
-
 int fc_tc_bf16x3(const float* x, int64_t m, int k, const float* w, const float* bias, int n, int act,
                  const float* residual, float* out, cudaStream_t s) {
-  // The per-vertex layers are <1% of the frame's FLOPs; they run on the fp32 FFMA kernel (exact
-  // fp32, no split needed).  The tensor-core budget goes to the per-edge GEMMs.
-  return fc_fp32_launch(x, m, k, w, bias, n, act, residual, out, n, s);
+  const TcShape t = tc_shape(k, n);
+  // narrow / shallow layers (N < 8, K < 64: the 64->3, 64->4, 64->7 heads) stay on the fp32 FFMA kernel
+  if (!t.ok || (k & 3) != 0 || m < 1) return fc_fp32_launch(x, m, k, w, bias, n, act, residual, out, n, s);
+  TcParams p{};
+  p.P = x;
+  p.ldp = k;
+  p.k_real = k;
+  p.num_rows = m;
+  p.out = out;
+  p.ldo = n;
+  p.act = act;
+  p.residual = residual;
+  Temp t_img, t_bias;
+  return launch_row_gemm<PROD_ROWS, EPI_STORE>(p, t, w, k, n, bias, t_img, t_bias, s);
 }
 
 int edge_mlp_max_tc(int mode, const float* features, int c_in, const float* xyz_src, const float* xyz_dst,
                     const int32_t* dst_index, const int32_t* src, const int32_t* dst, int64_t num_edges,
                     int64_t num_src, int64_t num_dst, const float* const* weights, const float* const* biases,
                     const int32_t* dims, int num_layers, float* out, cudaStream_t s) {
-  bool fits = (mode == PG_EDGE_GNN) && num_layers == 2 && pg_tc_available();
-  int kp = 0, np = 0, n1 = 0, n2 = 0;
-  if (fits) {
-    kp = (dims[1] + 15) / 16 * 16;
-    np = (dims[2] + 15) / 16 * 16;
-    if (np <= 256) { n1 = np; n2 = 0; }
-    else { n1 = ((np / 2) + 15) / 16 * 16; n2 = np - n1; }
-    fits = np <= 512 && kp / 16 > kStages && tc_edge_smem_bytes(kp, np) <= 227 * 1024 && dims[1] >= 8;
+  TcShape t{};
+  const bool pool_tc = mode == PG_EDGE_POOL && num_layers == 4 && c_in == 1 && dims[1] == kPoolC1 &&
+                       dims[2] == kPoolC2 && dims[3] == kPoolC3;
+  if (mode == PG_EDGE_GNN && num_layers == 2) t = tc_shape(dims[1], dims[2]);
+  if (pool_tc) {
+    t = tc_shape(dims[3], dims[4]);
+    t.ok = t.ok && tc_smem_bytes(t.kp, t.np, PROD_POOL) <= 227 * 1024;
   }
-  if (!fits || num_edges == 0)
+  if (t.ok && pool_tc && num_edges > 0) {
+    // PointSetPooling (gnn.py:256-277): layers 1-3 of the point MLP run in the producer warps (FFMA),
+    // the 128 -> 300 layer (79% of the FLOPs) on the tensor cores, max / bias / relu in the epilogue.
+    Temp t_w, t_img, t_bias, t_err;
+    PG_CUDA_OK(t_w.alloc(sizeof(float) * kPoolWFloats, s));
+    float* pw = t_w.as<float>();
+    const int sizes[6] = {4 * kPoolC1, kPoolC1, kPoolC1 * kPoolC2, kPoolC2, kPoolC2 * kPoolC3, kPoolC3};
+    const float* srcs[6] = {weights[0], biases[0], weights[1], biases[1], weights[2], biases[2]};
+    size_t off = 0;
+    for (int i = 0; i < 6; ++i) {
+      PG_CUDA_OK(cudaMemcpyAsync(pw + off, srcs[i], sizeof(float) * sizes[i], cudaMemcpyDeviceToDevice, s));
+      off += sizes[i];
+    }
+    PG_CUDA_OK(t_err.alloc(sizeof(int), s));
+    PG_CUDA_OK(cudaMemsetAsync(t_err.ptr, 0, sizeof(int), s));
+    const int n = dims[4];
+    if (int rc = fill_async(out, num_dst * n, -FLT_MAX, s)) return rc;
+    TcParams p{};
+    p.pool_w = pw;
+    p.pool_feat = features;
+    p.xyz_src = xyz_src;
+    p.xyz_dst = xyz_dst;
+    p.dst_index = dst_index;
+    p.src = src;
+    p.dst = dst;
+    p.num_rows = num_edges;
+    p.num_src = num_src;
+    p.num_dst = num_dst;
+    p.out = out;
+    p.err = t_err.as<int>();
+    if (int rc = launch_row_gemm<PROD_POOL, EPI_SEGMAX>(p, t, weights[3], dims[3], n, biases[3], t_img, t_bias, s)) return rc;
+    int h = 0;
+    PG_CUDA_OK(cudaMemcpyAsync(&h, t_err.ptr, sizeof(int), cudaMemcpyDeviceToHost, s));
+    PG_CUDA_OK(cudaStreamSynchronize(s));
+    PG_REQUIRE(h == 0, "set index out of range (point in [0,%lld), keypoint in [0,%lld))", (long long)num_src,
+               (long long)num_dst);
+    return PG_OK;
+  }
+  if (!t.ok || pool_tc || num_edges == 0)
     return edge_mlp_max_fp32(mode, features, c_in, xyz_src, xyz_dst, dst_index, src, dst, num_edges, num_src,
                              num_dst, weights, biases, dims, num_layers, out, s);
   PG_REQUIRE(dims[0] == c_in + 3, "dims[0]=%d must equal feature channels + 3 = %d", dims[0], c_in + 3);
   const int d1 = dims[1], n = dims[2];
-  TcEdgeParams p{};
-  Temp t_p, t_w1x, t_b2, t_img, t_err;
-  // P = F @ W1[:C] + b1, row stride kp, pad columns zero
-  PG_CUDA_OK(t_p.alloc(sizeof(float) * num_src * kp, s));
-  if (int rc = fc_fp32_launch(features, num_src, c_in, weights[0], biases[0], d1, 0, nullptr, t_p.as<float>(), kp, s))
-    return rc;
-  PG_CUDA_OK(t_w1x.alloc(sizeof(float) * 3 * kp, s));
-  pad_rows_kernel<<<4, 256, 0, s>>>(weights[0] + int64_t(c_in) * d1, 3, d1, kp, t_w1x.as<float>());
-  PG_LAUNCH_CHECK();
-  PG_CUDA_OK(t_b2.alloc(sizeof(float) * np, s));
-  pad_rows_kernel<<<2, 256, 0, s>>>(biases[1], 1, n, np, t_b2.as<float>());
-  PG_LAUNCH_CHECK();
-  const uint32_t part = uint32_t(np / 16) * uint32_t(kp / 8) * 128u;
-  PG_CUDA_OK(t_img.alloc(size_t(4) * part, s));
-  pack_w2_kernel<<<std::min(num_sms(), 64), 256, 0, s>>>(weights[1], d1, n, kp, n1, n2, t_img.as<uint8_t>(), part);
+  Temp t_p, t_w1x, t_img, t_bias, t_err;
+  // hoisted first layer: P = F @ W1[:C] + b1 (row stride kp, pad columns zero) on the tensor cores too
+  PG_CUDA_OK(t_p.alloc(sizeof(float) * num_src * t.kp, s));
+  {
+    const TcShape tp = tc_shape(c_in, d1);
+    if (tp.ok && (c_in & 3) == 0 && t.kp == tp.np) {
+      TcParams q{};
+      q.P = features;
+      q.ldp = c_in;
+      q.k_real = c_in;
+      q.num_rows = num_src;
+      q.out = t_p.as<float>();
+      q.ldo = t.kp;
+      q.act = 0;
+      q.residual = nullptr;
+      Temp q_img, q_bias;
+      // n = kp here: the pad columns [d1, kp) get bias 0 and zero weights -> written as exact zeros
+      Temp w_pad, b_pad;
+      PG_CUDA_OK(w_pad.alloc(sizeof(float) * size_t(c_in) * t.kp, s));
+      pad_rows_kernel<<<64, 256, 0, s>>>(weights[0], c_in, d1, t.kp, w_pad.as<float>());
+      PG_LAUNCH_CHECK();
+      PG_CUDA_OK(b_pad.alloc(sizeof(float) * t.kp, s));
+      pad_rows_kernel<<<2, 256, 0, s>>>(biases[0], 1, d1, t.kp, b_pad.as<float>());
+      PG_LAUNCH_CHECK();
+      const TcShape tq = tc_shape(c_in, t.kp);
+      if (int rc = launch_row_gemm<PROD_ROWS, EPI_STORE>(q, tq, w_pad.as<float>(), c_in, t.kp, b_pad.as<float>(), q_img,
+                                                         q_bias, s))
+        return rc;
+    } else if (int rc = fc_fp32_launch(features, num_src, c_in, weights[0], biases[0], d1, 0, nullptr, t_p.as<float>(),
+                                       t.kp, s)) {
+      return rc;
+    }
+  }
+  PG_CUDA_OK(t_w1x.alloc(sizeof(float) * 3 * t.kp, s));
+  pad_rows_kernel<<<4, 256, 0, s>>>(weights[0] + int64_t(c_in) * d1, 3, d1, t.kp, t_w1x.as<float>());
   PG_LAUNCH_CHECK();
   PG_CUDA_OK(t_err.alloc(sizeof(int), s));
   PG_CUDA_OK(cudaMemsetAsync(t_err.ptr, 0, sizeof(int), s));
   if (int rc = fill_async(out, num_dst * n, -FLT_MAX, s)) return rc;
-
+  TcParams p{};
   p.P = t_p.as<float>();
-  p.ldp = kp;
+  p.ldp = t.kp;
   p.xyz_src = xyz_src;
   p.xyz_dst = xyz_dst;
   p.dst_index = dst_index;
   p.src = src;
   p.dst = dst;
-  p.num_edges = num_edges;
+  p.num_rows = num_edges;
   p.num_src = num_src;
   p.num_dst = num_dst;
   p.w1x = t_w1x.as<float>();
-  p.b2 = t_b2.as<float>();
-  p.kp = kp;
-  p.ks = kp / 16;
-  p.n = n;
-  p.np = np;
-  p.n1 = n1;
-  p.n2 = n2;
-  p.wimg = t_img.as<uint8_t>();
-  p.part_bytes = part;
-  uint32_t cols = 32;
-  while (cols < uint32_t(np)) cols <<= 1;
-  p.tmem_cols = cols;
   p.out = out;
   p.err = t_err.as<int>();
-  p.num_pair_tiles = ceil_div(num_edges, 2 * kTileRows);
-  const size_t smem = tc_edge_smem_bytes(kp, np);
-  PG_CUDA_OK(cudaFuncSetAttribute(edge_gnn_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, int(smem)));
-  const int clusters = int(std::min<int64_t>(p.num_pair_tiles, num_sms() / 2));
-  edge_gnn_tc_kernel<<<2 * clusters, kThreads, smem, s>>>(p);
-  PG_LAUNCH_CHECK();
+  if (int rc = launch_row_gemm<PROD_GNN, EPI_SEGMAX>(p, t, weights[1], d1, n, biases[1], t_img, t_bias, s)) return rc;
   int h = 0;
   PG_CUDA_OK(cudaMemcpyAsync(&h, t_err.ptr, sizeof(int), cudaMemcpyDeviceToHost, s));
   PG_CUDA_OK(cudaStreamSynchronize(s));

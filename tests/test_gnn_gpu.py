@@ -176,7 +176,16 @@ def test_predict_matches_golden(name, precision, request):
     _need(precision)
     g = request.getfixturevalue(name)
     coords, keypoints, edges = g.graph_tuple()
+    from pointgnn_b200 import _lib
+    tc0 = (_lib.tc_launch_count(0), _lib.tc_launch_count(1))
     logits, boxes, probs = _predict(g, g.layer_configs, precision, (g.graph['intensity'], coords, keypoints, edges))
+    if precision == 'bf16x3':
+        # the tensor-core kernels must really have run: 3 GNN iterations (+ the car pooling layer) are
+        # fused tcgen05 edge launches, and the wide per-vertex layers go through the dense tcgen05
+        # kernel (no silent FFMA fallback).  The ped pooling MLP (256 -> 512 last layer) exceeds the
+        # resident-weight budget and stays on the fp32 fused kernel.
+        assert _lib.tc_launch_count(0) - tc0[0] == (4 if name == 'car' else 3)
+        assert _lib.tc_launch_count(1) - tc0[1] >= 10
     assert isinstance(logits, np.ndarray) and logits.shape == g.gnn['logits'].shape
     assert boxes.shape == g.gnn['boxes'].shape
     assert np.abs(logits - g.gnn['logits']).max() < TOL
@@ -277,9 +286,11 @@ def test_tc_edge_kernel_shapes_and_tails(d, c_in):
         h = np.maximum(np.maximum(e0 @ w1 + b1, 0) @ w2 + b2, 0)
         want = ognn.graph_scatter_max_fn(h, dst, nv)
         for prec in (0, 1):
+            before = _lib.tc_launch_count(0)
             got = _lib.edge_mlp_max(1, _cuda(f), _cuda(x), _cuda(xd), None, _cuda(src.astype(np.int32)),
                                     _cuda(dst.astype(np.int32)), nv, [_cuda(w1), _cuda(w2)], [_cuda(b1), _cuda(b2)],
                                     precision=prec).cpu().numpy()
+            assert _lib.tc_launch_count(0) - before == (1 if prec == 1 else 0), (d, prec)
             empty = want == np.finfo(np.float32).min
             assert np.array_equal(got == np.finfo(np.float32).min, empty), (case, prec)
             err = np.abs(got - want)[~empty].max() if (~empty).any() else 0.0

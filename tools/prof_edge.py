@@ -1,0 +1,42 @@
+"""Drive only the fused tcgen05 edge kernel (for ncu): 8 synthetic frames, car_auto_T3 layer-2 weights."""
+import json
+import os
+import sys
+
+import numpy as np
+import torch
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+sys.path.insert(0, ROOT)
+from oracle import synth  # noqa: E402
+from pointgnn_b200 import _lib  # noqa: E402
+from pointgnn_b200.models import graph_gen  # noqa: E402
+
+frames = int(sys.argv[1]) if len(sys.argv) > 1 else 8
+reps = int(sys.argv[2]) if len(sys.argv) > 2 else 3
+prec = int(sys.argv[3]) if len(sys.argv) > 3 else 1
+cfg = json.load(open(os.path.join(ROOT, 'tests/golden/config_car_auto_T3_train.json')))
+w = dict(np.load(os.path.join(ROOT, 'tests/golden/weights_car_auto_T3_train.npz')))
+pts = np.vstack([synth.lidar_frame(i, 20000)[0] for i in range(frames)])
+fp = torch.arange(frames + 1, dtype=torch.int32, device='cuda') * 20000
+coords, kp, edges = graph_gen.gen_multi_level_local_graph_v3(torch.from_numpy(pts).cuda(), frame_ptr=fp,
+                                                           **cfg['runtime_graph_gen_kwargs'])
+k = coords[1].shape[0]
+feats = torch.rand((k, 300), device='cuda') * 0.5
+s = 'layer2/extract_vertex_features/fully_connected'
+ws = [torch.from_numpy(w[s + '/weights']).cuda(), torch.from_numpy(w[s + '_1/weights']).cuda()]
+bs = [torch.from_numpy(w[s + '/biases']).cuda(), torch.from_numpy(w[s + '_1/biases']).cuda()]
+src, dst = edges[1][:, 0].contiguous(), edges[1][:, 1].contiguous()
+print('K', k, 'E1', src.numel())
+for _ in range(2):
+    _lib.edge_mlp_max(1, feats, coords[1], coords[1], None, src, dst, k, ws, bs, precision=prec)
+torch.cuda.synchronize()
+a = torch.cuda.Event(enable_timing=True)
+b = torch.cuda.Event(enable_timing=True)
+a.record()
+for _ in range(reps):
+    _lib.edge_mlp_max(1, feats, coords[1], coords[1], None, src, dst, k, ws, bs, precision=prec)
+b.record()
+b.synchronize()
+ms = a.elapsed_time(b) / reps
+print('edge_mlp_max precision %d: %.3f ms per call, %.1f algorithmic TFLOP/s' % (prec, ms, src.numel() * 361800 / ms / 1e9))
