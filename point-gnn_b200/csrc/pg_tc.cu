@@ -25,6 +25,8 @@
 // Operand layout (no swizzle, K-major): 8-row x 16-byte core matrices, 128 contiguous bytes each;
 // A stage: core(rg, kc) at rg*256 + kc*128; resident B: core(g, kc) at g*(KP/8)*128 + kc*128.
 #include <atomic>
+#include <cstdlib>
+#include <vector>
 
 #include "pg_common.cuh"
 #include "pg_umma.cuh"
@@ -65,7 +67,8 @@ constexpr int kProdWarps = 8;    // warps 9-16
 constexpr int kThreads = (kEpiWarps + 1 + kProdWarps) * 32;  // 544
 constexpr int kStageBytes = 8192;                            // A hi (4096) + A lo (4096): 128 rows x 16 k
 constexpr int kTileRows = 128;                               // rows (edges) per CTA per pair-tile
-constexpr int kScratchFloats = 16 * 33;                      // per epilogue warp: 16 columns x 32 rows (+1 pad)
+constexpr int kScratchStride = 36;                           // floats per scratch column: 32 rows + pad, 16 B aligned
+constexpr int kScratchFloats = 16 * kScratchStride;          // per epilogue warp: 16 columns x 32 rows
 
 enum { PROD_GNN = 0, PROD_ROWS = 1, PROD_POOL = 2 };
 constexpr int kPoolC1 = 32, kPoolC2 = 64, kPoolC3 = 128;   // point MLP widths the pooling producer is built for
@@ -101,7 +104,18 @@ struct TcParams {
   const float* residual;  // STORE: optional [num_rows, n]
   int* err;
   int64_t num_pair_tiles;
+  unsigned long long* trace;   // optional (PG_TC_TRACE): [role 0..7][slot 0..127][3] globaltimer ns, cluster 0 only
 };
+
+__device__ __forceinline__ unsigned long long gtime() {
+  unsigned long long t;
+  asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t));
+  return t;
+}
+#define PG_TRACE(role, slot, k)                                                                   \
+  do {                                                                                            \
+    if (p.trace != nullptr && cluster_id == 0 && (slot) < 128) p.trace[((role) * 128 + (slot)) * 3 + (k)] = gtime(); \
+  } while (0)
 
 // ---- W [K, N] -> resident B image ---------------------------------------------------------------
 // B operand rows are OUTPUT features (N), K-major.  Rank r of the pair holds rows
@@ -142,9 +156,7 @@ struct SmemMap {
   uint8_t* bres;
   uint8_t* a;
   float* w1x;
-  float* bias;
   float* scratch;
-  int* dstw;
   uint64_t* bar_full;      // [kStages]   (leader)
   uint64_t* bar_empty;     // [kStages]
   uint64_t* bar_tmem_full;
@@ -161,18 +173,14 @@ __host__ __device__ inline size_t smem_layout(uint8_t* base, int kp, int np, uin
   const size_t o_bres = take(2 * size_t(part_bytes));
   const size_t o_a = take(size_t(kStages) * kStageBytes);
   const size_t o_w1x = take((prod == PROD_POOL ? size_t(kPoolWFloats) : size_t(3) * kp) * sizeof(float));
-  const size_t o_bias = take(size_t(np) * sizeof(float));
   const size_t o_scr = take(size_t(kEpiWarps) * kScratchFloats * sizeof(float));
-  const size_t o_dst = take(size_t(kEpiWarps) * 32 * sizeof(int));
   const size_t o_bar = take((2 * kStages + 5) * sizeof(uint64_t));
   const size_t o_tmem = take(16);
   if (m != nullptr) {
     m->bres = base + o_bres;
     m->a = base + o_a;
     m->w1x = reinterpret_cast<float*>(base + o_w1x);
-    m->bias = reinterpret_cast<float*>(base + o_bias);
     m->scratch = reinterpret_cast<float*>(base + o_scr);
-    m->dstw = reinterpret_cast<int*>(base + o_dst);
     uint64_t* bars = reinterpret_cast<uint64_t*>(base + o_bar);
     m->bar_full = bars;
     m->bar_empty = bars + kStages;
@@ -187,41 +195,81 @@ __host__ __device__ inline size_t smem_layout(uint8_t* base, int kp, int np, uin
 
 // One 16-column chunk of the accumulator, segment-max flavour.  Thread = TMEM lane = tile row.
 // The chunk is transposed through a warp-private shared-memory scratch so that each lane then owns
-// one COLUMN and walks 16 rows with a running max (half-warp h covers rows 16h..16h+15); a max is
-// flushed (bias + relu + atomicMax) only where the destination changes (bm = boundary bit mask).
-__device__ __forceinline__ void epi_chunk_segmax(const TcParams& p, const SmemMap& sm, uint32_t taddr, int c_out,
-                                                  float* scratch, const int* sd, uint32_t bm, int lane) {
-  uint32_t v[16];
-  tmem_ld16(taddr, v);
-  tmem_ld_wait();
-#pragma unroll
-  for (int j = 0; j < 16; ++j) scratch[j * 33 + lane] = __uint_as_float(v[j]);
-  __syncwarp();
+// one COLUMN of one 16-row half (h = lane / 16): four 128-bit loads + 15 max.  `d` is the lane's own
+// destination; when no destination boundary falls inside either half (warp-uniform `slow` == false,
+// the common case: segments are ~150-250 edges long) the half's max is flushed with one atomic,
+// otherwise the rows are walked one by one and a flush happens at every boundary.
+struct SegState {
+  int d;          // destination of this lane's row (-1 = row beyond the edge list)
+  int cur0;       // destination of the first row of this lane's 16-row half
+  int nb;         // number of destination boundaries strictly inside this lane's half
+  int b;          // position (1..15) of the first such boundary
+  int d_b;        // destination that starts at that boundary
+  bool pair;      // both halves of the warp lie in ONE destination (no boundary anywhere in the warp)
+};
+
+__device__ __forceinline__ void seg_flush(const TcParams& p, int cur, int c, bool col_ok, float m, float bias) {
+  if (cur >= 0 && col_ok && m > -FLT_MAX && p.act != 99)   // act == 99: PG_TC_NOFLUSH experiment (results invalid)
+    atomicMax(reinterpret_cast<int*>(p.out + int64_t(cur) * p.n + c), __float_as_int(fmaxf(m + bias, 0.0f)));
+}
+
+// Second half of a chunk (the first half = tcgen05.ld + 16 stores into the scratch, see the caller).
+// Lane = (column jj, 16-row half h).  Destinations are non-decreasing along the rows, so a half
+// contains 0 boundaries (plain max), 1 boundary (two masked maxima, branch free) or - only for
+// destinations with fewer than 16 edges - several (sequential walk).  Every partial max is flushed
+// with one atomicMax; when the whole warp lies in one destination the two halves are combined first.
+__device__ __forceinline__ void epi_reduce_segmax(const TcParams& p, int c_out, const float* scratch,
+                                                   const SegState& st, int lane, float bias, int64_t warp_row0) {
   const int jj = lane & 15, h = lane >> 4;
-  const float* col = scratch + jj * 33 + 16 * h;
+  const float* col = scratch + jj * kScratchStride + 16 * h;
+  const float4 q0 = reinterpret_cast<const float4*>(col)[0];
+  const float4 q1 = reinterpret_cast<const float4*>(col)[1];
+  const float4 q2 = reinterpret_cast<const float4*>(col)[2];
+  const float4 q3 = reinterpret_cast<const float4*>(col)[3];
   const int c = c_out + jj;
   const bool col_ok = c < p.n;
-  const float bias = col_ok ? sm.bias[c] : 0.0f;
-  int cur = sd[16 * h];
+  if (st.pair) {   // warp uniform
+    float m = fmaxf(fmaxf(fmaxf(fmaxf(q0.x, q0.y), fmaxf(q0.z, q0.w)), fmaxf(fmaxf(q1.x, q1.y), fmaxf(q1.z, q1.w))),
+                    fmaxf(fmaxf(fmaxf(q2.x, q2.y), fmaxf(q2.z, q2.w)), fmaxf(fmaxf(q3.x, q3.y), fmaxf(q3.z, q3.w))));
+    m = fmaxf(m, __shfl_xor_sync(0xffffffffu, m, 16));
+    if (h == 0) seg_flush(p, st.cur0, c, col_ok, m, bias);
+    return;
+  }
+  const float val[16] = {q0.x, q0.y, q0.z, q0.w, q1.x, q1.y, q1.z, q1.w, q2.x, q2.y, q2.z, q2.w, q3.x, q3.y, q3.z, q3.w};
+  if (st.nb <= 1) {
+    float lo = -FLT_MAX, hi = -FLT_MAX;
+#pragma unroll
+    for (int i = 0; i < 16; ++i) {
+      const bool first = st.nb == 0 || i < st.b;
+      lo = fmaxf(lo, first ? val[i] : -FLT_MAX);
+      hi = fmaxf(hi, first ? -FLT_MAX : val[i]);
+    }
+    seg_flush(p, st.cur0, c, col_ok, lo, bias);
+    seg_flush(p, st.d_b, c, col_ok, hi, bias);   // hi stays -FLT_MAX (no-op) when nb == 0
+    return;
+  }
+  // several short segments inside 16 rows: walk them (destinations via shared memory is not
+  // available here, so they are re-read from global memory - rare path)
+  int cur = st.cur0;
   float m = -FLT_MAX;
 #pragma unroll
   for (int i = 0; i < 16; ++i) {
-    if (i > 0 && ((bm >> i) & 1u)) {
-      if (cur >= 0 && col_ok)
-        atomicMax(reinterpret_cast<int*>(p.out + int64_t(cur) * p.n + c), __float_as_int(fmaxf(m + bias, 0.0f)));
-      cur = sd[16 * h + i];
+    const int64_t r = warp_row0 + 16 * h + i;
+    int di = r < p.num_rows ? p.dst[r] : -1;
+    if (di >= p.num_dst) di = -1;
+    if (di != cur) {
+      seg_flush(p, cur, c, col_ok, m, bias);
+      cur = di;
       m = -FLT_MAX;
     }
-    m = fmaxf(m, col[i]);
+    m = fmaxf(m, val[i]);
   }
-  if (cur >= 0 && col_ok)
-    atomicMax(reinterpret_cast<int*>(p.out + int64_t(cur) * p.n + c), __float_as_int(fmaxf(m + bias, 0.0f)));
-  __syncwarp();
+  seg_flush(p, cur, c, col_ok, m, bias);
 }
 
 // Plain GEMM epilogue: out[row, c] = act(acc + bias[c]) (+ residual[row, c]).
-__device__ __forceinline__ void epi_chunk_store(const TcParams& p, const SmemMap& sm, uint32_t taddr, int c_out,
-                                                 int64_t row, bool row_ok) {
+__device__ __forceinline__ void epi_chunk_store(const TcParams& p, uint32_t taddr, int c_out, int64_t row,
+                                                 bool row_ok) {
   uint32_t v[16];
   tmem_ld16(taddr, v);
   tmem_ld_wait();
@@ -235,7 +283,7 @@ __device__ __forceinline__ void epi_chunk_store(const TcParams& p, const SmemMap
 #pragma unroll
     for (int j = 0; j < 4; ++j) {
       const int c = c_out + j4 + j;
-      float t = __uint_as_float(v[j4 + j]) + (c < p.np ? sm.bias[c] : 0.0f);
+      float t = __uint_as_float(v[j4 + j]) + __ldg(p.bias + c);   // bias is padded to np; warp-uniform address
       if (p.act == 1) t = fmaxf(t, 0.0f);
       r[j] = t;
     }
@@ -251,6 +299,41 @@ __device__ __forceinline__ void epi_chunk_store(const TcParams& p, const SmemMap
 #pragma unroll
       for (int j = 0; j < 4; ++j)
         if (c_out + j4 + j < p.n) o[j4 + j] = r[j] + (res ? res[j4 + j] : 0.0f);
+    }
+  }
+}
+
+// One accumulator section (instruction 1 or 2) for this warp: chunks par, par+2, ... of 16 columns.
+// The tcgen05.ld of chunk k+1 is in flight while chunk k is reduced out of the scratch.
+template <int kEpi, int kMaxChunks>
+__device__ __forceinline__ void epi_section(const TcParams& p, uint32_t tbase, int col0, int ncols, int par,
+                                             float* scratch, const SegState& st, int lane, int64_t row, bool row_ok,
+                                             int64_t warp_row0, const float (&bias)[kMaxChunks], int trace_slot = -1) {
+  const int64_t cluster_id = (trace_slot >= 0) ? 0 : 1;   // PG_TRACE only fires for cluster 0
+  if (kEpi == EPI_STORE) {
+#pragma unroll
+    for (int k = 0; k < kMaxChunks; ++k) {
+      const int ci = par + 2 * k;
+      if (ci * 16 < ncols) epi_chunk_store(p, tbase + ci * 16, col0 + ci * 16, row, row_ok);
+    }
+    return;
+  }
+  uint32_t v[16];
+  if (par * 16 < ncols) tmem_ld16(tbase + par * 16, v);
+#pragma unroll
+  for (int k = 0; k < kMaxChunks; ++k) {
+    const int ci = par + 2 * k;
+    if (ci * 16 < ncols) {
+      if (k < 2) PG_TRACE(6 + k, trace_slot, 0);
+      tmem_ld_wait();
+      __syncwarp();   // the previous chunk's scratch reads are done
+#pragma unroll
+      for (int j = 0; j < 16; ++j) scratch[j * kScratchStride + lane] = __uint_as_float(v[j]);
+      if ((ci + 2) * 16 < ncols) tmem_ld16(tbase + (ci + 2) * 16, v);
+      __syncwarp();
+      if (k < 2) PG_TRACE(6 + k, trace_slot, 1);
+      epi_reduce_segmax(p, col0 + ci * 16, scratch, st, lane, bias[k], warp_row0);
+      if (k < 2) PG_TRACE(6 + k, trace_slot, 2);
     }
   }
 }
@@ -273,7 +356,6 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kThreads, 1) row_gem
     for (int i = threadIdx.x; i < 3 * p.kp; i += kThreads) sm.w1x[i] = p.w1x[i];
   if (kProd == PROD_POOL)
     for (int i = threadIdx.x; i < kPoolWFloats; i += kThreads) sm.w1x[i] = p.pool_w[i];
-  for (int i = threadIdx.x; i < p.np; i += kThreads) sm.bias[i] = p.bias[i];
   if (threadIdx.x == 0) {
     for (int i = 0; i < kStages; ++i) {
       mbar_init(&sm.bar_full[i], 2 * kProdWarps);
@@ -315,9 +397,12 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kThreads, 1) row_gem
       const uint32_t idesc1 = make_idesc_bf16(256, p.n1);
       const uint32_t idesc2 = make_idesc_bf16(256, p.n2 > 0 ? p.n2 : 16);
       const uint32_t sbo_b = uint32_t(p.kp / 8) * 128u;
-      const uint32_t b_hi = smem_u32(sm.bres), b_lo = b_hi + p.part_bytes;
-      const uint32_t b2_off = uint32_t(p.n1 / 16) * sbo_b;   // first row group of instruction 2
-      uint32_t it = 0;
+      // descriptors differ only in the 14-bit start-address field: build them once, then add offsets
+      const uint64_t a_hi0 = make_smem_desc(smem_u32(sm.a), 128, 256);
+      const uint64_t b_hi0 = make_smem_desc(smem_u32(sm.bres), 128, sbo_b);
+      const uint64_t b_lo0 = make_smem_desc(smem_u32(sm.bres) + p.part_bytes, 128, sbo_b);
+      const uint64_t b2_off = uint64_t((uint32_t(p.n1 / 16) * sbo_b) >> 4);   // first row group of instruction 2
+      uint32_t it = 0, stage = 0, phase = 0;
       uint32_t tile_iter = 0;
       for (int64_t tile = cluster_id; tile < p.num_pair_tiles; tile += num_clusters, ++tile_iter) {
         const uint32_t buf = tile_iter & 1u;
@@ -325,29 +410,32 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kThreads, 1) row_gem
         if (p.n2 > 0) mbar_wait(sm.bar_i2_empty, (tile_iter & 1u) ^ 1u);
         tc_fence_after();
         const uint32_t d1 = tmem + col_i1[buf], d2 = tmem + col_i2;
-        for (int s = 0; s < p.ks; ++s, ++it) {
-          const uint32_t stage = it % kStages;
-          mbar_wait(&sm.bar_full[stage], (it / kStages) & 1u);
+        uint64_t kb = 0;   // (k-step * 256 bytes) >> 4: two K-adjacent cores per k-step
+        bool ready = false;   // full[stage] already observed complete by the probe of the previous k-step
+        for (int s = 0; s < p.ks; ++s, ++it, kb += 16) {
+          PG_TRACE(0, it, 0);
+          if (!ready) mbar_wait(&sm.bar_full[stage], phase);
+          PG_TRACE(0, it, 1);
           tc_fence_after();
-          const uint32_t a_hi = smem_u32(sm.a + stage * kStageBytes), a_lo = a_hi + kStageBytes / 2;
-          const uint64_t da_hi = make_smem_desc(a_hi, 128, 256);
-          const uint64_t da_lo = make_smem_desc(a_lo, 128, 256);
-          const uint32_t koff = uint32_t(s) * 256u;   // two K-adjacent cores per k-step
-          {
-            const uint64_t db_hi = make_smem_desc(b_hi + koff, 128, sbo_b);
-            const uint64_t db_lo = make_smem_desc(b_lo + koff, 128, sbo_b);
-            mma_bf16<2>(d1, da_hi, db_hi, idesc1, s > 0);
-            mma_bf16<2>(d1, da_lo, db_hi, idesc1, true);
-            mma_bf16<2>(d1, da_hi, db_lo, idesc1, true);
-          }
+          // probe the NEXT stage's barrier now: its ~90-cycle latency hides behind the MMA issue below
+          const uint32_t nstage = (stage + 1 == kStages) ? 0u : stage + 1;
+          const uint32_t nphase = (stage + 1 == kStages) ? (phase ^ 1u) : phase;
+          ready = mbar_try_wait(&sm.bar_full[nstage], nphase);
+          const uint64_t da_hi = a_hi0 + uint64_t(stage * (kStageBytes >> 4));
+          const uint64_t da_lo = da_hi + uint64_t((kStageBytes / 2) >> 4);
+          const uint64_t db_hi = b_hi0 + kb, db_lo = b_lo0 + kb;
+          mma_bf16<2>(d1, da_hi, db_hi, idesc1, s > 0);
+          mma_bf16<2>(d1, da_lo, db_hi, idesc1, true);
+          mma_bf16<2>(d1, da_hi, db_lo, idesc1, true);
           if (p.n2 > 0) {
-            const uint64_t db_hi = make_smem_desc(b_hi + b2_off + koff, 128, sbo_b);
-            const uint64_t db_lo = make_smem_desc(b_lo + b2_off + koff, 128, sbo_b);
-            mma_bf16<2>(d2, da_hi, db_hi, idesc2, s > 0);
-            mma_bf16<2>(d2, da_lo, db_hi, idesc2, true);
-            mma_bf16<2>(d2, da_hi, db_lo, idesc2, true);
+            mma_bf16<2>(d2, da_hi, db_hi + b2_off, idesc2, s > 0);
+            mma_bf16<2>(d2, da_lo, db_hi + b2_off, idesc2, true);
+            mma_bf16<2>(d2, da_hi, db_lo + b2_off, idesc2, true);
           }
           mma_commit_2cta(&sm.bar_empty[stage], 0x3);    // frees this A stage in both CTAs
+          PG_TRACE(0, it, 2);
+          stage = nstage;
+          phase = nphase;
         }
         mma_commit_2cta(sm.bar_tmem_full, 0x3);          // accumulators of this tile are complete
       }
@@ -358,47 +446,65 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kThreads, 1) row_gem
     cluster_sync();   // [sync A]
     const int quarter = warp & 3, par = warp >> 2;
     float* scratch = sm.scratch + warp * kScratchFloats;
-    int* sd = sm.dstw + warp * 32;
     const uint32_t lane_base = uint32_t(quarter * 32) << 16;
+    constexpr int kMaxChunks = 8;   // chunks of one section handled by one warp: <= 256 / 16 / 2
+    // this lane's column in each of its chunks never changes: keep the biases in registers
+    float bias1[kMaxChunks], bias2[kMaxChunks];
+    if (kEpi == EPI_SEGMAX) {
+#pragma unroll
+      for (int k = 0; k < kMaxChunks; ++k) {
+        const int c1 = (par + 2 * k) * 16 + (lane & 15);
+        const int c2 = p.n1 + c1;
+        bias1[k] = ((par + 2 * k) * 16 < p.n1 && c1 < p.n) ? __ldg(p.bias + c1) : 0.0f;
+        bias2[k] = ((par + 2 * k) * 16 < p.n2 && c2 < p.n) ? __ldg(p.bias + c2) : 0.0f;
+      }
+    }
     uint32_t tile_iter = 0;
     for (int64_t tile = cluster_id; tile < p.num_pair_tiles; tile += num_clusters, ++tile_iter) {
       const uint32_t buf = tile_iter & 1u;
       const int64_t row = tile * 256 + int64_t(rank) * kTileRows + quarter * 32 + lane;
       const bool row_ok = row < p.num_rows;
-      uint32_t bm = 0;
+      const int64_t warp_row0 = tile * 256 + int64_t(rank) * kTileRows + quarter * 32;
+      SegState st{-1, -1, 0, 0, -1, false};
       if (kEpi == EPI_SEGMAX) {
-        int d = -1;
         if (row_ok) {
-          d = p.dst[row];
-          if (d < 0 || d >= p.num_dst) { *p.err = 1; d = -1; }
+          st.d = p.dst[row];
+          if (st.d < 0 || st.d >= p.num_dst) { *p.err = 1; st.d = -1; }
         }
-        sd[lane] = d;
-        __syncwarp();
-        const int h = lane >> 4;
-#pragma unroll
-        for (int i = 1; i < 16; ++i) bm |= (sd[16 * h + i] != sd[16 * h + i - 1]) ? (1u << i) : 0u;
+        const int prev = __shfl_up_sync(0xffffffffu, st.d, 1);
+        const uint32_t bits = __ballot_sync(0xffffffffu, (lane & 15) != 0 && prev != st.d);
+        const uint32_t mine = (bits >> (lane & 16)) & 0xffffu;    // boundaries inside this lane's half
+        st.nb = __popc(mine);
+        st.b = mine ? __ffs(mine) - 1 : 16;
+        st.cur0 = __shfl_sync(0xffffffffu, st.d, lane & 16);
+        st.d_b = __shfl_sync(0xffffffffu, st.d, (lane & 16) + (st.b & 15));
+        const int d16 = __shfl_sync(0xffffffffu, st.d, 16);
+        st.pair = bits == 0 && __shfl_sync(0xffffffffu, st.d, 0) == d16;
       }
+      if (warp == 0 && lane == 0) PG_TRACE(3 + rank, tile_iter, 0);
       mbar_wait(sm.bar_tmem_full, tile_iter & 1u);
+      if (warp == 0 && lane == 0) PG_TRACE(3 + rank, tile_iter, 1);
       tc_fence_after();
-      // ---- instruction-2 columns first: they are single buffered, free them as early as possible
+      // ---- instruction-2 columns first: they are single buffered, free them as early as possible.
+      // TMEM is handed back with a relaxed arrive (ordered by the tcgen05 fences): a release arrive
+      // would wait for the reductions still in flight (~2 us, measured with PG_TC_TRACE).
       if (p.n2 > 0) {
-        for (int ci = par; ci * 16 < p.n2; ci += 2) {
-          const uint32_t taddr = tmem + lane_base + col_i2 + ci * 16;
-          if (kEpi == EPI_SEGMAX) epi_chunk_segmax(p, sm, taddr, p.n1 + ci * 16, scratch, sd, bm, lane);
-          else epi_chunk_store(p, sm, taddr, p.n1 + ci * 16, row, row_ok);
-        }
+        epi_section<kEpi, kMaxChunks>(p, tmem + lane_base + col_i2, p.n1, p.n2, par, scratch, st, lane, row, row_ok,
+                                       warp_row0, bias2,
+                                       (warp == 0 && lane == 0 && rank == 0 && cluster_id == 0) ? int(tile_iter) : -1);
         tc_fence_before();
         __syncwarp();
-        if (lane == 0) mbar_arrive_cluster(sm.bar_i2_empty, 0);
+        if (lane == 0) mbar_arrive_cluster_relaxed(sm.bar_i2_empty, 0);
+        if (warp == 0 && lane == 0 && rank == 0) PG_TRACE(5, tile_iter, 0);
       }
-      for (int ci = par; ci * 16 < p.n1; ci += 2) {
-        const uint32_t taddr = tmem + lane_base + col_i1[buf] + ci * 16;
-        if (kEpi == EPI_SEGMAX) epi_chunk_segmax(p, sm, taddr, ci * 16, scratch, sd, bm, lane);
-        else epi_chunk_store(p, sm, taddr, ci * 16, row, row_ok);
-      }
+      if (warp == 0 && lane == 0 && rank == 0) PG_TRACE(5, tile_iter, 1);
+      epi_section<kEpi, kMaxChunks>(p, tmem + lane_base + col_i1[buf], 0, p.n1, par, scratch, st, lane, row, row_ok,
+                                     warp_row0, bias1);
       tc_fence_before();
       __syncwarp();
-      if (lane == 0) mbar_arrive_cluster(&sm.bar_i1_empty[buf], 0);
+      if (lane == 0) mbar_arrive_cluster_relaxed(&sm.bar_i1_empty[buf], 0);
+      if (warp == 0 && lane == 0 && rank == 0) PG_TRACE(5, tile_iter, 2);
+      if (warp == 0 && lane == 0) PG_TRACE(3 + rank, tile_iter, 2);
     }
   } else {
     // =================================== producer warps =======================================
@@ -407,7 +513,7 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kThreads, 1) row_gem
     const int r = pt & 127;                              // tile row
     const int kc = pt >> 7;                              // which 8-wide K chunk of the k-step
     const uint32_t a_off = uint32_t(r >> 3) * 256u + uint32_t(kc) * 128u + uint32_t(r & 7) * 16u;
-    uint32_t it = 0;
+    uint32_t it = 0, stage = 0, phase = 0;
     for (int64_t tile = cluster_id; tile < p.num_pair_tiles; tile += num_clusters) {
       const int64_t row = tile * 256 + int64_t(rank) * kTileRows + r;
       bool valid = row < p.num_rows;
@@ -435,15 +541,18 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kThreads, 1) row_gem
         split_bf16x2(h[2], h[3], &hi.y, &lo.y);
         split_bf16x2(h[4], h[5], &hi.z, &lo.z);
         split_bf16x2(h[6], h[7], &hi.w, &lo.w);
-        const uint32_t stage = it % kStages;
-        mbar_wait(&sm.bar_empty[stage], ((it / kStages) & 1u) ^ 1u);
+        if (pt == 0) PG_TRACE(1 + rank, it, 0);
+        mbar_wait(&sm.bar_empty[stage], phase ^ 1u);
+        if (pt == 0) PG_TRACE(1 + rank, it, 1);
         uint8_t* st = sm.a + stage * kStageBytes + a_off;
         *reinterpret_cast<uint4*>(st) = hi;
         *reinterpret_cast<uint4*>(st + kStageBytes / 2) = lo;
         fence_proxy_async_smem();
         __syncwarp();
         if (lane == 0) mbar_arrive_cluster(&sm.bar_full[stage], 0);
+        if (pt == 0) PG_TRACE(1 + rank, it, 2);
         ++it;
+        if (++stage == kStages) { stage = 0; phase ^= 1u; }
       };
       if (kProd == PROD_POOL) {
         // per-edge point MLP 4 -> 32 -> 64 (registers), then 64 -> 128 eight outputs per k-step;
@@ -498,7 +607,7 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kThreads, 1) row_gem
           }
           float h[8];
 #pragma unroll
-          for (int j = 0; j < 8; ++j) h[j] = valid ? fmaxf(acc[j], 0.0f) : 0.0f;
+          for (int j = 0; j < 8; ++j) h[j] = fmaxf(acc[j], 0.0f);   // rows past the end are dropped by the epilogue
           publish(h);
         }
       } else {
@@ -529,11 +638,11 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kThreads, 1) row_gem
               float t = fmaf(rx, wx[j], pv[j]);
               t = fmaf(ry, wy[j], t);
               t = fmaf(rz, wz[j], t);
-              h[j] = valid ? fmaxf(t, 0.0f) : 0.0f;
+              h[j] = fmaxf(t, 0.0f);   // rows past the end are dropped by the epilogue
             }
           } else {
 #pragma unroll
-            for (int j = 0; j < 8; ++j) h[j] = valid ? pv[j] : 0.0f;
+            for (int j = 0; j < 8; ++j) h[j] = pv[j];
           }
           publish(h);
         }
@@ -563,8 +672,11 @@ TcShape tc_shape(int k, int n) {
   TcShape t{};
   t.kp = (k + 15) / 16 * 16;
   t.np = (n + 15) / 16 * 16;
+  // instruction 1 is double buffered in TMEM, instruction 2 single: 2*n1 + n2 <= 512 columns.
+  // Make n1 as large as that allows so that the single-buffered part (whose drain the MMA of the
+  // next tile has to wait for) is as small as possible: np = 304 -> 208 + 96.
   if (t.np <= 256) { t.n1 = t.np; t.n2 = 0; }
-  else { t.n1 = ((t.np / 2) + 15) / 16 * 16; t.n2 = t.np - t.n1; }
+  else { t.n1 = std::min(256, (512 - t.np) / 16 * 16); t.n2 = t.np - t.n1; }
   t.part = uint32_t(t.np / 16) * uint32_t(t.kp / 8) * 128u;
   const int cols_needed = 2 * t.n1 + t.n2;
   uint32_t cols = 32;
@@ -599,8 +711,27 @@ int launch_row_gemm(TcParams& p, const TcShape& t, const float* w, int k, int n,
   PG_REQUIRE(smem <= 227 * 1024, "tcgen05 kernel needs %zu B of shared memory", smem);
   PG_CUDA_OK(cudaFuncSetAttribute(row_gemm_tc_kernel<kProd, kEpi>, cudaFuncAttributeMaxDynamicSharedMemorySize, int(smem)));
   const int clusters = int(std::min<int64_t>(p.num_pair_tiles, num_sms() / 2));
+  const char* trace_path = (kProd == PROD_GNN) ? getenv("PG_TC_TRACE") : nullptr;   // debugging aid
+  if (kEpi == EPI_SEGMAX && getenv("PG_TC_NOFLUSH") != nullptr) p.act = 99;       // timing experiment only
+  Temp t_trace;
+  const size_t trace_words = size_t(8) * 128 * 3;
+  if (trace_path != nullptr) {
+    PG_CUDA_OK(t_trace.alloc(trace_words * 8, s));
+    PG_CUDA_OK(cudaMemsetAsync(t_trace.ptr, 0, trace_words * 8, s));
+    p.trace = t_trace.as<unsigned long long>();
+  }
   row_gemm_tc_kernel<kProd, kEpi><<<2 * clusters, kThreads, smem, s>>>(p);
   PG_LAUNCH_CHECK();
+  if (trace_path != nullptr) {
+    std::vector<unsigned long long> h(trace_words);
+    PG_CUDA_OK(cudaMemcpyAsync(h.data(), t_trace.ptr, trace_words * 8, cudaMemcpyDeviceToHost, s));
+    PG_CUDA_OK(cudaStreamSynchronize(s));
+    if (FILE* f = fopen(trace_path, "w")) {
+      for (size_t i = 0; i < trace_words; i += 3)
+        fprintf(f, "%zu %zu %llu %llu %llu\n", i / 3 / 128, (i / 3) % 128, h[i], h[i + 1], h[i + 2]);
+      fclose(f);
+    }
+  }
   g_tc_launches[kEpi == EPI_SEGMAX ? 0 : 1].fetch_add(1, std::memory_order_relaxed);
   return PG_OK;
 }

@@ -47,6 +47,13 @@ __device__ __forceinline__ void mbar_arrive_cluster(uint64_t* bar, uint32_t rank
   const uint32_t remote = mapa(smem_u32(bar), rank);
   asm volatile("mbarrier.arrive.shared::cluster.b64 _, [%0];" ::"r"(remote) : "memory");
 }
+// Relaxed arrive (no memory ordering, compiles to a bare SYNCS.ARRIVE).  Used where the hand-over is
+// ordered by tcgen05 fences instead of the memory model: returning TMEM to the MMA warp.  A release
+// arrive there would wait for the epilogue's global reductions still in flight (~2 us, measured).
+__device__ __forceinline__ void mbar_arrive_cluster_relaxed(uint64_t* bar, uint32_t rank) {
+  const uint32_t remote = mapa(smem_u32(bar), rank);
+  asm volatile("mbarrier.arrive.relaxed.cluster.shared::cluster.b64 _, [%0];" ::"r"(remote) : "memory");
+}
 __device__ __forceinline__ void mbar_arrive_expect_tx(uint64_t* bar, uint32_t bytes) {
   asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)), "r"(bytes)
                : "memory");

@@ -1,0 +1,44 @@
+"""Drive only the pooling-layer kernel (PointSetPooling edge part) for ncu / timing."""
+import json
+import os
+import sys
+
+import numpy as np
+import torch
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+sys.path.insert(0, ROOT)
+from oracle import synth  # noqa: E402
+from pointgnn_b200 import _lib  # noqa: E402
+from pointgnn_b200.models import graph_gen  # noqa: E402
+
+frames = int(sys.argv[1]) if len(sys.argv) > 1 else 8
+reps = int(sys.argv[2]) if len(sys.argv) > 2 else 3
+prec = int(sys.argv[3]) if len(sys.argv) > 3 else 1
+cfg = json.load(open(os.path.join(ROOT, 'tests/golden/config_car_auto_T3_train.json')))
+w = dict(np.load(os.path.join(ROOT, 'tests/golden/weights_car_auto_T3_train.npz')))
+fr = [synth.lidar_frame(i, 20000) for i in range(frames)]
+pts = torch.from_numpy(np.vstack([f[0] for f in fr])).cuda()
+inten = torch.from_numpy(np.vstack([f[1] for f in fr])).cuda()
+fp = torch.arange(frames + 1, dtype=torch.int32, device='cuda') * 20000
+coords, kp, edges = graph_gen.gen_multi_level_local_graph_v3(pts, frame_ptr=fp, **cfg['runtime_graph_gen_kwargs'])
+k = coords[1].shape[0]
+s = 'layer1/extract_vertex_features/fully_connected'
+names = [s, s + '_1', s + '_2', s + '_3']
+ws = [torch.from_numpy(w[n + '/weights']).cuda() for n in names]
+bs = [torch.from_numpy(w[n + '/biases']).cuda() for n in names]
+src, dst = edges[0][:, 0].contiguous(), edges[0][:, 1].contiguous()
+kpi = kp[0].reshape(-1).contiguous()
+print('K', k, 'E0', src.numel())
+for _ in range(2):
+    _lib.edge_mlp_max(0, inten, pts, pts, kpi, src, dst, k, ws, bs, precision=prec)
+torch.cuda.synchronize()
+a = torch.cuda.Event(enable_timing=True)
+b = torch.cuda.Event(enable_timing=True)
+a.record()
+for _ in range(reps):
+    _lib.edge_mlp_max(0, inten, pts, pts, kpi, src, dst, k, ws, bs, precision=prec)
+b.record()
+b.synchronize()
+ms = a.elapsed_time(b) / reps
+print('pool edge_mlp_max precision %d: %.3f ms per call, %.1f algorithmic TFLOP/s' % (prec, ms, src.numel() * 97536 / ms / 1e9))

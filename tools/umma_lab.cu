@@ -211,6 +211,108 @@ static int run_redux() {
   return bad;
 }
 
+// ---- raw tensor-core rate of the production instruction mix -------------------------------------
+// cta_group::2, M = 256, no-swizzle K-major operands resident in shared memory, kp/16 k-steps per
+// "tile", three products per k-step (the BF16x3 pattern) for each of the instructions N1 (+ N2).
+__global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(128) mma_rate_kernel(int n1, int n2, int kp, int tiles,
+                                                                                  int commit_every_stage,
+                                                                                  long long* cycles) {
+  extern __shared__ __align__(128) uint8_t smem[];
+  __shared__ uint64_t bar;
+  __shared__ uint64_t bar2[3];
+  __shared__ uint32_t tmem_base;
+  const uint32_t rank = cluster_ctarank();
+  const int np = n1 + n2;
+  const uint32_t part = uint32_t(np / 16) * uint32_t(kp / 8) * 128u;
+  uint8_t* s_b = smem;
+  uint8_t* s_a = smem + 2 * part;
+  for (int i = threadIdx.x; i < int(2 * part + 3 * 8192) / 4; i += blockDim.x) reinterpret_cast<uint32_t*>(smem)[i] = 0x3c003c00u + i;
+  fence_proxy_async_smem();
+  if (threadIdx.x == 0) {
+    mbar_init(&bar, 1);
+    for (int i = 0; i < 3; ++i) mbar_init(&bar2[i], 1);
+    fence_barrier_init();
+  }
+  if (threadIdx.x < 32) {
+    tmem_alloc<2>(&tmem_base, 512);
+    tmem_relinquish<2>();
+  }
+  tc_fence_before();
+  __syncthreads();
+  cluster_sync();
+  tc_fence_after();
+  const uint32_t tmem = tmem_base;
+  if (threadIdx.x == 0 && rank == 0) {
+    const uint32_t idesc1 = make_idesc_bf16(256, n1), idesc2 = make_idesc_bf16(256, n2 > 0 ? n2 : 16);
+    const uint32_t sbo_b = uint32_t(kp / 8) * 128u;
+    const uint32_t b_hi = smem_u32(s_b), b_lo = b_hi + part, b2_off = uint32_t(n1 / 16) * sbo_b;
+    uint32_t phase = 0;
+    const long long t0 = clock64();
+    for (int t = 0; t < tiles; ++t) {
+      for (int s = 0; s < kp / 16; ++s) {
+        const uint32_t a_hi = smem_u32(s_a + (s % 3) * 8192), a_lo = a_hi + 4096;
+        const uint64_t da_hi = make_smem_desc(a_hi, 128, 256), da_lo = make_smem_desc(a_lo, 128, 256);
+        const uint32_t koff = uint32_t(s) * 256u;
+        const uint64_t db_hi = make_smem_desc(b_hi + koff, 128, sbo_b), db_lo = make_smem_desc(b_lo + koff, 128, sbo_b);
+        if (commit_every_stage == 2 && n2 > 0) {   // interleave the two accumulators
+          const uint64_t eb_hi = make_smem_desc(b_hi + b2_off + koff, 128, sbo_b), eb_lo = make_smem_desc(b_lo + b2_off + koff, 128, sbo_b);
+          mma_bf16<2>(tmem, da_hi, db_hi, idesc1, s > 0);
+          mma_bf16<2>(tmem + n1, da_hi, eb_hi, idesc2, s > 0);
+          mma_bf16<2>(tmem, da_lo, db_hi, idesc1, true);
+          mma_bf16<2>(tmem + n1, da_lo, eb_hi, idesc2, true);
+          mma_bf16<2>(tmem, da_hi, db_lo, idesc1, true);
+          mma_bf16<2>(tmem + n1, da_hi, eb_lo, idesc2, true);
+        } else {
+        mma_bf16<2>(tmem, da_hi, db_hi, idesc1, s > 0);
+        mma_bf16<2>(tmem, da_lo, db_hi, idesc1, true);
+        mma_bf16<2>(tmem, da_hi, db_lo, idesc1, true);
+        if (n2 > 0) {
+          const uint64_t eb_hi = make_smem_desc(b_hi + b2_off + koff, 128, sbo_b), eb_lo = make_smem_desc(b_lo + b2_off + koff, 128, sbo_b);
+          mma_bf16<2>(tmem + n1, da_hi, eb_hi, idesc2, s > 0);
+          mma_bf16<2>(tmem + n1, da_lo, eb_hi, idesc2, true);
+          mma_bf16<2>(tmem + n1, da_hi, eb_lo, idesc2, true);
+        }
+        }
+        if (commit_every_stage == 1) {
+          mma_commit_2cta(&bar, 0x1);
+          mbar_wait(&bar, phase);
+          phase ^= 1;
+        }
+        if (commit_every_stage == 3) mma_commit_2cta(&bar2[s % 3], 0x3);   // commit, nobody waits
+      }
+      if (commit_every_stage != 1) {
+        mma_commit_2cta(&bar, 0x1);
+        mbar_wait(&bar, phase);
+        phase ^= 1;
+      }
+    }
+    cycles[0] = clock64() - t0;
+  }
+  tc_fence_before();
+  __syncthreads();
+  cluster_sync();
+  if (threadIdx.x < 32) tmem_dealloc<2>(tmem, 512);
+}
+
+static int run_rate(int n1, int n2, int kp, int per_stage) {
+  long long* c;
+  CK(cudaMalloc(&c, 8));
+  const int np = n1 + n2;
+  const size_t smem = size_t(2) * (np / 16) * (kp / 8) * 128 + 3 * 8192;
+  CK(cudaFuncSetAttribute(mma_rate_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, int(smem)));
+  const int tiles = 200;
+  mma_rate_kernel<<<2, 128, smem>>>(n1, n2, kp, tiles, per_stage, c);
+  CK(cudaGetLastError());
+  CK(cudaDeviceSynchronize());
+  long long h;
+  CK(cudaMemcpy(&h, c, 8, cudaMemcpyDeviceToHost));
+  const double per_tile = double(h) / tiles;
+  const double ideal = double(kp / 16) * 3.0 * (256.0 * np / 512.0);
+  printf("mma rate n1=%d n2=%d kp=%d commit/wait per %s: %.0f cycles per 256-row tile (ideal %.0f, ratio %.2f)\n", n1, n2, kp,
+         per_stage ? "stage" : "tile", per_tile, ideal, per_tile / ideal);
+  return 0;
+}
+
 int main(int argc, char** argv) {
   if (argc < 2) return 1;
   cudaDeviceProp prop;
@@ -218,5 +320,6 @@ int main(int argc, char** argv) {
   if (!strcmp(argv[1], "1cta")) return run_gemm(1, argc > 2 ? atoi(argv[2]) : 0);
   if (!strcmp(argv[1], "2cta")) return run_gemm(2, argc > 2 ? atoi(argv[2]) : 0);
   if (!strcmp(argv[1], "redux")) return run_redux();
+  if (!strcmp(argv[1], "rate")) return run_rate(atoi(argv[2]), atoi(argv[3]), atoi(argv[4]), atoi(argv[5]));
   return 1;
 }
