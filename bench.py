@@ -195,6 +195,7 @@ def run_gpu(args, rank, world):
     from oracle import synth                      # synthetic input generator only
     from pointgnn_b200 import _lib
     from pointgnn_b200.models import graph_gen, models
+    from pointgnn_b200.utils import sharding
 
     local_rank = int(os.environ.get('LOCAL_RANK', 0))
     torch.cuda.set_device(local_rank)
@@ -220,7 +221,7 @@ def run_gpu(args, rank, world):
     for s in range(pool):
         pts, inten = [], []
         for f in range(frames_per_step):
-            x, it = synth.lidar_frame((rank * 100003 + s * frames_per_step + f) % 100000, num_points, full_360)
+            x, it = synth.lidar_frame(sharding.frame_seed(s, f, rank, frames_per_step), num_points, full_360)
             pts.append(x)
             inten.append(it)
         fp = np.arange(frames_per_step + 1, dtype=np.int32) * num_points
@@ -313,19 +314,12 @@ def run_gpu(args, rank, world):
         step_device(*dev_steps[(args.warmup + s) % pool], instrument=True)
     edge_ms, edge_flops, edge_launches = time_edge_kernel(model, graph_fn, gkw, dev_steps[args.warmup % pool], config)
 
-    # ---- reduce over ranks ------------------------------------------------------------------
-    t = torch.tensor([elapsed_ms, e2e_s * 1e3], dtype=torch.float64, device=dev)
-    stats = torch.tensor([frames, elapsed_ms, counters['edges1'], counters['edges0'], counters['keypoints']],
-                         dtype=torch.float64, device=dev)
-    if world > 1:
-        dist.all_reduce(t, op=dist.ReduceOp.MAX)
-        gathered = [torch.zeros_like(stats) for _ in range(world)]
-        dist.all_gather(gathered, stats)                 # the only data-path-free collective: counters
-        stats_all = torch.stack(gathered).sum(0)
-    else:
-        stats_all = stats
-    max_ms, max_e2e_ms = float(t[0]), float(t[1])
-    total_frames = float(stats_all[0])
+    # ---- reduce over ranks: the only collective of the job is this all-gather of counters --------
+    _, summary = sharding.gather_counters(
+        {'frames': frames, 'device_ms': elapsed_ms, 'e2e_ms': e2e_s * 1e3, 'edges0': counters['edges0'],
+         'edges1': counters['edges1'], 'keypoints': counters['keypoints']}, device=dev)
+    max_ms, max_e2e_ms = summary['device_ms'], summary['e2e_ms']
+    total_frames = summary['frames']
 
     if rank == 0:
         peaks = {}
