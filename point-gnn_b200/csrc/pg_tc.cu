@@ -122,7 +122,7 @@ __device__ __forceinline__ unsigned long long gtime() {
 // [r*N1/2, (r+1)*N1/2) of instruction 1 followed by [N1 + r*N2/2, ...) of instruction 2, as 8-row
 // groups g: core(g, kc) at g*sbo + kc*128, element (row%8)*16 + (k%8)*2.  hi / lo = BF16 split.
 __global__ void pack_w2_kernel(const float* __restrict__ w2, int k, int n, int kp, int n1, int n2,
-                               uint8_t* __restrict__ img, uint32_t part_bytes) {
+                               uint8_t* __restrict__ img, uint32_t part_bytes, uint32_t rank_stride) {
   const int rows_per_rank = (n1 + n2) / 2;
   const int total = 2 * rows_per_rank * kp;
   const uint32_t sbo = uint32_t(kp / 8) * 128u;
@@ -138,7 +138,7 @@ __global__ void pack_w2_kernel(const float* __restrict__ w2, int k, int n, int k
     const __nv_bfloat16 hi = __float2bfloat16_rn(v);
     const __nv_bfloat16 lo = __float2bfloat16_rn(v - __bfloat162float(hi));
     const uint32_t off = uint32_t(lr / 8) * sbo + uint32_t(kk / 8) * 128u + uint32_t(lr % 8) * 16u + uint32_t(kk % 8) * 2u;
-    uint8_t* base = img + size_t(rank) * 2 * part_bytes;
+    uint8_t* base = img + size_t(rank) * rank_stride;
     *reinterpret_cast<__nv_bfloat16*>(base + off) = hi;
     *reinterpret_cast<__nv_bfloat16*>(base + part_bytes + off) = lo;
   }
@@ -338,6 +338,150 @@ __device__ __forceinline__ void epi_section(const TcParams& p, uint32_t tbase, i
   }
 }
 
+// A-operand producers of the GNN edge layer / a plain row matrix (shared by row_gemm_tc_kernel and
+// seg_gemm_tc_kernel).  `pt` = producer thread index 0..255.
+template <int kProd>
+__device__ __forceinline__ void gnn_rows_producer(const TcParams& p, const SmemMap& sm, int pt, int lane, uint32_t rank,
+                                                  int64_t cluster_id, int64_t num_clusters) {
+    // GNN / ROWS.  Two producer groups of four warps; a thread owns tile row r and produces the
+    // WHOLE 16-wide k-step of every second pipeline iteration (group g: iterations g, g+2, ...),
+    // so two k-steps are always in flight per CTA and each thread has two k-step periods to
+    // produce one.  All global loads are issued one own-iteration (the P slice), half a tile (the
+    // next tile's coordinates) or a whole tile (the next tile's edge indices) before their use.
+    const int r = pt & 127, g = pt >> 7;
+    const uint32_t a_off = uint32_t(r >> 3) * 256u + uint32_t(r & 7) * 16u;
+    const int64_t my_tiles = (p.num_pair_tiles - cluster_id + num_clusters - 1) / num_clusters;
+    const int ks = p.ks, mid = p.ks >> 1;
+    auto row_of = [&](int64_t j) { return (cluster_id + j * num_clusters) * 256 + int64_t(rank) * kTileRows + r; };
+    auto load_idx = [&](int64_t j, int& si, int& di) {
+      si = 0;
+      di = 0;
+      if (kProd == PROD_GNN && j < my_tiles) {
+        const int64_t row = row_of(j);
+        if (row < p.num_rows) {
+          si = __ldg(p.src + row);
+          di = __ldg(p.dst + row);
+        }
+      }
+    };
+    auto check_idx = [&](int& si, int& di) {
+      if (kProd == PROD_GNN && (si < 0 || si >= p.num_src || di < 0 || di >= p.num_dst)) {
+        *p.err = 1;
+        si = 0;
+        di = 0;
+      }
+    };
+    auto load_xyz = [&](int si, int di, float (&x)[6]) {
+      if (kProd == PROD_GNN) {
+        const int64_t drow = p.dst_index ? int64_t(p.dst_index[di]) : int64_t(di);
+        const float* a = p.xyz_src + int64_t(si) * 3;
+        const float* b = p.xyz_dst + drow * 3;
+        x[0] = __ldg(a); x[1] = __ldg(a + 1); x[2] = __ldg(a + 2);
+        x[3] = __ldg(b); x[4] = __ldg(b + 1); x[5] = __ldg(b + 2);
+      }
+    };
+    auto row_ptr_of = [&](int64_t j, int si) -> const float* {
+      if (kProd == PROD_GNN) return p.P + int64_t(si) * p.ldp;
+      const int64_t row = row_of(j);
+      return p.P + (row < p.num_rows ? row : 0) * int64_t(p.ldp);
+    };
+    auto load16 = [&](const float* prow, int s, float4 (&q)[4]) {
+      const float* a = prow + s * 16;
+#pragma unroll
+      for (int i = 0; i < 4; ++i) {
+        if (kProd == PROD_GNN) q[i] = __ldg(reinterpret_cast<const float4*>(a) + i);
+        else q[i] = (s * 16 + 4 * i + 4 <= p.k_real) ? __ldg(reinterpret_cast<const float4*>(a) + i)
+                                                     : make_float4(0.f, 0.f, 0.f, 0.f);
+      }
+    };
+    if (my_tiles > 0) {
+      int64_t j = 0;
+      int s = g;
+      uint32_t stage = uint32_t(g), phase = 0, it = 0;
+      int si_n, di_n;
+      float rx = 0.f, ry = 0.f, rz = 0.f;
+      float nx[6] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
+      const float* prow;
+      {
+        int si, di;
+        load_idx(0, si, di);
+        check_idx(si, di);
+        load_xyz(si, di, nx);
+        rx = nx[0] - nx[3]; ry = nx[1] - nx[4]; rz = nx[2] - nx[5];
+        prow = row_ptr_of(0, si);
+      }
+      load_idx(1, si_n, di_n);
+      float4 q[4];
+      load16(prow, s, q);
+      while (j < my_tiles) {
+        // ---- prefetch this thread's next k-step (two pipeline iterations ahead) ---------------
+        int s2 = s + 2;
+        int64_t j2 = j;
+        if (s2 >= ks) { s2 -= ks; j2 = j + 1; }
+        if ((s == mid || s == mid + 1) && j + 1 < my_tiles) {   // exactly one own iteration per tile
+          check_idx(si_n, di_n);
+          load_xyz(si_n, di_n, nx);
+        }
+        float4 qn[4];
+        if (j2 < my_tiles) load16(j2 == j ? prow : row_ptr_of(j2, si_n), s2, qn);
+        // ---- this k-step: 16 values of row r -------------------------------------------------
+        uint4 hi[2], lo[2];
+#pragma unroll
+        for (int h8 = 0; h8 < 2; ++h8) {
+          const float pv[8] = {q[2 * h8].x, q[2 * h8].y, q[2 * h8].z, q[2 * h8].w,
+                               q[2 * h8 + 1].x, q[2 * h8 + 1].y, q[2 * h8 + 1].z, q[2 * h8 + 1].w};
+          float v[8];
+          if (kProd == PROD_GNN) {
+            const int k0 = s * 16 + h8 * 8;
+            const float4* wx = reinterpret_cast<const float4*>(sm.w1x + k0);
+            const float4* wy = reinterpret_cast<const float4*>(sm.w1x + p.kp + k0);
+            const float4* wz = reinterpret_cast<const float4*>(sm.w1x + 2 * p.kp + k0);
+#pragma unroll
+            for (int i = 0; i < 2; ++i) {
+              const float4 a = wx[i], b = wy[i], c = wz[i];
+              v[4 * i + 0] = fmaxf(fmaf(rz, c.x, fmaf(ry, b.x, fmaf(rx, a.x, pv[4 * i + 0]))), 0.0f);
+              v[4 * i + 1] = fmaxf(fmaf(rz, c.y, fmaf(ry, b.y, fmaf(rx, a.y, pv[4 * i + 1]))), 0.0f);
+              v[4 * i + 2] = fmaxf(fmaf(rz, c.z, fmaf(ry, b.z, fmaf(rx, a.z, pv[4 * i + 2]))), 0.0f);
+              v[4 * i + 3] = fmaxf(fmaf(rz, c.w, fmaf(ry, b.w, fmaf(rx, a.w, pv[4 * i + 3]))), 0.0f);
+            }
+          } else {
+#pragma unroll
+            for (int i = 0; i < 8; ++i) v[i] = pv[i];
+          }
+          split_bf16x2(v[0], v[1], &hi[h8].x, &lo[h8].x);
+          split_bf16x2(v[2], v[3], &hi[h8].y, &lo[h8].y);
+          split_bf16x2(v[4], v[5], &hi[h8].z, &lo[h8].z);
+          split_bf16x2(v[6], v[7], &hi[h8].w, &lo[h8].w);
+        }
+        if (pt == 0) PG_TRACE(1 + rank, it, 0);
+        mbar_wait(&sm.bar_empty[stage], phase ^ 1u);
+        if (pt == 0) PG_TRACE(1 + rank, it, 1);
+        uint8_t* st = sm.a + stage * kStageBytes + a_off;
+        *reinterpret_cast<uint4*>(st) = hi[0];
+        *reinterpret_cast<uint4*>(st + 128) = hi[1];
+        *reinterpret_cast<uint4*>(st + kStageBytes / 2) = lo[0];
+        *reinterpret_cast<uint4*>(st + kStageBytes / 2 + 128) = lo[1];
+        fence_proxy_async_smem();
+        __syncwarp();
+        if (lane == 0) mbar_arrive_cluster(&sm.bar_full[stage], 0);
+        if (pt == 0) PG_TRACE(1 + rank, it, 2);
+        ++it;
+        // ---- advance to the next own iteration ----------------------------------------------
+        stage += 2;
+        if (stage >= uint32_t(kStages)) { stage -= kStages; phase ^= 1u; }
+        if (j2 != j && j2 < my_tiles) {   // tile switch: adopt the prefetched context, look one more tile ahead
+          prow = row_ptr_of(j2, si_n);
+          rx = nx[0] - nx[3]; ry = nx[1] - nx[4]; rz = nx[2] - nx[5];
+          load_idx(j2 + 1, si_n, di_n);
+        }
+        j = j2;
+        s = s2;
+#pragma unroll
+        for (int i = 0; i < 4; ++i) q[i] = qn[i];
+      }
+    }
+}
+
 template <int kProd, int kEpi>
 __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kThreads, 1) row_gemm_tc_kernel(TcParams p) {
   // No-swizzle operands, bulk copies and mbarriers only need 16-byte alignment; the carve-up is
@@ -358,7 +502,9 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kThreads, 1) row_gem
     for (int i = threadIdx.x; i < kPoolWFloats; i += kThreads) sm.w1x[i] = p.pool_w[i];
   if (threadIdx.x == 0) {
     for (int i = 0; i < kStages; ++i) {
-      mbar_init(&sm.bar_full[i], 2 * kProdWarps);
+      // arrivals per stage: every producer warp of both CTAs (POOL), or the four warps of the one
+      // producer group that owns the k-step, in both CTAs (GNN / ROWS)
+      mbar_init(&sm.bar_full[i], kProd == PROD_POOL ? 2 * kProdWarps : kProdWarps);
       mbar_init(&sm.bar_empty[i], 1);
     }
     mbar_init(sm.bar_tmem_full, 1);
@@ -510,51 +656,43 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kThreads, 1) row_gem
     // =================================== producer warps =======================================
     cluster_sync();   // [sync A]
     const int pt = threadIdx.x - (kEpiWarps + 1) * 32;   // 0..255
-    const int r = pt & 127;                              // tile row
-    const int kc = pt >> 7;                              // which 8-wide K chunk of the k-step
-    const uint32_t a_off = uint32_t(r >> 3) * 256u + uint32_t(kc) * 128u + uint32_t(r & 7) * 16u;
-    uint32_t it = 0, stage = 0, phase = 0;
-    for (int64_t tile = cluster_id; tile < p.num_pair_tiles; tile += num_clusters) {
-      const int64_t row = tile * 256 + int64_t(rank) * kTileRows + r;
-      bool valid = row < p.num_rows;
-      float rx = 0.f, ry = 0.f, rz = 0.f;
-      const float* prow = p.P;
-      int sidx = 0, didx = 0;
-      if (kProd != PROD_ROWS) {
+    if (kProd != PROD_POOL) {
+      gnn_rows_producer<kProd>(p, sm, pt, lane, rank, cluster_id, num_clusters);
+    } else {
+      const int r = pt & 127;                              // tile row
+      const int kc = pt >> 7;                              // which 8-wide K chunk of the k-step
+      const uint32_t a_off = uint32_t(r >> 3) * 256u + uint32_t(kc) * 128u + uint32_t(r & 7) * 16u;
+      uint32_t it = 0, stage = 0, phase = 0;
+      for (int64_t tile = cluster_id; tile < p.num_pair_tiles; tile += num_clusters) {
+        const int64_t row = tile * 256 + int64_t(rank) * kTileRows + r;
+        bool valid = row < p.num_rows;
+        int sidx = 0, didx = 0;
         if (valid) {
           sidx = p.src[row];
           didx = p.dst[row];
           if (sidx < 0 || sidx >= p.num_src || didx < 0 || didx >= p.num_dst) { *p.err = 1; valid = false; sidx = 0; didx = 0; }
         }
         const int64_t drow = p.dst_index ? int64_t(p.dst_index[didx]) : int64_t(didx);
-        rx = p.xyz_src[int64_t(sidx) * 3 + 0] - p.xyz_dst[drow * 3 + 0];
-        ry = p.xyz_src[int64_t(sidx) * 3 + 1] - p.xyz_dst[drow * 3 + 1];
-        rz = p.xyz_src[int64_t(sidx) * 3 + 2] - p.xyz_dst[drow * 3 + 2];
-        if (kProd == PROD_GNN) prow = p.P + int64_t(sidx) * p.ldp + kc * 8;
-      } else {
-        prow = p.P + (valid ? row : 0) * int64_t(p.ldp) + kc * 8;
-      }
-      // hand one k-step (8 values of this thread's row) to the tensor core
-      auto publish = [&](const float (&h)[8]) {
-        uint4 hi, lo;
-        split_bf16x2(h[0], h[1], &hi.x, &lo.x);
-        split_bf16x2(h[2], h[3], &hi.y, &lo.y);
-        split_bf16x2(h[4], h[5], &hi.z, &lo.z);
-        split_bf16x2(h[6], h[7], &hi.w, &lo.w);
-        if (pt == 0) PG_TRACE(1 + rank, it, 0);
-        mbar_wait(&sm.bar_empty[stage], phase ^ 1u);
-        if (pt == 0) PG_TRACE(1 + rank, it, 1);
-        uint8_t* st = sm.a + stage * kStageBytes + a_off;
-        *reinterpret_cast<uint4*>(st) = hi;
-        *reinterpret_cast<uint4*>(st + kStageBytes / 2) = lo;
-        fence_proxy_async_smem();
-        __syncwarp();
-        if (lane == 0) mbar_arrive_cluster(&sm.bar_full[stage], 0);
-        if (pt == 0) PG_TRACE(1 + rank, it, 2);
-        ++it;
-        if (++stage == kStages) { stage = 0; phase ^= 1u; }
-      };
-      if (kProd == PROD_POOL) {
+        const float rx = p.xyz_src[int64_t(sidx) * 3 + 0] - p.xyz_dst[drow * 3 + 0];
+        const float ry = p.xyz_src[int64_t(sidx) * 3 + 1] - p.xyz_dst[drow * 3 + 1];
+        const float rz = p.xyz_src[int64_t(sidx) * 3 + 2] - p.xyz_dst[drow * 3 + 2];
+        // hand one k-step (8 values of this thread's row) to the tensor core
+        auto publish = [&](const float (&h)[8]) {
+          uint4 hi, lo;
+          split_bf16x2(h[0], h[1], &hi.x, &lo.x);
+          split_bf16x2(h[2], h[3], &hi.y, &lo.y);
+          split_bf16x2(h[4], h[5], &hi.z, &lo.z);
+          split_bf16x2(h[6], h[7], &hi.w, &lo.w);
+          mbar_wait(&sm.bar_empty[stage], phase ^ 1u);
+          uint8_t* st = sm.a + stage * kStageBytes + a_off;
+          *reinterpret_cast<uint4*>(st) = hi;
+          *reinterpret_cast<uint4*>(st + kStageBytes / 2) = lo;
+          fence_proxy_async_smem();
+          __syncwarp();
+          if (lane == 0) mbar_arrive_cluster(&sm.bar_full[stage], 0);
+          ++it;
+          if (++stage == kStages) { stage = 0; phase ^= 1u; }
+        };
         // per-edge point MLP 4 -> 32 -> 64 (registers), then 64 -> 128 eight outputs per k-step;
         // weights are warp-uniform shared-memory broadcasts.  gnn.py:264-274 (layers 1-3 of 4).
         const float* w1 = sm.w1x;
@@ -610,42 +748,6 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kThreads, 1) row_gem
           for (int j = 0; j < 8; ++j) h[j] = fmaxf(acc[j], 0.0f);   // rows past the end are dropped by the epilogue
           publish(h);
         }
-      } else {
-        auto load_chunk = [&](int s, float4& q0, float4& q1) {
-          if (kProd == PROD_GNN) {
-            q0 = *reinterpret_cast<const float4*>(prow + s * 16);
-            q1 = *reinterpret_cast<const float4*>(prow + s * 16 + 4);
-          } else {
-            const int k0 = s * 16 + kc * 8;
-            q0 = (k0 + 4 <= p.k_real) ? *reinterpret_cast<const float4*>(prow + s * 16) : make_float4(0.f, 0.f, 0.f, 0.f);
-            q1 = (k0 + 8 <= p.k_real) ? *reinterpret_cast<const float4*>(prow + s * 16 + 4) : make_float4(0.f, 0.f, 0.f, 0.f);
-          }
-        };
-        float4 n0, n1;
-        load_chunk(0, n0, n1);
-        for (int s = 0; s < p.ks; ++s) {
-          const float4 c0 = n0, c1 = n1;
-          if (s + 1 < p.ks) load_chunk(s + 1, n0, n1);   // prefetch the next k-step's slice
-          float h[8];
-          const float pv[8] = {c0.x, c0.y, c0.z, c0.w, c1.x, c1.y, c1.z, c1.w};
-          if (kProd == PROD_GNN) {
-            const int k0 = s * 16 + kc * 8;
-            const float* wx = sm.w1x + k0;
-            const float* wy = sm.w1x + p.kp + k0;
-            const float* wz = sm.w1x + 2 * p.kp + k0;
-#pragma unroll
-            for (int j = 0; j < 8; ++j) {
-              float t = fmaf(rx, wx[j], pv[j]);
-              t = fmaf(ry, wy[j], t);
-              t = fmaf(rz, wz[j], t);
-              h[j] = fmaxf(t, 0.0f);   // rows past the end are dropped by the epilogue
-            }
-          } else {
-#pragma unroll
-            for (int j = 0; j < 8; ++j) h[j] = pv[j];
-          }
-          publish(h);
-        }
       }
     }
   }
@@ -655,6 +757,577 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kThreads, 1) row_gem
   __syncthreads();
   cluster_sync();
   if (warp == kMmaWarp) tmem_dealloc<2>(tmem, p.tmem_cols);
+}
+
+// ================================================================================================
+// seg_gemm_tc_kernel - the fused GNN edge layer with the big GEMM TRANSPOSED: D1[feature, edge].
+//
+// Same producers, same resident W image and same stage ring as row_gemm_tc_kernel<PROD_GNN, .>, but
+// the first 256 output features are computed as  D1 = W2^T (A operand, M = 256 features over the
+// CTA pair) x h1^T (B operand, N = 256 edges of the pair tile), so that in tensor memory a LANE is a
+// feature and the COLUMNS are the tile's edges.  The per-destination max then runs inside one thread
+// along its registers: no transposition through shared memory, no shuffles, destination boundaries
+// are warp-uniform, the running max is carried across the 128 edges a warp drains, and each flush is
+// one 128-byte coalesced atomicMax (32 consecutive features of one destination).  That removes the
+// ~17 KB of shared-memory traffic per k-step the row-major epilogue costs (the tensor core's operand
+// fetches already use ~2/3 of the shared-memory bandwidth) and ~16x of the atomics.
+// Features 256 .. N-1 (48 of 304 for the car model) keep the row-major form (D2[edge, feature],
+// M = 256 edges, N = n2) and the transposing epilogue: the same two smem operands serve both
+// instructions with the A / B roles swapped.  Accumulators are single buffered (256 + n2 columns):
+// draining D1 takes a few hundred cycles against ~9 000 of MMA per tile.
+template <int kProd>
+__global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kThreads, 1) seg_gemm_tc_kernel(TcParams p) {
+  extern __shared__ __align__(128) uint8_t smem_raw[];
+  SmemMap sm;
+  smem_layout(smem_raw, p.kp, p.np, p.part_bytes, &sm, kProd);
+  uint64_t* bar_tmem_empty = &sm.bar_i1_empty[0];
+
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const uint32_t rank = cluster_ctarank();
+  const int64_t cluster_id = blockIdx.x >> 1;
+  const int64_t num_clusters = gridDim.x >> 1;
+
+  // ---- prologue ------------------------------------------------------------------------------
+  for (int i = threadIdx.x; i < 3 * p.kp; i += kThreads) sm.w1x[i] = p.w1x[i];
+  if (threadIdx.x == 0) {
+    for (int i = 0; i < kStages; ++i) {
+      mbar_init(&sm.bar_full[i], kProdWarps);     // the four warps of one producer group, both CTAs
+      mbar_init(&sm.bar_empty[i], 1);
+    }
+    mbar_init(sm.bar_tmem_full, 1);
+    mbar_init(bar_tmem_empty, 2 * kEpiWarps);
+    mbar_init(sm.bar_wres, 1);
+    fence_barrier_init();
+  }
+  if (warp == kMmaWarp) {
+    tmem_alloc<2>(sm.tmem, p.tmem_cols);
+    tmem_relinquish<2>();
+  }
+  tc_fence_before();
+  __syncthreads();
+  cluster_sync();
+  tc_fence_after();
+  const uint32_t tmem = *sm.tmem;
+  constexpr uint32_t kD2Col = 256;
+
+  if (warp == kMmaWarp) {
+    // =================================== MMA warp =============================================
+    if (lane == 0) {
+      mbar_arrive_expect_tx(sm.bar_wres, 2 * p.part_bytes);
+      const uint8_t* g = p.wimg + size_t(rank) * 2 * p.part_bytes;
+      bulk_g2s(sm.bres, g, p.part_bytes, sm.bar_wres);
+      bulk_g2s(sm.bres + p.part_bytes, g + p.part_bytes, p.part_bytes, sm.bar_wres);
+      mbar_wait(sm.bar_wres, 0);
+    }
+    __syncwarp();
+    cluster_sync();   // [sync A]
+    if (rank == 0 && lane == 0) {
+      const uint32_t idesc1 = make_idesc_bf16(256, 256);                       // M = features, N = edges
+      const uint32_t idesc2 = make_idesc_bf16(256, p.n2 > 0 ? p.n2 : 16);      // M = edges, N = features
+      const uint32_t sbo_b = uint32_t(p.kp / 8) * 128u;
+      const uint64_t h_hi0 = make_smem_desc(smem_u32(sm.a), 128, 256);
+      const uint64_t w_hi0 = make_smem_desc(smem_u32(sm.bres), 128, sbo_b);
+      const uint64_t w_lo0 = make_smem_desc(smem_u32(sm.bres) + p.part_bytes, 128, sbo_b);
+      const uint64_t w2_off = uint64_t((16u * sbo_b) >> 4);   // rows 128.. of this rank's image = features 256..
+      const uint32_t d1 = tmem, d2 = tmem + kD2Col;
+      uint32_t stage = 0, phase = 0, tile_iter = 0;
+      for (int64_t tile = cluster_id; tile < p.num_pair_tiles; tile += num_clusters, ++tile_iter) {
+        mbar_wait(bar_tmem_empty, (tile_iter & 1u) ^ 1u);
+        tc_fence_after();
+        uint64_t kb = 0;
+        bool ready = false;
+        for (int s = 0; s < p.ks; ++s, kb += 16) {
+          if (!ready) mbar_wait(&sm.bar_full[stage], phase);
+          tc_fence_after();
+          const uint32_t nstage = (stage + 1 == kStages) ? 0u : stage + 1;
+          const uint32_t nphase = (stage + 1 == kStages) ? (phase ^ 1u) : phase;
+          ready = mbar_try_wait(&sm.bar_full[nstage], nphase);
+          const uint64_t h_hi = h_hi0 + uint64_t(stage * (kStageBytes >> 4));
+          const uint64_t h_lo = h_hi + uint64_t((kStageBytes / 2) >> 4);
+          const uint64_t w_hi = w_hi0 + kb, w_lo = w_lo0 + kb;
+          mma_bf16<2>(d1, w_hi, h_hi, idesc1, s > 0);
+          mma_bf16<2>(d1, w_hi, h_lo, idesc1, true);
+          mma_bf16<2>(d1, w_lo, h_hi, idesc1, true);
+          if (p.n2 > 0) {
+            mma_bf16<2>(d2, h_hi, w_hi + w2_off, idesc2, s > 0);
+            mma_bf16<2>(d2, h_lo, w_hi + w2_off, idesc2, true);
+            mma_bf16<2>(d2, h_hi, w_lo + w2_off, idesc2, true);
+          }
+          mma_commit_2cta(&sm.bar_empty[stage], 0x3);
+          stage = nstage;
+          phase = nphase;
+        }
+        mma_commit_2cta(sm.bar_tmem_full, 0x3);
+      }
+    }
+    __syncwarp();
+  } else if (warp < kEpiWarps) {
+    // =================================== epilogue warps =======================================
+    cluster_sync();   // [sync A]
+    const int quarter = warp & 3, par = warp >> 2;
+    float* scratch = sm.scratch + warp * kScratchFloats;
+    int* ids = reinterpret_cast<int*>(scratch);                // 128 destination ids of this warp's edges
+    const uint32_t lane_base = uint32_t(quarter * 32) << 16;
+    const int f = int(rank) * 128 + quarter * 32 + lane;       // D1: this thread's feature
+    const bool f_ok = f < p.n;
+    const float bias_f = f_ok ? __ldg(p.bias + f) : 0.0f;
+    constexpr int kMaxChunks = 8;
+    float bias2[kMaxChunks];
+#pragma unroll
+    for (int k = 0; k < kMaxChunks; ++k) {
+      const int c2 = int(kD2Col) + (par + 2 * k) * 16 + (lane & 15);
+      bias2[k] = ((par + 2 * k) * 16 < p.n2 && c2 < p.n) ? __ldg(p.bias + c2) : 0.0f;
+    }
+    auto flush = [&](int cur, float m) {
+      if (cur >= 0 && f_ok && m > -FLT_MAX && p.act != 99)
+        atomicMax(reinterpret_cast<int*>(p.out + int64_t(cur) * p.n + f), __float_as_int(fmaxf(m + bias_f, 0.0f)));
+    };
+    uint32_t tile_iter = 0;
+    for (int64_t tile = cluster_id; tile < p.num_pair_tiles; tile += num_clusters, ++tile_iter) {
+      // destinations of the 128 edges (D1 columns par*128 ..) this warp drains
+      const int64_t e0 = tile * 256 + int64_t(par) * 128 + lane * 4;
+      int4 d4;
+      int* dd = reinterpret_cast<int*>(&d4);
+#pragma unroll
+      for (int i = 0; i < 4; ++i) {
+        int d = (e0 + i < p.num_rows) ? __ldg(p.dst + e0 + i) : -1;
+        if (d >= p.num_dst || d < -1) { *p.err = 1; d = -1; }
+        dd[i] = d;
+      }
+      // row-major view for D2: this thread's edge row
+      const int64_t row = tile * 256 + int64_t(rank) * kTileRows + quarter * 32 + lane;
+      const bool row_ok = row < p.num_rows;
+      const int64_t warp_row0 = tile * 256 + int64_t(rank) * kTileRows + quarter * 32;
+      SegState st{-1, -1, 0, 0, -1, false};
+      if (p.n2 > 0) {
+        if (row_ok) {
+          st.d = __ldg(p.dst + row);
+          if (st.d < 0 || st.d >= p.num_dst) st.d = -1;
+        }
+        const int prev = __shfl_up_sync(0xffffffffu, st.d, 1);
+        const uint32_t bits = __ballot_sync(0xffffffffu, (lane & 15) != 0 && prev != st.d);
+        const uint32_t mine = (bits >> (lane & 16)) & 0xffffu;
+        st.nb = __popc(mine);
+        st.b = mine ? __ffs(mine) - 1 : 16;
+        st.cur0 = __shfl_sync(0xffffffffu, st.d, lane & 16);
+        st.d_b = __shfl_sync(0xffffffffu, st.d, (lane & 16) + (st.b & 15));
+        const int d16 = __shfl_sync(0xffffffffu, st.d, 16);
+        st.pair = bits == 0 && __shfl_sync(0xffffffffu, st.d, 0) == d16;
+      }
+      __syncwarp();                                   // the previous tile's D2 transposes are done with the scratch
+      *reinterpret_cast<int4*>(ids + lane * 4) = d4;
+      __syncwarp();
+      mbar_wait(sm.bar_tmem_full, tile_iter & 1u);
+      tc_fence_after();
+      // ---- D1: running max along this thread's registers ----------------------------------------
+      {
+        const uint32_t tbase = tmem + lane_base + uint32_t(par * 128);
+        uint32_t v[16];
+        tmem_ld16(tbase, v);
+        int cur = -1;
+        float m = -FLT_MAX;
+#pragma unroll 1
+        for (int c = 0; c < 8; ++c) {
+          tmem_ld_wait();
+          float w[16];
+#pragma unroll
+          for (int j = 0; j < 16; ++j) w[j] = __uint_as_float(v[j]);
+          if (c + 1 < 8) tmem_ld16(tbase + uint32_t((c + 1) * 16), v);
+          const int4 i0 = *reinterpret_cast<const int4*>(ids + c * 16);
+          const int4 i1 = *reinterpret_cast<const int4*>(ids + c * 16 + 4);
+          const int4 i2 = *reinterpret_cast<const int4*>(ids + c * 16 + 8);
+          const int4 i3 = *reinterpret_cast<const int4*>(ids + c * 16 + 12);
+          const int id[16] = {i0.x, i0.y, i0.z, i0.w, i1.x, i1.y, i1.z, i1.w, i2.x, i2.y, i2.z, i2.w, i3.x, i3.y, i3.z, i3.w};
+          if (id[0] == cur && id[15] == cur) {        // warp uniform; destinations are non-decreasing
+            float t = w[0];
+#pragma unroll
+            for (int j = 1; j < 16; ++j) t = fmaxf(t, w[j]);
+            m = fmaxf(m, t);
+          } else {
+#pragma unroll
+            for (int j = 0; j < 16; ++j) {
+              if (id[j] != cur) {                      // warp uniform
+                flush(cur, m);
+                cur = id[j];
+                m = -FLT_MAX;
+              }
+              m = fmaxf(m, w[j]);
+            }
+          }
+        }
+        flush(cur, m);
+      }
+      // ---- D2: features 256 .. (row-major accumulator, transposing epilogue) ----------------------
+      if (p.n2 > 0)
+        epi_section<EPI_SEGMAX, kMaxChunks>(p, tmem + lane_base + kD2Col, int(kD2Col), p.n2, par, scratch, st, lane, row,
+                                            row_ok, warp_row0, bias2);
+      tc_fence_before();
+      __syncwarp();
+      if (lane == 0) mbar_arrive_cluster_relaxed(bar_tmem_empty, 0);
+    }
+  } else {
+    // =================================== producer warps =======================================
+    cluster_sync();   // [sync A]
+    gnn_rows_producer<kProd>(p, sm, threadIdx.x - (kEpiWarps + 1) * 32, lane, rank, cluster_id, num_clusters);
+  }
+
+  // ---- teardown ------------------------------------------------------------------------------
+  tc_fence_before();
+  __syncthreads();
+  cluster_sync();
+  if (warp == kMmaWarp) tmem_dealloc<2>(tmem, p.tmem_cols);
+}
+
+// ================================================================================================
+// mlp_chain_tc_kernel - a chain of fully-connected layers per edge, every layer on the tensor cores,
+// followed by the per-destination max: PointSetPooling's gather -> point MLP -> segment max
+// (/root/reference/models/gnn.py:256-277) without any [E, *] tensor leaving the SM.
+//
+//   layer 1 (4 -> K0, K0 <= 64)  FFMA in the four producer warps (128 FMAs per edge), written as the A
+//                                operand of phase 0
+//   phase p (K_p -> N_p)         tcgen05.mma, BF16x3 split, accumulator D_p in TMEM; all B images are
+//                                resident in shared memory (each CTA of the pair holds its N/2 half)
+//   mid stage p                  the eight epilogue warps drain D_p (tcgen05.ld 16 columns = one
+//                                k-step of the thread's row), add bias, relu, split, and write the A
+//                                operand of phase p+1 straight into the stage ring
+//   final stage                  segment max of the last accumulator (same code as the GNN kernel)
+//
+// One ring of kChainStages A stages carries the k-steps of ALL phases in MMA issue order
+// (iteration it = tile * its_per_tile + phase offset + k-step); its writers are the producer
+// warps (phase 0) or the mid-stage warps of one chunk parity (4 warps x 2 CTAs = 8 arrivals either way).
+constexpr int kChainStages = 4;      // power of two: stage = it & 3, parity = (it >> 2) & 1
+constexpr int kChainMaxPhases = 4;
+constexpr int kChainProdWarps = 4;
+constexpr int kChainThreads = (kEpiWarps + 1 + kChainProdWarps) * 32;   // 416
+constexpr int kChainMaxK0 = 64;
+
+struct ChainPhase {
+  int ks;                // k-steps of this phase (K / 16)
+  int n1, n2;            // MMA instruction split of the padded N (n1 <= 256, n2 <= 256, multiples of 16)
+  uint32_t d_col;        // first TMEM column of the accumulator
+  uint32_t b_off;        // byte offset of this phase's B image (hi part; lo part follows) in the weight region
+  uint32_t part_bytes;   // bytes of one part (hi or lo) of this rank's image
+  uint32_t sbo;          // byte stride between 8-row groups of the image (K / 8 * 128)
+  uint32_t it_off;       // first ring iteration of this phase inside a tile
+  uint32_t bias_off;     // float offset of this phase's (padded) bias in the mid-bias region
+};
+
+struct ChainParams {
+  TcParams seg;             // final epilogue view (out, n, n1, n2, bias, dst, num_rows, num_dst, act)
+  const float* feat;        // [num_src, 1]
+  const float* first;       // layer 1, packed [W (4 x K0) | b (K0)] fp32
+  int k0;
+  const float* mid_bias;    // padded biases of phases 0 .. P-2, concatenated
+  int mid_bias_floats;
+  const uint8_t* wimg;      // per rank: for every phase [hi part | lo part]
+  uint32_t wimg_rank_bytes;
+  int num_phases;
+  uint32_t its_per_tile;
+  ChainPhase ph[kChainMaxPhases];
+};
+
+struct ChainSmem {
+  uint8_t* w;
+  uint8_t* a;             // ring of kChainStages stages: the k-steps of phases >= 1 (written by the mid stages)
+  uint8_t* a0;            // k0 / 16 dedicated stages: the A operand of phase 0 (written by the producer warps)
+  float* first;
+  float* mid_bias;
+  float* scratch;
+  uint64_t* bar_full;     // [kChainStages]  (leader)
+  uint64_t* bar_empty;    // [kChainStages]
+  uint64_t* bar_d_full;   // [kChainMaxPhases]
+  uint64_t* bar_d_empty;  // [kChainMaxPhases] (leader)
+  uint64_t* bar_a0_full;  //                  (leader)
+  uint64_t* bar_a0_empty;
+  uint64_t* bar_wres;
+  uint32_t* tmem;
+};
+
+__host__ __device__ inline size_t chain_smem_layout(uint8_t* base, uint32_t wbytes, int k0, int mid_bias_floats,
+                                                    ChainSmem* m) {
+  size_t off = 0;
+  auto take = [&](size_t bytes) { size_t o = off; off += (bytes + 15) & ~size_t(15); return o; };
+  const size_t o_w = take(wbytes);
+  const size_t o_a = take(size_t(kChainStages) * kStageBytes);
+  const size_t o_a0 = take(size_t(k0 / 16) * kStageBytes);
+  const size_t o_first = take(size_t(5) * k0 * sizeof(float));
+  const size_t o_mb = take(size_t(mid_bias_floats > 0 ? mid_bias_floats : 4) * sizeof(float));
+  const size_t o_scr = take(size_t(kEpiWarps) * kScratchFloats * sizeof(float));
+  const size_t o_bar = take((2 * kChainStages + 2 * kChainMaxPhases + 3) * sizeof(uint64_t));
+  const size_t o_tmem = take(16);
+  if (m != nullptr) {
+    m->w = base + o_w;
+    m->a = base + o_a;
+    m->a0 = base + o_a0;
+    m->first = reinterpret_cast<float*>(base + o_first);
+    m->mid_bias = reinterpret_cast<float*>(base + o_mb);
+    m->scratch = reinterpret_cast<float*>(base + o_scr);
+    uint64_t* bars = reinterpret_cast<uint64_t*>(base + o_bar);
+    m->bar_full = bars;
+    m->bar_empty = bars + kChainStages;
+    m->bar_d_full = bars + 2 * kChainStages;
+    m->bar_d_empty = bars + 2 * kChainStages + kChainMaxPhases;
+    m->bar_a0_full = bars + 2 * kChainStages + 2 * kChainMaxPhases;
+    m->bar_a0_empty = bars + 2 * kChainStages + 2 * kChainMaxPhases + 1;
+    m->bar_wres = bars + 2 * kChainStages + 2 * kChainMaxPhases + 2;
+    m->tmem = reinterpret_cast<uint32_t*>(base + o_tmem);
+  }
+  return off;
+}
+
+// split one k-step (16 values of tile row r) and write it into the A stage at `st` (= stage base + row offset)
+__device__ __forceinline__ void chain_write(uint8_t* st, const float (&v)[16]) {
+  uint4 hi[2], lo[2];
+#pragma unroll
+  for (int h8 = 0; h8 < 2; ++h8) {
+    split_bf16x2(v[8 * h8 + 0], v[8 * h8 + 1], &hi[h8].x, &lo[h8].x);
+    split_bf16x2(v[8 * h8 + 2], v[8 * h8 + 3], &hi[h8].y, &lo[h8].y);
+    split_bf16x2(v[8 * h8 + 4], v[8 * h8 + 5], &hi[h8].z, &lo[h8].z);
+    split_bf16x2(v[8 * h8 + 6], v[8 * h8 + 7], &hi[h8].w, &lo[h8].w);
+  }
+  *reinterpret_cast<uint4*>(st) = hi[0];
+  *reinterpret_cast<uint4*>(st + 128) = hi[1];
+  *reinterpret_cast<uint4*>(st + kStageBytes / 2) = lo[0];
+  *reinterpret_cast<uint4*>(st + kStageBytes / 2 + 128) = lo[1];
+}
+
+// Ring iteration `it` (phases >= 1).  Only the eight mid-stage warps write the ring, each in
+// increasing `it`, and a warp has waited for the accumulator of the previous phase before the first
+// k-step of a phase, so a writer is never more than one lap ahead of the MMA warp: the parity wait
+// on the empty barrier is unambiguous.
+__device__ __forceinline__ void chain_publish(const ChainSmem& sm, uint32_t it, uint32_t a_off, const float (&v)[16],
+                                              int lane) {
+  const uint32_t stage = it & (kChainStages - 1), parity = (it / kChainStages) & 1u;
+  mbar_wait(&sm.bar_empty[stage], parity ^ 1u);
+  chain_write(sm.a + stage * kStageBytes + a_off, v);
+  fence_proxy_async_smem();
+  __syncwarp();
+  if (lane == 0) mbar_arrive_cluster(&sm.bar_full[stage], 0);
+}
+
+__global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kChainThreads, 1) mlp_chain_tc_kernel(ChainParams cp) {
+  extern __shared__ __align__(128) uint8_t smem_raw[];
+  ChainSmem sm;
+  chain_smem_layout(smem_raw, cp.wimg_rank_bytes, cp.k0, cp.mid_bias_floats, &sm);
+  const TcParams& p = cp.seg;
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const uint32_t rank = cluster_ctarank();
+  const int64_t cluster_id = blockIdx.x >> 1;
+  const int64_t num_clusters = gridDim.x >> 1;
+  const int P = cp.num_phases;
+
+  // ---- prologue ------------------------------------------------------------------------------
+  for (int i = threadIdx.x; i < 5 * cp.k0; i += kChainThreads) sm.first[i] = cp.first[i];
+  for (int i = threadIdx.x; i < cp.mid_bias_floats; i += kChainThreads) sm.mid_bias[i] = cp.mid_bias[i];
+  if (threadIdx.x == 0) {
+    for (int i = 0; i < kChainStages; ++i) {
+      mbar_init(&sm.bar_full[i], 2 * 4);      // four writer warps per CTA, both CTAs
+      mbar_init(&sm.bar_empty[i], 1);
+    }
+    for (int i = 0; i < kChainMaxPhases; ++i) {
+      mbar_init(&sm.bar_d_full[i], 1);
+      mbar_init(&sm.bar_d_empty[i], 2 * kEpiWarps);
+    }
+    mbar_init(sm.bar_a0_full, 2 * kChainProdWarps);
+    mbar_init(sm.bar_a0_empty, 1);
+    mbar_init(sm.bar_wres, 1);
+    fence_barrier_init();
+  }
+  if (warp == kMmaWarp) {
+    tmem_alloc<2>(sm.tmem, 512);
+    tmem_relinquish<2>();
+  }
+  tc_fence_before();
+  __syncthreads();
+  cluster_sync();
+  tc_fence_after();
+  const uint32_t tmem = *sm.tmem;
+
+  if (warp == kMmaWarp) {
+    // =================================== MMA warp =============================================
+    if (lane == 0) {
+      mbar_arrive_expect_tx(sm.bar_wres, cp.wimg_rank_bytes);
+      bulk_g2s(sm.w, cp.wimg + size_t(rank) * cp.wimg_rank_bytes, cp.wimg_rank_bytes, sm.bar_wres);
+      mbar_wait(sm.bar_wres, 0);
+    }
+    __syncwarp();
+    cluster_sync();   // [sync A] both CTAs' weights are resident
+    if (rank == 0 && lane == 0) {
+      const uint64_t a_hi0 = make_smem_desc(smem_u32(sm.a), 128, 256);
+      const uint64_t a0_hi0 = make_smem_desc(smem_u32(sm.a0), 128, 256);
+      uint32_t it = 0, tile_iter = 0;
+      for (int64_t tile = cluster_id; tile < p.num_pair_tiles; tile += num_clusters, ++tile_iter) {
+        for (int ph = 0; ph < P; ++ph) {
+          const ChainPhase& c = cp.ph[ph];
+          const uint32_t idesc1 = make_idesc_bf16(256, c.n1);
+          const uint32_t idesc2 = make_idesc_bf16(256, c.n2 > 0 ? c.n2 : 16);
+          const uint64_t b_hi0 = make_smem_desc(smem_u32(sm.w) + c.b_off, 128, c.sbo);
+          const uint64_t b_lo0 = make_smem_desc(smem_u32(sm.w) + c.b_off + c.part_bytes, 128, c.sbo);
+          const uint64_t b2_off = uint64_t((uint32_t(c.n1 / 16) * c.sbo) >> 4);
+          const uint32_t d1 = tmem + c.d_col, d2 = tmem + c.d_col + uint32_t(c.n1);
+          mbar_wait(&sm.bar_d_empty[ph], (tile_iter & 1u) ^ 1u);   // last tile's readers of D_ph are done
+          tc_fence_after();
+          uint64_t kb = 0;
+          if (ph == 0) mbar_wait(sm.bar_a0_full, tile_iter & 1u);
+          for (int s = 0; s < c.ks; ++s, kb += 16) {
+            uint64_t da_hi;
+            uint32_t stage = 0;
+            if (ph == 0) {
+              da_hi = a0_hi0 + uint64_t(uint32_t(s) * (kStageBytes >> 4));
+            } else {
+              stage = it & (kChainStages - 1);
+              mbar_wait(&sm.bar_full[stage], (it / kChainStages) & 1u);
+              da_hi = a_hi0 + uint64_t(stage * (kStageBytes >> 4));
+              ++it;
+            }
+            tc_fence_after();
+            const uint64_t da_lo = da_hi + uint64_t((kStageBytes / 2) >> 4);
+            const uint64_t db_hi = b_hi0 + kb, db_lo = b_lo0 + kb;
+            mma_bf16<2>(d1, da_hi, db_hi, idesc1, s > 0);
+            mma_bf16<2>(d1, da_lo, db_hi, idesc1, true);
+            mma_bf16<2>(d1, da_hi, db_lo, idesc1, true);
+            if (c.n2 > 0) {
+              mma_bf16<2>(d2, da_hi, db_hi + b2_off, idesc2, s > 0);
+              mma_bf16<2>(d2, da_lo, db_hi + b2_off, idesc2, true);
+              mma_bf16<2>(d2, da_hi, db_lo + b2_off, idesc2, true);
+            }
+            if (ph != 0) mma_commit_2cta(&sm.bar_empty[stage], 0x3);
+          }
+          if (ph == 0) mma_commit_2cta(sm.bar_a0_empty, 0x3);   // the producers may write the next tile's layer-1 output
+          mma_commit_2cta(&sm.bar_d_full[ph], 0x3);
+        }
+      }
+    }
+    __syncwarp();
+  } else if (warp < kEpiWarps) {
+    // ============================ mid stages + final epilogue ==================================
+    cluster_sync();   // [sync A]
+    const int quarter = warp & 3, par = warp >> 2;
+    float* scratch = sm.scratch + warp * kScratchFloats;
+    const uint32_t lane_base = uint32_t(quarter * 32) << 16;
+    const int r = quarter * 32 + lane;                       // tile row of this thread (TMEM lane)
+    const uint32_t a_off = uint32_t(r >> 3) * 256u + uint32_t(r & 7) * 16u;
+    constexpr int kMaxChunks = 8;
+    float bias1[kMaxChunks], bias2[kMaxChunks];
+#pragma unroll
+    for (int k = 0; k < kMaxChunks; ++k) {
+      const int c1 = (par + 2 * k) * 16 + (lane & 15);
+      const int c2 = p.n1 + c1;
+      bias1[k] = ((par + 2 * k) * 16 < p.n1 && c1 < p.n) ? __ldg(p.bias + c1) : 0.0f;
+      bias2[k] = ((par + 2 * k) * 16 < p.n2 && c2 < p.n) ? __ldg(p.bias + c2) : 0.0f;
+    }
+    uint32_t tile_iter = 0;
+    for (int64_t tile = cluster_id; tile < p.num_pair_tiles; tile += num_clusters, ++tile_iter) {
+      const int64_t row = tile * 256 + int64_t(rank) * kTileRows + r;
+      const bool row_ok = row < p.num_rows;
+      const int64_t warp_row0 = tile * 256 + int64_t(rank) * kTileRows + quarter * 32;
+      // ---- mid stages: D_ph -> bias, relu -> A operand of phase ph + 1 ---------------------------
+      for (int ph = 0; ph + 1 < P; ++ph) {
+        const ChainPhase& c = cp.ph[ph];
+        const uint32_t it0 = tile_iter * cp.its_per_tile + cp.ph[ph + 1].it_off;
+        const float* bias = sm.mid_bias + c.bias_off;
+        const int chunks = (c.n1 + c.n2) >> 4;                // == k-steps of phase ph + 1
+        mbar_wait(&sm.bar_d_full[ph], tile_iter & 1u);
+        tc_fence_after();
+        uint32_t v[16];
+        if (par < chunks) tmem_ld16(tmem + lane_base + c.d_col + uint32_t(par * 16), v);
+        for (int ci = par; ci < chunks; ci += 2) {
+          tmem_ld_wait();
+          float h[16];
+#pragma unroll
+          for (int j4 = 0; j4 < 4; ++j4) {
+            const float4 b = *reinterpret_cast<const float4*>(bias + ci * 16 + 4 * j4);
+            h[4 * j4 + 0] = fmaxf(__uint_as_float(v[4 * j4 + 0]) + b.x, 0.0f);
+            h[4 * j4 + 1] = fmaxf(__uint_as_float(v[4 * j4 + 1]) + b.y, 0.0f);
+            h[4 * j4 + 2] = fmaxf(__uint_as_float(v[4 * j4 + 2]) + b.z, 0.0f);
+            h[4 * j4 + 3] = fmaxf(__uint_as_float(v[4 * j4 + 3]) + b.w, 0.0f);
+          }
+          if (ci + 2 < chunks) tmem_ld16(tmem + lane_base + c.d_col + uint32_t((ci + 2) * 16), v);
+          chain_publish(sm, it0 + uint32_t(ci), a_off, h, lane);
+        }
+        tmem_ld_wait();
+        tc_fence_before();
+        __syncwarp();
+        if (lane == 0) mbar_arrive_cluster_relaxed(&sm.bar_d_empty[ph], 0);
+      }
+      // ---- final stage: segment max of the last accumulator ------------------------------------
+      SegState st{-1, -1, 0, 0, -1, false};
+      if (row_ok) {
+        st.d = p.dst[row];
+        if (st.d < 0 || st.d >= p.num_dst) { *p.err = 1; st.d = -1; }
+      }
+      {
+        const int prev = __shfl_up_sync(0xffffffffu, st.d, 1);
+        const uint32_t bits = __ballot_sync(0xffffffffu, (lane & 15) != 0 && prev != st.d);
+        const uint32_t mine = (bits >> (lane & 16)) & 0xffffu;
+        st.nb = __popc(mine);
+        st.b = mine ? __ffs(mine) - 1 : 16;
+        st.cur0 = __shfl_sync(0xffffffffu, st.d, lane & 16);
+        st.d_b = __shfl_sync(0xffffffffu, st.d, (lane & 16) + (st.b & 15));
+        const int d16 = __shfl_sync(0xffffffffu, st.d, 16);
+        st.pair = bits == 0 && __shfl_sync(0xffffffffu, st.d, 0) == d16;
+      }
+      const ChainPhase& cl = cp.ph[P - 1];
+      mbar_wait(&sm.bar_d_full[P - 1], tile_iter & 1u);
+      tc_fence_after();
+      epi_section<EPI_SEGMAX, kMaxChunks>(p, tmem + lane_base + cl.d_col, 0, p.n1, par, scratch, st, lane, row, row_ok,
+                                          warp_row0, bias1);
+      if (p.n2 > 0)
+        epi_section<EPI_SEGMAX, kMaxChunks>(p, tmem + lane_base + cl.d_col + uint32_t(p.n1), p.n1, p.n2, par, scratch, st,
+                                            lane, row, row_ok, warp_row0, bias2);
+      tc_fence_before();
+      __syncwarp();
+      if (lane == 0) mbar_arrive_cluster_relaxed(&sm.bar_d_empty[P - 1], 0);
+    }
+  } else {
+    // =================================== producer warps =======================================
+    // layer 1 of the point MLP (gnn.py:264-270): e0 = [feature, x_src - x_dst[kp]], h = relu(e0 @ W + b)
+    cluster_sync();   // [sync A]
+    const int r = threadIdx.x - (kEpiWarps + 1) * 32;         // 0..127: tile row
+    const uint32_t a_off = uint32_t(r >> 3) * 256u + uint32_t(r & 7) * 16u;
+    const int k0 = cp.k0;
+    const float* w = sm.first;            // [4][k0]
+    const float* b = sm.first + 4 * k0;   // [k0]
+    uint32_t tile_iter = 0;
+    for (int64_t tile = cluster_id; tile < p.num_pair_tiles; tile += num_clusters, ++tile_iter) {
+      const int64_t row = tile * 256 + int64_t(rank) * kTileRows + r;
+      int sidx = 0, didx = 0;
+      if (row < p.num_rows) {
+        sidx = __ldg(p.src + row);
+        didx = __ldg(p.dst + row);
+        if (sidx < 0 || sidx >= p.num_src || didx < 0 || didx >= p.num_dst) { *p.err = 1; sidx = 0; didx = 0; }
+      }
+      const int64_t drow = p.dst_index ? int64_t(__ldg(p.dst_index + didx)) : int64_t(didx);
+      const float f0 = __ldg(cp.feat + sidx);
+      const float rx = __ldg(p.xyz_src + int64_t(sidx) * 3 + 0) - __ldg(p.xyz_dst + drow * 3 + 0);
+      const float ry = __ldg(p.xyz_src + int64_t(sidx) * 3 + 1) - __ldg(p.xyz_dst + drow * 3 + 1);
+      const float rz = __ldg(p.xyz_src + int64_t(sidx) * 3 + 2) - __ldg(p.xyz_dst + drow * 3 + 2);
+      mbar_wait(sm.bar_a0_empty, (tile_iter & 1u) ^ 1u);       // phase 0 of the previous tile has been consumed
+      for (int s = 0; s < cp.ph[0].ks; ++s) {
+        float h[16];
+#pragma unroll
+        for (int j = 0; j < 16; ++j) {
+          const int k = s * 16 + j;
+          float t = b[k];
+          t = fmaf(f0, w[k], t);
+          t = fmaf(rx, w[k0 + k], t);
+          t = fmaf(ry, w[2 * k0 + k], t);
+          t = fmaf(rz, w[3 * k0 + k], t);
+          h[j] = fmaxf(t, 0.0f);
+        }
+        chain_write(sm.a0 + s * kStageBytes + a_off, h);
+      }
+      fence_proxy_async_smem();
+      __syncwarp();
+      if (lane == 0) mbar_arrive_cluster(sm.bar_a0_full, 0);
+    }
+  }
+
+  // ---- teardown ------------------------------------------------------------------------------
+  tc_fence_before();
+  __syncthreads();
+  cluster_sync();
+  if (warp == kMmaWarp) tmem_dealloc<2>(tmem, 512);
 }
 
 size_t tc_smem_bytes(int kp, int np, int prod = PROD_GNN) {
@@ -694,7 +1367,7 @@ int launch_row_gemm(TcParams& p, const TcShape& t, const float* w, int k, int n,
   pad_rows_kernel<<<2, 256, 0, s>>>(bias, 1, n, t.np, t_bias.as<float>());
   PG_LAUNCH_CHECK();
   PG_CUDA_OK(t_img.alloc(size_t(4) * t.part, s));
-  pack_w2_kernel<<<std::min(num_sms(), 64), 256, 0, s>>>(w, k, n, t.kp, t.n1, t.n2, t_img.as<uint8_t>(), t.part);
+  pack_w2_kernel<<<std::min(num_sms(), 64), 256, 0, s>>>(w, k, n, t.kp, t.n1, t.n2, t_img.as<uint8_t>(), t.part, 2 * t.part);
   PG_LAUNCH_CHECK();
   p.bias = t_bias.as<float>();
   p.kp = t.kp;
@@ -736,6 +1409,151 @@ int launch_row_gemm(TcParams& p, const TcShape& t, const float* w, int k, int n,
   return PG_OK;
 }
 
+// Launch seg_gemm_tc_kernel (transposed GNN edge GEMM + in-register segment max).  `p` carries the
+// producer fields; W is [k, n] row-major.  Requires k >= 64 (more k-steps than stages) and n <= 512.
+bool seg_gemm_fits(int k, int n) {
+  const int kp = (k + 15) / 16 * 16, np = (n + 15) / 16 * 16;
+  const int n2 = std::max(0, np - 256);
+  const uint32_t part = uint32_t((256 + n2) / 16) * uint32_t(kp / 8) * 128u;
+  return pg_tc_available() && n >= 8 && n2 <= 256 && kp / 16 > kStages &&
+         smem_layout(nullptr, kp, 256 + n2, part, nullptr, PROD_GNN) <= 227 * 1024;
+}
+
+int launch_seg_gemm(TcParams& p, const float* w, int k, int n, const float* bias, Temp& t_img, Temp& t_bias,
+                    cudaStream_t s) {
+  const int kp = (k + 15) / 16 * 16, np = (n + 15) / 16 * 16;
+  const int n2 = std::max(0, np - 256);
+  const uint32_t part = uint32_t((256 + n2) / 16) * uint32_t(kp / 8) * 128u;
+  PG_CUDA_OK(t_bias.alloc(sizeof(float) * (256 + n2), s));
+  pad_rows_kernel<<<2, 256, 0, s>>>(bias, 1, n, 256 + n2, t_bias.as<float>());
+  PG_LAUNCH_CHECK();
+  PG_CUDA_OK(t_img.alloc(size_t(4) * part, s));
+  pack_w2_kernel<<<std::min(num_sms(), 64), 256, 0, s>>>(w, k, n, kp, 256, n2, t_img.as<uint8_t>(), part, 2 * part);
+  PG_LAUNCH_CHECK();
+  p.bias = t_bias.as<float>();
+  p.kp = kp;
+  p.ks = kp / 16;
+  p.n = n;
+  p.np = 256 + n2;
+  p.n1 = 256;
+  p.n2 = n2;
+  p.wimg = t_img.as<uint8_t>();
+  p.part_bytes = part;
+  p.tmem_cols = n2 > 0 ? 512 : 256;
+  p.num_pair_tiles = ceil_div(p.num_rows, 2 * kTileRows);
+  const size_t smem = smem_layout(nullptr, kp, p.np, part, nullptr, PROD_GNN);
+  PG_REQUIRE(smem <= 227 * 1024, "tcgen05 kernel needs %zu B of shared memory", smem);
+  PG_CUDA_OK(cudaFuncSetAttribute(seg_gemm_tc_kernel<PROD_GNN>, cudaFuncAttributeMaxDynamicSharedMemorySize, int(smem)));
+  if (getenv("PG_TC_NOFLUSH") != nullptr) p.act = 99;       // timing experiment only
+  const int clusters = int(std::min<int64_t>(p.num_pair_tiles, num_sms() / 2));
+  seg_gemm_tc_kernel<PROD_GNN><<<2 * clusters, kThreads, smem, s>>>(p);
+  PG_LAUNCH_CHECK();
+  g_tc_launches[0].fetch_add(1, std::memory_order_relaxed);
+  return PG_OK;
+}
+
+// PointSetPooling's per-edge MLP + segment max on the chain kernel.  Returns PG_OK with *handled = false
+// when the layer shapes do not fit it (the caller then falls back to the other paths).
+int pool_chain_launch(const float* features, const float* xyz_src, const float* xyz_dst, const int32_t* dst_index,
+                      const int32_t* src, const int32_t* dst, int64_t num_edges, int64_t num_src, int64_t num_dst,
+                      const float* const* weights, const float* const* biases, const int32_t* dims, int num_layers,
+                      float* out, cudaStream_t s, bool* handled) {
+  *handled = false;
+  const int P = num_layers - 1;
+  if (!pg_tc_available() || P < 1 || P > kChainMaxPhases || dims[0] != 4 || num_edges < 1) return PG_OK;
+  const int k0 = dims[1];
+  if (k0 % 16 != 0 || k0 > kChainMaxK0) return PG_OK;
+  ChainParams cp{};
+  uint32_t d_col = 0, b_off = 0, it_off = 0, bias_off = 0;
+  for (int ph = 0; ph < P; ++ph) {
+    const int k = dims[ph + 1], n = dims[ph + 2];
+    const int np = (n + 15) / 16 * 16;
+    if (k % 16 != 0 || np > 512 || (ph + 1 < P && n % 16 != 0)) return PG_OK;
+    ChainPhase& c = cp.ph[ph];
+    c.ks = k / 16;
+    c.n1 = std::min(np, 256);
+    c.n2 = np - c.n1;
+    c.d_col = d_col;
+    c.sbo = uint32_t(k / 8) * 128u;
+    c.part_bytes = uint32_t(np / 16) * c.sbo;      // this rank's np/2 rows = np/16 groups of 8
+    c.b_off = b_off;
+    c.it_off = it_off;
+    c.bias_off = bias_off;
+    d_col += uint32_t(np);
+    b_off += 2 * c.part_bytes;
+    if (ph > 0) it_off += uint32_t(c.ks);      // the ring carries the k-steps of phases >= 1 only
+    if (ph + 1 < P) bias_off += uint32_t(np);
+  }
+  if (d_col > 512) return PG_OK;
+  cp.num_phases = P;
+  cp.its_per_tile = it_off;
+  cp.wimg_rank_bytes = b_off;
+  cp.mid_bias_floats = int(bias_off);
+  cp.k0 = k0;
+  const size_t smem = chain_smem_layout(nullptr, cp.wimg_rank_bytes, k0, cp.mid_bias_floats, nullptr);
+  if (smem > 227 * 1024) return PG_OK;
+  *handled = true;
+
+  const int n = dims[num_layers], np_last = cp.ph[P - 1].n1 + cp.ph[P - 1].n2;
+  Temp t_first, t_img, t_mid, t_bias, t_err;
+  PG_CUDA_OK(t_first.alloc(sizeof(float) * 5 * k0, s));
+  PG_CUDA_OK(cudaMemcpyAsync(t_first.ptr, weights[0], sizeof(float) * 4 * k0, cudaMemcpyDeviceToDevice, s));
+  PG_CUDA_OK(cudaMemcpyAsync(t_first.as<float>() + 4 * k0, biases[0], sizeof(float) * k0, cudaMemcpyDeviceToDevice, s));
+  PG_CUDA_OK(t_img.alloc(size_t(2) * cp.wimg_rank_bytes, s));
+  PG_CUDA_OK(t_mid.alloc(sizeof(float) * std::max(cp.mid_bias_floats, 4), s));
+  for (int ph = 0; ph < P; ++ph) {
+    const ChainPhase& c = cp.ph[ph];
+    pack_w2_kernel<<<std::min(num_sms(), 64), 256, 0, s>>>(weights[ph + 1], dims[ph + 1], dims[ph + 2], dims[ph + 1], c.n1,
+                                                           c.n2, t_img.as<uint8_t>() + c.b_off, c.part_bytes,
+                                                           cp.wimg_rank_bytes);
+    PG_LAUNCH_CHECK();
+    if (ph + 1 < P) {
+      pad_rows_kernel<<<2, 256, 0, s>>>(biases[ph + 1], 1, dims[ph + 2], c.n1 + c.n2, t_mid.as<float>() + c.bias_off);
+      PG_LAUNCH_CHECK();
+    }
+  }
+  PG_CUDA_OK(t_bias.alloc(sizeof(float) * np_last, s));
+  pad_rows_kernel<<<2, 256, 0, s>>>(biases[num_layers - 1], 1, n, np_last, t_bias.as<float>());
+  PG_LAUNCH_CHECK();
+  PG_CUDA_OK(t_err.alloc(sizeof(int), s));
+  PG_CUDA_OK(cudaMemsetAsync(t_err.ptr, 0, sizeof(int), s));
+  if (int rc = fill_async(out, num_dst * n, -FLT_MAX, s)) return rc;
+
+  cp.feat = features;
+  cp.first = t_first.as<float>();
+  cp.mid_bias = t_mid.as<float>();
+  cp.wimg = t_img.as<uint8_t>();
+  TcParams& p = cp.seg;
+  p.xyz_src = xyz_src;
+  p.xyz_dst = xyz_dst;
+  p.dst_index = dst_index;
+  p.src = src;
+  p.dst = dst;
+  p.num_rows = num_edges;
+  p.num_src = num_src;
+  p.num_dst = num_dst;
+  p.bias = t_bias.as<float>();
+  p.n = n;
+  p.np = np_last;
+  p.n1 = cp.ph[P - 1].n1;
+  p.n2 = cp.ph[P - 1].n2;
+  p.out = out;
+  p.err = t_err.as<int>();
+  p.num_pair_tiles = ceil_div(num_edges, 2 * kTileRows);
+  if (getenv("PG_TC_NOFLUSH") != nullptr) p.act = 99;   // timing experiment only
+  PG_CUDA_OK(cudaFuncSetAttribute(mlp_chain_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, int(smem)));
+  const int clusters = int(std::min<int64_t>(p.num_pair_tiles, num_sms() / 2));
+  mlp_chain_tc_kernel<<<2 * clusters, kChainThreads, smem, s>>>(cp);
+  PG_LAUNCH_CHECK();
+  g_tc_launches[0].fetch_add(1, std::memory_order_relaxed);
+  int h = 0;
+  PG_CUDA_OK(cudaMemcpyAsync(&h, t_err.ptr, sizeof(int), cudaMemcpyDeviceToHost, s));
+  PG_CUDA_OK(cudaStreamSynchronize(s));
+  PG_REQUIRE(h == 0, "set index out of range (point in [0,%lld), keypoint in [0,%lld))", (long long)num_src,
+             (long long)num_dst);
+  return PG_OK;
+}
+
 }  // namespace
 
 int fc_tc_bf16x3(const float* x, int64_t m, int k, const float* w, const float* bias, int n, int act,
@@ -760,6 +1578,13 @@ int edge_mlp_max_tc(int mode, const float* features, int c_in, const float* xyz_
                     const int32_t* dst_index, const int32_t* src, const int32_t* dst, int64_t num_edges,
                     int64_t num_src, int64_t num_dst, const float* const* weights, const float* const* biases,
                     const int32_t* dims, int num_layers, float* out, cudaStream_t s) {
+  if (mode == PG_EDGE_POOL && c_in == 1 && getenv("PG_POOL_NO_CHAIN") == nullptr) {
+    bool handled = false;
+    if (int rc = pool_chain_launch(features, xyz_src, xyz_dst, dst_index, src, dst, num_edges, num_src, num_dst, weights,
+                                   biases, dims, num_layers, out, s, &handled))
+      return rc;
+    if (handled) return PG_OK;
+  }
   TcShape t{};
   const bool pool_tc = mode == PG_EDGE_POOL && num_layers == 4 && c_in == 1 && dims[1] == kPoolC1 &&
                        dims[2] == kPoolC2 && dims[3] == kPoolC3;
@@ -864,7 +1689,11 @@ int edge_mlp_max_tc(int mode, const float* features, int c_in, const float* xyz_
   p.w1x = t_w1x.as<float>();
   p.out = out;
   p.err = t_err.as<int>();
-  if (int rc = launch_row_gemm<PROD_GNN, EPI_SEGMAX>(p, t, weights[1], d1, n, biases[1], t_img, t_bias, s)) return rc;
+  if (getenv("PG_TC_ROWMAJOR") == nullptr && seg_gemm_fits(d1, n)) {
+    if (int rc = launch_seg_gemm(p, weights[1], d1, n, biases[1], t_img, t_bias, s)) return rc;
+  } else if (int rc = launch_row_gemm<PROD_GNN, EPI_SEGMAX>(p, t, weights[1], d1, n, biases[1], t_img, t_bias, s)) {
+    return rc;
+  }
   int h = 0;
   PG_CUDA_OK(cudaMemcpyAsync(&h, t_err.ptr, sizeof(int), cudaMemcpyDeviceToHost, s));
   PG_CUDA_OK(cudaStreamSynchronize(s));
