@@ -539,7 +539,9 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kThreads, 1) row_gem
     }
     __syncwarp();
     cluster_sync();   // both CTAs' weights are resident before the leader issues any MMA   [sync A]
-    if (rank == 0 && lane == 0) {
+    if (rank == 0) {
+      // The whole warp runs this loop converged; elect_one() predicates the tcgen05 instructions only.
+      const uint32_t tmem_u = __shfl_sync(0xffffffffu, tmem, 0);
       const uint32_t idesc1 = make_idesc_bf16(256, p.n1);
       const uint32_t idesc2 = make_idesc_bf16(256, p.n2 > 0 ? p.n2 : 16);
       const uint32_t sbo_b = uint32_t(p.kp / 8) * 128u;
@@ -548,42 +550,41 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kThreads, 1) row_gem
       const uint64_t b_hi0 = make_smem_desc(smem_u32(sm.bres), 128, sbo_b);
       const uint64_t b_lo0 = make_smem_desc(smem_u32(sm.bres) + p.part_bytes, 128, sbo_b);
       const uint64_t b2_off = uint64_t((uint32_t(p.n1 / 16) * sbo_b) >> 4);   // first row group of instruction 2
+      const bool has2 = p.n2 > 0;
       uint32_t it = 0, stage = 0, phase = 0;
       uint32_t tile_iter = 0;
       for (int64_t tile = cluster_id; tile < p.num_pair_tiles; tile += num_clusters, ++tile_iter) {
         const uint32_t buf = tile_iter & 1u;
         mbar_wait(&sm.bar_i1_empty[buf], ((tile_iter >> 1) & 1u) ^ 1u);
-        if (p.n2 > 0) mbar_wait(sm.bar_i2_empty, (tile_iter & 1u) ^ 1u);
+        if (has2) mbar_wait(sm.bar_i2_empty, (tile_iter & 1u) ^ 1u);
         tc_fence_after();
-        const uint32_t d1 = tmem + col_i1[buf], d2 = tmem + col_i2;
+        const uint32_t d1 = tmem_u + (buf ? uint32_t(p.n1 + p.n2) : 0u), d2 = tmem_u + uint32_t(p.n1);
         uint64_t kb = 0;   // (k-step * 256 bytes) >> 4: two K-adjacent cores per k-step
-        bool ready = false;   // full[stage] already observed complete by the probe of the previous k-step
         for (int s = 0; s < p.ks; ++s, ++it, kb += 16) {
-          PG_TRACE(0, it, 0);
-          if (!ready) mbar_wait(&sm.bar_full[stage], phase);
-          PG_TRACE(0, it, 1);
+          if (lane == 0) PG_TRACE(0, it, 0);
+          mbar_wait(&sm.bar_full[stage], phase);
+          if (lane == 0) PG_TRACE(0, it, 1);
           tc_fence_after();
-          // probe the NEXT stage's barrier now: its ~90-cycle latency hides behind the MMA issue below
-          const uint32_t nstage = (stage + 1 == kStages) ? 0u : stage + 1;
-          const uint32_t nphase = (stage + 1 == kStages) ? (phase ^ 1u) : phase;
-          ready = mbar_try_wait(&sm.bar_full[nstage], nphase);
           const uint64_t da_hi = a_hi0 + uint64_t(stage * (kStageBytes >> 4));
           const uint64_t da_lo = da_hi + uint64_t((kStageBytes / 2) >> 4);
           const uint64_t db_hi = b_hi0 + kb, db_lo = b_lo0 + kb;
-          mma_bf16<2>(d1, da_hi, db_hi, idesc1, s > 0);
-          mma_bf16<2>(d1, da_lo, db_hi, idesc1, true);
-          mma_bf16<2>(d1, da_hi, db_lo, idesc1, true);
-          if (p.n2 > 0) {
-            mma_bf16<2>(d2, da_hi, db_hi + b2_off, idesc2, s > 0);
-            mma_bf16<2>(d2, da_lo, db_hi + b2_off, idesc2, true);
-            mma_bf16<2>(d2, da_hi, db_lo + b2_off, idesc2, true);
+          if (elect_one()) {
+            mma_bf16<2>(d1, da_hi, db_hi, idesc1, s > 0);
+            mma_bf16<2>(d1, da_lo, db_hi, idesc1, true);
+            mma_bf16<2>(d1, da_hi, db_lo, idesc1, true);
+            if (has2) {
+              mma_bf16<2>(d2, da_hi, db_hi + b2_off, idesc2, s > 0);
+              mma_bf16<2>(d2, da_lo, db_hi + b2_off, idesc2, true);
+              mma_bf16<2>(d2, da_hi, db_lo + b2_off, idesc2, true);
+            }
+            mma_commit_2cta(&sm.bar_empty[stage], 0x3);    // frees this A stage in both CTAs
           }
-          mma_commit_2cta(&sm.bar_empty[stage], 0x3);    // frees this A stage in both CTAs
-          PG_TRACE(0, it, 2);
-          stage = nstage;
-          phase = nphase;
+          __syncwarp();
+          if (lane == 0) PG_TRACE(0, it, 2);
+          if (++stage == kStages) { stage = 0; phase ^= 1u; }
         }
-        mma_commit_2cta(sm.bar_tmem_full, 0x3);          // accumulators of this tile are complete
+        if (elect_one()) mma_commit_2cta(sm.bar_tmem_full, 0x3);          // accumulators of this tile are complete
+        __syncwarp();
       }
     }
     __syncwarp();
@@ -821,7 +822,9 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kThreads, 1) seg_gem
     }
     __syncwarp();
     cluster_sync();   // [sync A]
-    if (rank == 0 && lane == 0) {
+    if (rank == 0) {
+      // The whole warp runs this loop converged; elect_one() predicates the tcgen05 instructions only.
+      const uint32_t tmem_u = __shfl_sync(0xffffffffu, tmem, 0);
       const uint32_t idesc1 = make_idesc_bf16(256, 256);                       // M = features, N = edges
       const uint32_t idesc2 = make_idesc_bf16(256, p.n2 > 0 ? p.n2 : 16);      // M = edges, N = features
       const uint32_t sbo_b = uint32_t(p.kp / 8) * 128u;
@@ -829,35 +832,38 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kThreads, 1) seg_gem
       const uint64_t w_hi0 = make_smem_desc(smem_u32(sm.bres), 128, sbo_b);
       const uint64_t w_lo0 = make_smem_desc(smem_u32(sm.bres) + p.part_bytes, 128, sbo_b);
       const uint64_t w2_off = uint64_t((16u * sbo_b) >> 4);   // rows 128.. of this rank's image = features 256..
-      const uint32_t d1 = tmem, d2 = tmem + kD2Col;
-      uint32_t stage = 0, phase = 0, tile_iter = 0;
+      const uint32_t d1 = tmem_u, d2 = tmem_u + kD2Col;
+      const bool has2 = p.n2 > 0;
+      uint32_t stage = 0, phase = 0, tile_iter = 0, it = 0;
       for (int64_t tile = cluster_id; tile < p.num_pair_tiles; tile += num_clusters, ++tile_iter) {
         mbar_wait(bar_tmem_empty, (tile_iter & 1u) ^ 1u);
         tc_fence_after();
         uint64_t kb = 0;
-        bool ready = false;
-        for (int s = 0; s < p.ks; ++s, kb += 16) {
-          if (!ready) mbar_wait(&sm.bar_full[stage], phase);
+        for (int s = 0; s < p.ks; ++s, kb += 16, ++it) {
+          if (lane == 0) PG_TRACE(0, it, 0);
+          mbar_wait(&sm.bar_full[stage], phase);
+          if (lane == 0) PG_TRACE(0, it, 1);
           tc_fence_after();
-          const uint32_t nstage = (stage + 1 == kStages) ? 0u : stage + 1;
-          const uint32_t nphase = (stage + 1 == kStages) ? (phase ^ 1u) : phase;
-          ready = mbar_try_wait(&sm.bar_full[nstage], nphase);
           const uint64_t h_hi = h_hi0 + uint64_t(stage * (kStageBytes >> 4));
           const uint64_t h_lo = h_hi + uint64_t((kStageBytes / 2) >> 4);
           const uint64_t w_hi = w_hi0 + kb, w_lo = w_lo0 + kb;
-          mma_bf16<2>(d1, w_hi, h_hi, idesc1, s > 0);
-          mma_bf16<2>(d1, w_hi, h_lo, idesc1, true);
-          mma_bf16<2>(d1, w_lo, h_hi, idesc1, true);
-          if (p.n2 > 0) {
-            mma_bf16<2>(d2, h_hi, w_hi + w2_off, idesc2, s > 0);
-            mma_bf16<2>(d2, h_lo, w_hi + w2_off, idesc2, true);
-            mma_bf16<2>(d2, h_hi, w_lo + w2_off, idesc2, true);
+          if (elect_one()) {
+            mma_bf16<2>(d1, w_hi, h_hi, idesc1, s > 0);
+            mma_bf16<2>(d1, w_hi, h_lo, idesc1, true);
+            mma_bf16<2>(d1, w_lo, h_hi, idesc1, true);
+            if (has2) {
+              mma_bf16<2>(d2, h_hi, w_hi + w2_off, idesc2, s > 0);
+              mma_bf16<2>(d2, h_lo, w_hi + w2_off, idesc2, true);
+              mma_bf16<2>(d2, h_hi, w_lo + w2_off, idesc2, true);
+            }
+            mma_commit_2cta(&sm.bar_empty[stage], 0x3);
           }
-          mma_commit_2cta(&sm.bar_empty[stage], 0x3);
-          stage = nstage;
-          phase = nphase;
+          __syncwarp();
+          if (lane == 0) PG_TRACE(0, it, 2);
+          if (++stage == kStages) { stage = 0; phase ^= 1u; }
         }
-        mma_commit_2cta(sm.bar_tmem_full, 0x3);
+        if (elect_one()) mma_commit_2cta(sm.bar_tmem_full, 0x3);
+        __syncwarp();
       }
     }
     __syncwarp();
@@ -872,12 +878,6 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kThreads, 1) seg_gem
     const bool f_ok = f < p.n;
     const float bias_f = f_ok ? __ldg(p.bias + f) : 0.0f;
     constexpr int kMaxChunks = 8;
-    float bias2[kMaxChunks];
-#pragma unroll
-    for (int k = 0; k < kMaxChunks; ++k) {
-      const int c2 = int(kD2Col) + (par + 2 * k) * 16 + (lane & 15);
-      bias2[k] = ((par + 2 * k) * 16 < p.n2 && c2 < p.n) ? __ldg(p.bias + c2) : 0.0f;
-    }
     auto flush = [&](int cur, float m) {
       if (cur >= 0 && f_ok && m > -FLT_MAX && p.act != 99)
         atomicMax(reinterpret_cast<int*>(p.out + int64_t(cur) * p.n + f), __float_as_int(fmaxf(m + bias_f, 0.0f)));
@@ -898,12 +898,83 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kThreads, 1) seg_gem
       const int64_t row = tile * 256 + int64_t(rank) * kTileRows + quarter * 32 + lane;
       const bool row_ok = row < p.num_rows;
       const int64_t warp_row0 = tile * 256 + int64_t(rank) * kTileRows + quarter * 32;
-      SegState st{-1, -1, 0, 0, -1, false};
+      int row_d = -1;                                  // D2: destination of this thread's edge row
+      if (p.n2 > 0 && row_ok) row_d = __ldg(p.dst + row);
+      __syncwarp();                                   // the previous tile's D2 transposes are done with the scratch
+      *reinterpret_cast<int4*>(ids + lane * 4) = d4;
+      __syncwarp();
+      if (warp == 0 && lane == 0) PG_TRACE(3 + rank, tile_iter, 0);
+      mbar_wait(sm.bar_tmem_full, tile_iter & 1u);
+      if (warp == 0 && lane == 0) PG_TRACE(3 + rank, tile_iter, 1);
+      tc_fence_after();
+      // ---- D1: running max along this thread's registers ----------------------------------------
+      // 128 columns = 4 loads of 32, double buffered (the TMEM load latency, not its bandwidth, is what
+      // an epilogue warp waits for).  Destinations are non-decreasing, so a block of 32 edges lies in one
+      // destination iff its first and last ids are equal (warp-uniform test; the common case).
+      {
+        const uint32_t tbase = tmem + lane_base + uint32_t(par * 128);
+        uint32_t va[32], vb[32];
+        int cur = -1;
+        float m = -FLT_MAX;
+        auto block = [&](const uint32_t (&v)[32], int c) {
+          // bit j of `bits` (j >= 1): a new destination starts at edge j of this block (warp uniform)
+          const int my = ids[c * 32 + lane];
+          const int pv = ids[c * 32 + (lane > 0 ? lane - 1 : 0)];
+          const uint32_t bits = __ballot_sync(0xffffffffu, my != pv);
+          const int first = __shfl_sync(0xffffffffu, my, 0);
+          if (first != cur) {
+            flush(cur, m);
+            cur = first;
+            m = -FLT_MAX;
+          }
+          if (bits == 0) {
+            float t0 = fmaxf(__uint_as_float(v[0]), __uint_as_float(v[1]));
+            float t1 = fmaxf(__uint_as_float(v[2]), __uint_as_float(v[3]));
+#pragma unroll
+            for (int j = 4; j < 32; j += 2) {
+              t0 = fmaxf(t0, __uint_as_float(v[j]));
+              t1 = fmaxf(t1, __uint_as_float(v[j + 1]));
+            }
+            m = fmaxf(m, fmaxf(t0, t1));
+          } else {
+            // one masked max per destination run [sb, eb) of the block; runs are few (a destination has
+            // ~150 edges) and the bounds are warp uniform, so no register is indexed dynamically
+            int sb = 0;
+#pragma unroll 1
+            while (true) {
+              const uint32_t rest = bits >> (sb + 1);
+              const int eb = rest ? sb + __ffs(rest) : 32;
+              float t = -FLT_MAX;
+#pragma unroll
+              for (int j = 0; j < 32; ++j) t = fmaxf(t, (j >= sb && j < eb) ? __uint_as_float(v[j]) : -FLT_MAX);
+              m = fmaxf(m, t);
+              if (eb >= 32) break;
+              flush(cur, m);
+              cur = ids[c * 32 + eb];
+              m = -FLT_MAX;
+              sb = eb;
+            }
+          }
+        };
+        tmem_ld32(tbase, va);
+        tmem_ld_wait();
+        tmem_ld32(tbase + 32, vb);
+        block(va, 0);
+        tmem_ld_wait();
+        tmem_ld32(tbase + 64, va);
+        block(vb, 1);
+        tmem_ld_wait();
+        tmem_ld32(tbase + 96, vb);
+        block(va, 2);
+        tmem_ld_wait();
+        block(vb, 3);
+        flush(cur, m);
+      }
+      if (warp == 0 && lane == 0) PG_TRACE(3 + rank, tile_iter, 2);
+      // ---- D2: features 256 .. (row-major accumulator, transposing epilogue) ----------------------
       if (p.n2 > 0) {
-        if (row_ok) {
-          st.d = __ldg(p.dst + row);
-          if (st.d < 0 || st.d >= p.num_dst) st.d = -1;
-        }
+        SegState st{row_d, -1, 0, 0, -1, false};
+        if (st.d < 0 || st.d >= p.num_dst) st.d = -1;
         const int prev = __shfl_up_sync(0xffffffffu, st.d, 1);
         const uint32_t bits = __ballot_sync(0xffffffffu, (lane & 15) != 0 && prev != st.d);
         const uint32_t mine = (bits >> (lane & 16)) & 0xffffu;
@@ -913,56 +984,18 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kThreads, 1) seg_gem
         st.d_b = __shfl_sync(0xffffffffu, st.d, (lane & 16) + (st.b & 15));
         const int d16 = __shfl_sync(0xffffffffu, st.d, 16);
         st.pair = bits == 0 && __shfl_sync(0xffffffffu, st.d, 0) == d16;
-      }
-      __syncwarp();                                   // the previous tile's D2 transposes are done with the scratch
-      *reinterpret_cast<int4*>(ids + lane * 4) = d4;
-      __syncwarp();
-      mbar_wait(sm.bar_tmem_full, tile_iter & 1u);
-      tc_fence_after();
-      // ---- D1: running max along this thread's registers ----------------------------------------
-      {
-        const uint32_t tbase = tmem + lane_base + uint32_t(par * 128);
-        uint32_t v[16];
-        tmem_ld16(tbase, v);
-        int cur = -1;
-        float m = -FLT_MAX;
-#pragma unroll 1
-        for (int c = 0; c < 8; ++c) {
-          tmem_ld_wait();
-          float w[16];
+        float bias2[kMaxChunks];
 #pragma unroll
-          for (int j = 0; j < 16; ++j) w[j] = __uint_as_float(v[j]);
-          if (c + 1 < 8) tmem_ld16(tbase + uint32_t((c + 1) * 16), v);
-          const int4 i0 = *reinterpret_cast<const int4*>(ids + c * 16);
-          const int4 i1 = *reinterpret_cast<const int4*>(ids + c * 16 + 4);
-          const int4 i2 = *reinterpret_cast<const int4*>(ids + c * 16 + 8);
-          const int4 i3 = *reinterpret_cast<const int4*>(ids + c * 16 + 12);
-          const int id[16] = {i0.x, i0.y, i0.z, i0.w, i1.x, i1.y, i1.z, i1.w, i2.x, i2.y, i2.z, i2.w, i3.x, i3.y, i3.z, i3.w};
-          if (id[0] == cur && id[15] == cur) {        // warp uniform; destinations are non-decreasing
-            float t = w[0];
-#pragma unroll
-            for (int j = 1; j < 16; ++j) t = fmaxf(t, w[j]);
-            m = fmaxf(m, t);
-          } else {
-#pragma unroll
-            for (int j = 0; j < 16; ++j) {
-              if (id[j] != cur) {                      // warp uniform
-                flush(cur, m);
-                cur = id[j];
-                m = -FLT_MAX;
-              }
-              m = fmaxf(m, w[j]);
-            }
-          }
+        for (int k = 0; k < kMaxChunks; ++k) {
+          const int c2 = int(kD2Col) + (par + 2 * k) * 16 + (lane & 15);
+          bias2[k] = ((par + 2 * k) * 16 < p.n2 && c2 < p.n) ? __ldg(p.bias + c2) : 0.0f;
         }
-        flush(cur, m);
-      }
-      // ---- D2: features 256 .. (row-major accumulator, transposing epilogue) ----------------------
-      if (p.n2 > 0)
         epi_section<EPI_SEGMAX, kMaxChunks>(p, tmem + lane_base + kD2Col, int(kD2Col), p.n2, par, scratch, st, lane, row,
                                             row_ok, warp_row0, bias2);
+      }
       tc_fence_before();
       __syncwarp();
+      if (warp == 0 && lane == 0) PG_TRACE(5 + rank, tile_iter, 0);
       if (lane == 0) mbar_arrive_cluster_relaxed(bar_tmem_empty, 0);
     }
   } else {
@@ -1152,7 +1185,9 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kChainThreads, 1) ml
     }
     __syncwarp();
     cluster_sync();   // [sync A] both CTAs' weights are resident
-    if (rank == 0 && lane == 0) {
+    if (rank == 0) {
+      // whole warp converged; elect_one() predicates the tcgen05 instructions (uniform descriptors)
+      const uint32_t tmem_u = __shfl_sync(0xffffffffu, tmem, 0);
       const uint64_t a_hi0 = make_smem_desc(smem_u32(sm.a), 128, 256);
       const uint64_t a0_hi0 = make_smem_desc(smem_u32(sm.a0), 128, 256);
       uint32_t it = 0, tile_iter = 0;
@@ -1164,7 +1199,7 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kChainThreads, 1) ml
           const uint64_t b_hi0 = make_smem_desc(smem_u32(sm.w) + c.b_off, 128, c.sbo);
           const uint64_t b_lo0 = make_smem_desc(smem_u32(sm.w) + c.b_off + c.part_bytes, 128, c.sbo);
           const uint64_t b2_off = uint64_t((uint32_t(c.n1 / 16) * c.sbo) >> 4);
-          const uint32_t d1 = tmem + c.d_col, d2 = tmem + c.d_col + uint32_t(c.n1);
+          const uint32_t d1 = tmem_u + c.d_col, d2 = tmem_u + c.d_col + uint32_t(c.n1);
           mbar_wait(&sm.bar_d_empty[ph], (tile_iter & 1u) ^ 1u);   // last tile's readers of D_ph are done
           tc_fence_after();
           uint64_t kb = 0;
@@ -1183,18 +1218,24 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kChainThreads, 1) ml
             tc_fence_after();
             const uint64_t da_lo = da_hi + uint64_t((kStageBytes / 2) >> 4);
             const uint64_t db_hi = b_hi0 + kb, db_lo = b_lo0 + kb;
-            mma_bf16<2>(d1, da_hi, db_hi, idesc1, s > 0);
-            mma_bf16<2>(d1, da_lo, db_hi, idesc1, true);
-            mma_bf16<2>(d1, da_hi, db_lo, idesc1, true);
-            if (c.n2 > 0) {
-              mma_bf16<2>(d2, da_hi, db_hi + b2_off, idesc2, s > 0);
-              mma_bf16<2>(d2, da_lo, db_hi + b2_off, idesc2, true);
-              mma_bf16<2>(d2, da_hi, db_lo + b2_off, idesc2, true);
+            if (elect_one()) {
+              mma_bf16<2>(d1, da_hi, db_hi, idesc1, s > 0);
+              mma_bf16<2>(d1, da_lo, db_hi, idesc1, true);
+              mma_bf16<2>(d1, da_hi, db_lo, idesc1, true);
+              if (c.n2 > 0) {
+                mma_bf16<2>(d2, da_hi, db_hi + b2_off, idesc2, s > 0);
+                mma_bf16<2>(d2, da_lo, db_hi + b2_off, idesc2, true);
+                mma_bf16<2>(d2, da_hi, db_lo + b2_off, idesc2, true);
+              }
+              if (ph != 0) mma_commit_2cta(&sm.bar_empty[stage], 0x3);
             }
-            if (ph != 0) mma_commit_2cta(&sm.bar_empty[stage], 0x3);
+            __syncwarp();
           }
-          if (ph == 0) mma_commit_2cta(sm.bar_a0_empty, 0x3);   // the producers may write the next tile's layer-1 output
-          mma_commit_2cta(&sm.bar_d_full[ph], 0x3);
+          if (elect_one()) {
+            if (ph == 0) mma_commit_2cta(sm.bar_a0_empty, 0x3);   // the producers may write the next tile's layer-1 output
+            mma_commit_2cta(&sm.bar_d_full[ph], 0x3);
+          }
+          __syncwarp();
         }
       }
     }
@@ -1446,8 +1487,26 @@ int launch_seg_gemm(TcParams& p, const float* w, int k, int n, const float* bias
   PG_CUDA_OK(cudaFuncSetAttribute(seg_gemm_tc_kernel<PROD_GNN>, cudaFuncAttributeMaxDynamicSharedMemorySize, int(smem)));
   if (getenv("PG_TC_NOFLUSH") != nullptr) p.act = 99;       // timing experiment only
   const int clusters = int(std::min<int64_t>(p.num_pair_tiles, num_sms() / 2));
+  const char* trace_path = getenv("PG_TC_TRACE");           // debugging aid
+  Temp t_trace;
+  const size_t trace_words = size_t(8) * 128 * 3;
+  if (trace_path != nullptr) {
+    PG_CUDA_OK(t_trace.alloc(trace_words * 8, s));
+    PG_CUDA_OK(cudaMemsetAsync(t_trace.ptr, 0, trace_words * 8, s));
+    p.trace = t_trace.as<unsigned long long>();
+  }
   seg_gemm_tc_kernel<PROD_GNN><<<2 * clusters, kThreads, smem, s>>>(p);
   PG_LAUNCH_CHECK();
+  if (trace_path != nullptr) {
+    std::vector<unsigned long long> h(trace_words);
+    PG_CUDA_OK(cudaMemcpyAsync(h.data(), t_trace.ptr, trace_words * 8, cudaMemcpyDeviceToHost, s));
+    PG_CUDA_OK(cudaStreamSynchronize(s));
+    if (FILE* f = fopen(trace_path, "w")) {
+      for (size_t i = 0; i < trace_words; i += 3)
+        fprintf(f, "%zu %zu %llu %llu %llu\n", i / 3 / 128, (i / 3) % 128, h[i], h[i + 1], h[i + 2]);
+      fclose(f);
+    }
+  }
   g_tc_launches[0].fetch_add(1, std::memory_order_relaxed);
   return PG_OK;
 }
