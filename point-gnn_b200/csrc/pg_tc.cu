@@ -338,148 +338,185 @@ __device__ __forceinline__ void epi_section(const TcParams& p, uint32_t tbase, i
   }
 }
 
+// 16-byte read-only global load the compiler may not move: the producers' software pipeline depends on
+// WHERE its loads are issued (see gnn_rows_producer), and with ordinary loads ptxas sinks them below the
+// compute that should hide their latency to save registers.
+__device__ __forceinline__ float4 ldg_nc_pinned(const float* ptr) {
+  float4 v;
+  asm volatile("ld.global.nc.v4.f32 {%0, %1, %2, %3}, [%4];" : "=f"(v.x), "=f"(v.y), "=f"(v.z), "=f"(v.w) : "l"(ptr));
+  return v;
+}
+
 // A-operand producers of the GNN edge layer / a plain row matrix (shared by row_gemm_tc_kernel and
 // seg_gemm_tc_kernel).  `pt` = producer thread index 0..255.
+//
+// Two producer groups of four warps; a thread owns tile row r and produces the WHOLE 16-wide k-step of
+// every second pipeline iteration (group g: iterations g, g+2, ...), so two k-steps are in flight per
+// CTA and a thread has two k-step periods per k-step it produces.
+// Load schedule (all latencies are L2 hits, ~1 us under load):
+//   P slice of own iteration i+2   issued right AFTER the fence + arrive of iteration i, into the buffer
+//                                  iteration i just consumed (two register buffers, ping-pong).  It is
+//                                  one full own-iteration old when the next fence executes - the proxy
+//                                  fence compiles to MEMBAR.ALL.CTA, which waits for every load the
+//                                  thread still has in flight, so nothing young may be pending there.
+//   coordinates of the next tile   issued half a tile ahead; edge indices a whole tile ahead.
 template <int kProd>
 __device__ __forceinline__ void gnn_rows_producer(const TcParams& p, const SmemMap& sm, int pt, int lane, uint32_t rank,
                                                   int64_t cluster_id, int64_t num_clusters) {
-    // GNN / ROWS.  Two producer groups of four warps; a thread owns tile row r and produces the
-    // WHOLE 16-wide k-step of every second pipeline iteration (group g: iterations g, g+2, ...),
-    // so two k-steps are always in flight per CTA and each thread has two k-step periods to
-    // produce one.  All global loads are issued one own-iteration (the P slice), half a tile (the
-    // next tile's coordinates) or a whole tile (the next tile's edge indices) before their use.
-    const int r = pt & 127, g = pt >> 7;
-    const uint32_t a_off = uint32_t(r >> 3) * 256u + uint32_t(r & 7) * 16u;
-    const int64_t my_tiles = (p.num_pair_tiles - cluster_id + num_clusters - 1) / num_clusters;
-    const int ks = p.ks, mid = p.ks >> 1;
-    auto row_of = [&](int64_t j) { return (cluster_id + j * num_clusters) * 256 + int64_t(rank) * kTileRows + r; };
-    auto load_idx = [&](int64_t j, int& si, int& di) {
-      si = 0;
-      di = 0;
-      if (kProd == PROD_GNN && j < my_tiles) {
-        const int64_t row = row_of(j);
-        if (row < p.num_rows) {
-          si = __ldg(p.src + row);
-          di = __ldg(p.dst + row);
-        }
-      }
-    };
-    auto check_idx = [&](int& si, int& di) {
-      if (kProd == PROD_GNN && (si < 0 || si >= p.num_src || di < 0 || di >= p.num_dst)) {
-        *p.err = 1;
-        si = 0;
-        di = 0;
-      }
-    };
-    auto load_xyz = [&](int si, int di, float (&x)[6]) {
-      if (kProd == PROD_GNN) {
-        const int64_t drow = p.dst_index ? int64_t(p.dst_index[di]) : int64_t(di);
-        const float* a = p.xyz_src + int64_t(si) * 3;
-        const float* b = p.xyz_dst + drow * 3;
-        x[0] = __ldg(a); x[1] = __ldg(a + 1); x[2] = __ldg(a + 2);
-        x[3] = __ldg(b); x[4] = __ldg(b + 1); x[5] = __ldg(b + 2);
-      }
-    };
-    auto row_ptr_of = [&](int64_t j, int si) -> const float* {
-      if (kProd == PROD_GNN) return p.P + int64_t(si) * p.ldp;
+  const int r = pt & 127, g = pt >> 7;
+  const uint32_t a_off = uint32_t(r >> 3) * 256u + uint32_t(r & 7) * 16u;
+  const int64_t my_tiles = (p.num_pair_tiles - cluster_id + num_clusters - 1) / num_clusters;
+  if (my_tiles <= 0) return;
+  const int ks = p.ks, mid = p.ks >> 1;
+  auto row_of = [&](int64_t j) { return (cluster_id + j * num_clusters) * 256 + int64_t(rank) * kTileRows + r; };
+  auto load_idx = [&](int64_t j, int& si, int& di) {
+    si = 0;
+    di = 0;
+    if (kProd == PROD_GNN && j < my_tiles) {
       const int64_t row = row_of(j);
-      return p.P + (row < p.num_rows ? row : 0) * int64_t(p.ldp);
-    };
-    auto load16 = [&](const float* prow, int s, float4 (&q)[4]) {
-      const float* a = prow + s * 16;
-#pragma unroll
-      for (int i = 0; i < 4; ++i) {
-        if (kProd == PROD_GNN) q[i] = __ldg(reinterpret_cast<const float4*>(a) + i);
-        else q[i] = (s * 16 + 4 * i + 4 <= p.k_real) ? __ldg(reinterpret_cast<const float4*>(a) + i)
-                                                     : make_float4(0.f, 0.f, 0.f, 0.f);
-      }
-    };
-    if (my_tiles > 0) {
-      int64_t j = 0;
-      int s = g;
-      uint32_t stage = uint32_t(g), phase = 0, it = 0;
-      int si_n, di_n;
-      float rx = 0.f, ry = 0.f, rz = 0.f;
-      float nx[6] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
-      const float* prow;
-      {
-        int si, di;
-        load_idx(0, si, di);
-        check_idx(si, di);
-        load_xyz(si, di, nx);
-        rx = nx[0] - nx[3]; ry = nx[1] - nx[4]; rz = nx[2] - nx[5];
-        prow = row_ptr_of(0, si);
-      }
-      load_idx(1, si_n, di_n);
-      float4 q[4];
-      load16(prow, s, q);
-      while (j < my_tiles) {
-        // ---- prefetch this thread's next k-step (two pipeline iterations ahead) ---------------
-        int s2 = s + 2;
-        int64_t j2 = j;
-        if (s2 >= ks) { s2 -= ks; j2 = j + 1; }
-        if ((s == mid || s == mid + 1) && j + 1 < my_tiles) {   // exactly one own iteration per tile
-          check_idx(si_n, di_n);
-          load_xyz(si_n, di_n, nx);
-        }
-        float4 qn[4];
-        if (j2 < my_tiles) load16(j2 == j ? prow : row_ptr_of(j2, si_n), s2, qn);
-        // ---- this k-step: 16 values of row r -------------------------------------------------
-        uint4 hi[2], lo[2];
-#pragma unroll
-        for (int h8 = 0; h8 < 2; ++h8) {
-          const float pv[8] = {q[2 * h8].x, q[2 * h8].y, q[2 * h8].z, q[2 * h8].w,
-                               q[2 * h8 + 1].x, q[2 * h8 + 1].y, q[2 * h8 + 1].z, q[2 * h8 + 1].w};
-          float v[8];
-          if (kProd == PROD_GNN) {
-            const int k0 = s * 16 + h8 * 8;
-            const float4* wx = reinterpret_cast<const float4*>(sm.w1x + k0);
-            const float4* wy = reinterpret_cast<const float4*>(sm.w1x + p.kp + k0);
-            const float4* wz = reinterpret_cast<const float4*>(sm.w1x + 2 * p.kp + k0);
-#pragma unroll
-            for (int i = 0; i < 2; ++i) {
-              const float4 a = wx[i], b = wy[i], c = wz[i];
-              v[4 * i + 0] = fmaxf(fmaf(rz, c.x, fmaf(ry, b.x, fmaf(rx, a.x, pv[4 * i + 0]))), 0.0f);
-              v[4 * i + 1] = fmaxf(fmaf(rz, c.y, fmaf(ry, b.y, fmaf(rx, a.y, pv[4 * i + 1]))), 0.0f);
-              v[4 * i + 2] = fmaxf(fmaf(rz, c.z, fmaf(ry, b.z, fmaf(rx, a.z, pv[4 * i + 2]))), 0.0f);
-              v[4 * i + 3] = fmaxf(fmaf(rz, c.w, fmaf(ry, b.w, fmaf(rx, a.w, pv[4 * i + 3]))), 0.0f);
-            }
-          } else {
-#pragma unroll
-            for (int i = 0; i < 8; ++i) v[i] = pv[i];
-          }
-          split_bf16x2(v[0], v[1], &hi[h8].x, &lo[h8].x);
-          split_bf16x2(v[2], v[3], &hi[h8].y, &lo[h8].y);
-          split_bf16x2(v[4], v[5], &hi[h8].z, &lo[h8].z);
-          split_bf16x2(v[6], v[7], &hi[h8].w, &lo[h8].w);
-        }
-        if (pt == 0) PG_TRACE(1 + rank, it, 0);
-        mbar_wait(&sm.bar_empty[stage], phase ^ 1u);
-        if (pt == 0) PG_TRACE(1 + rank, it, 1);
-        uint8_t* st = sm.a + stage * kStageBytes + a_off;
-        *reinterpret_cast<uint4*>(st) = hi[0];
-        *reinterpret_cast<uint4*>(st + 128) = hi[1];
-        *reinterpret_cast<uint4*>(st + kStageBytes / 2) = lo[0];
-        *reinterpret_cast<uint4*>(st + kStageBytes / 2 + 128) = lo[1];
-        fence_proxy_async_smem();
-        __syncwarp();
-        if (lane == 0) mbar_arrive_cluster(&sm.bar_full[stage], 0);
-        if (pt == 0) PG_TRACE(1 + rank, it, 2);
-        ++it;
-        // ---- advance to the next own iteration ----------------------------------------------
-        stage += 2;
-        if (stage >= uint32_t(kStages)) { stage -= kStages; phase ^= 1u; }
-        if (j2 != j && j2 < my_tiles) {   // tile switch: adopt the prefetched context, look one more tile ahead
-          prow = row_ptr_of(j2, si_n);
-          rx = nx[0] - nx[3]; ry = nx[1] - nx[4]; rz = nx[2] - nx[5];
-          load_idx(j2 + 1, si_n, di_n);
-        }
-        j = j2;
-        s = s2;
-#pragma unroll
-        for (int i = 0; i < 4; ++i) q[i] = qn[i];
+      if (row < p.num_rows) {
+        si = __ldg(p.src + row);
+        di = __ldg(p.dst + row);
       }
     }
+  };
+  auto check_idx = [&](int& si, int& di) {
+    if (kProd == PROD_GNN && (si < 0 || si >= p.num_src || di < 0 || di >= p.num_dst)) {
+      *p.err = 1;
+      si = 0;
+      di = 0;
+    }
+  };
+  auto load_xyz = [&](int si, int di, float (&x)[6]) {
+    if (kProd == PROD_GNN) {
+      const int64_t drow = p.dst_index ? int64_t(p.dst_index[di]) : int64_t(di);
+      const float* a = p.xyz_src + int64_t(si) * 3;
+      const float* b = p.xyz_dst + drow * 3;
+      x[0] = __ldg(a); x[1] = __ldg(a + 1); x[2] = __ldg(a + 2);
+      x[3] = __ldg(b); x[4] = __ldg(b + 1); x[5] = __ldg(b + 2);
+    }
+  };
+  auto row_ptr_of = [&](int64_t j, int si) -> const float* {
+    if (kProd == PROD_GNN) return p.P + int64_t(si) * p.ldp;
+    const int64_t row = row_of(j);
+    return p.P + (row < p.num_rows ? row : 0) * int64_t(p.ldp);
+  };
+  auto load16 = [&](const float* prow, int s, float4 (&q)[4]) {
+    const float* a = prow + s * 16;
+#pragma unroll
+    for (int i = 0; i < 4; ++i) {
+      if (kProd == PROD_GNN || s * 16 + 4 * i + 4 <= p.k_real) q[i] = ldg_nc_pinned(a + 4 * i);
+      else q[i] = make_float4(0.f, 0.f, 0.f, 0.f);
+    }
+  };
+
+  int64_t j = 0;        // tile (local index) of the iteration to produce next
+  int s = g;            // its k-step
+  uint32_t stage = uint32_t(g), phase = 0, it = 0;
+  int si_n, di_n;       // edge of row r in tile j + 1
+  float rx = 0.f, ry = 0.f, rz = 0.f;
+  float nx[6] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
+  const float* prow;
+  {
+    int si, di;
+    load_idx(0, si, di);
+    check_idx(si, di);
+    load_xyz(si, di, nx);
+    rx = nx[0] - nx[3]; ry = nx[1] - nx[4]; rz = nx[2] - nx[5];
+    prow = row_ptr_of(0, si);
+  }
+  load_idx(1, si_n, di_n);
+  auto advance = [&](int64_t& jj, int& ss) {
+    ss += 2;
+    if (ss >= ks) { ss -= ks; ++jj; }
+  };
+  // fetch the P slice of position (jj, ss), jj in {j, j + 1}, into q
+  auto fetch = [&](float4 (&q)[4], int64_t jj, int ss) {
+    if (jj >= my_tiles) return;
+    if (jj != j) check_idx(si_n, di_n);
+    load16(jj == j ? prow : row_ptr_of(jj, si_n), ss, q);
+  };
+  // produce iteration (j, s) from q, then refill q for the iteration two own-steps ahead
+  auto step = [&](float4 (&q)[4]) {
+    if ((s == mid || s == mid + 1) && j + 1 < my_tiles) {   // exactly one own iteration per tile
+      check_idx(si_n, di_n);
+      load_xyz(si_n, di_n, nx);
+    }
+    uint4 hi[2], lo[2];
+#pragma unroll
+    for (int h8 = 0; h8 < 2; ++h8) {
+      const float pv[8] = {q[2 * h8].x, q[2 * h8].y, q[2 * h8].z, q[2 * h8].w,
+                           q[2 * h8 + 1].x, q[2 * h8 + 1].y, q[2 * h8 + 1].z, q[2 * h8 + 1].w};
+      float v[8];
+      if (kProd == PROD_GNN) {
+        const int k0 = s * 16 + h8 * 8;
+        const float4* wx = reinterpret_cast<const float4*>(sm.w1x + k0);
+        const float4* wy = reinterpret_cast<const float4*>(sm.w1x + p.kp + k0);
+        const float4* wz = reinterpret_cast<const float4*>(sm.w1x + 2 * p.kp + k0);
+#pragma unroll
+        for (int i = 0; i < 2; ++i) {
+          const float4 a = wx[i], b = wy[i], c = wz[i];
+          v[4 * i + 0] = fmaxf(fmaf(rz, c.x, fmaf(ry, b.x, fmaf(rx, a.x, pv[4 * i + 0]))), 0.0f);
+          v[4 * i + 1] = fmaxf(fmaf(rz, c.y, fmaf(ry, b.y, fmaf(rx, a.y, pv[4 * i + 1]))), 0.0f);
+          v[4 * i + 2] = fmaxf(fmaf(rz, c.z, fmaf(ry, b.z, fmaf(rx, a.z, pv[4 * i + 2]))), 0.0f);
+          v[4 * i + 3] = fmaxf(fmaf(rz, c.w, fmaf(ry, b.w, fmaf(rx, a.w, pv[4 * i + 3]))), 0.0f);
+        }
+      } else {
+#pragma unroll
+        for (int i = 0; i < 8; ++i) v[i] = pv[i];
+      }
+      split_bf16x2(v[0], v[1], &hi[h8].x, &lo[h8].x);
+      split_bf16x2(v[2], v[3], &hi[h8].y, &lo[h8].y);
+      split_bf16x2(v[4], v[5], &hi[h8].z, &lo[h8].z);
+      split_bf16x2(v[6], v[7], &hi[h8].w, &lo[h8].w);
+    }
+    if (pt == 0) PG_TRACE(1 + rank, it, 0);
+    mbar_wait(&sm.bar_empty[stage], phase ^ 1u);
+    if (pt == 0) PG_TRACE(1 + rank, it, 1);
+    uint8_t* st = sm.a + stage * kStageBytes + a_off;
+    *reinterpret_cast<uint4*>(st) = hi[0];
+    *reinterpret_cast<uint4*>(st + 128) = hi[1];
+    *reinterpret_cast<uint4*>(st + kStageBytes / 2) = lo[0];
+    *reinterpret_cast<uint4*>(st + kStageBytes / 2 + 128) = lo[1];
+    fence_proxy_async_smem();
+    __syncwarp();
+    if (lane == 0) mbar_arrive_cluster(&sm.bar_full[stage], 0);
+    if (pt == 0) PG_TRACE(1 + rank, it, 2);
+    ++it;
+    stage += 2;
+    if (stage >= uint32_t(kStages)) { stage -= kStages; phase ^= 1u; }
+    // positions: n1 = the other buffer's iteration, n2 = the one this buffer is refilled for
+    int64_t j1 = j, j2;
+    int s1 = s, s2;
+    advance(j1, s1);
+    j2 = j1;
+    s2 = s1;
+    advance(j2, s2);
+    fetch(q, j2, s2);
+    asm volatile("" ::: "memory");       // the refill stays here, ahead of the next iteration's compute
+    if (j1 != j && j1 < my_tiles) {      // tile switch: adopt the prefetched context, look one more tile ahead
+      prow = row_ptr_of(j1, si_n);
+      rx = nx[0] - nx[3]; ry = nx[1] - nx[4]; rz = nx[2] - nx[5];
+      load_idx(j1 + 1, si_n, di_n);
+    }
+    j = j1;
+    s = s1;
+  };
+  float4 qa[4], qb[4];
+  load16(prow, s, qa);
+  {
+    int64_t j1 = 0;
+    int s1 = s;
+    advance(j1, s1);
+    fetch(qb, j1, s1);
+  }
+  asm volatile("" ::: "memory");
+  while (true) {
+    step(qa);
+    if (j >= my_tiles) break;
+    step(qb);
+    if (j >= my_tiles) break;
+  }
 }
 
 template <int kProd, int kEpi>
@@ -763,25 +800,225 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kThreads, 1) row_gem
 // ================================================================================================
 // seg_gemm_tc_kernel - the fused GNN edge layer with the big GEMM TRANSPOSED: D1[feature, edge].
 //
-// Same producers, same resident W image and same stage ring as row_gemm_tc_kernel<PROD_GNN, .>, but
-// the first 256 output features are computed as  D1 = W2^T (A operand, M = 256 features over the
-// CTA pair) x h1^T (B operand, N = 256 edges of the pair tile), so that in tensor memory a LANE is a
-// feature and the COLUMNS are the tile's edges.  The per-destination max then runs inside one thread
-// along its registers: no transposition through shared memory, no shuffles, destination boundaries
-// are warp-uniform, the running max is carried across the 128 edges a warp drains, and each flush is
-// one 128-byte coalesced atomicMax (32 consecutive features of one destination).  That removes the
-// ~17 KB of shared-memory traffic per k-step the row-major epilogue costs (the tensor core's operand
-// fetches already use ~2/3 of the shared-memory bandwidth) and ~16x of the atomics.
-// Features 256 .. N-1 (48 of 304 for the car model) keep the row-major form (D2[edge, feature],
-// M = 256 edges, N = n2) and the transposing epilogue: the same two smem operands serve both
-// instructions with the A / B roles swapped.  Accumulators are single buffered (256 + n2 columns):
-// draining D1 takes a few hundred cycles against ~9 000 of MMA per tile.
-template <int kProd>
+// Same resident W image as row_gemm_tc_kernel<PROD_GNN, .>, but the first 256 output features are
+// computed as  D1 = W2^T (A operand, M = 256 features over the CTA pair) x h1^T (B operand, N = 256
+// edges of the pair tile), so that in tensor memory a LANE is a feature and the COLUMNS are the
+// tile's edges.  The per-destination max then runs inside one thread along its registers: no
+// transposition through shared memory, no shuffles, destination boundaries are warp-uniform, the
+// running max is carried across the 128 edges a warp drains, and each flush is one 128-byte coalesced
+// atomicMax (32 consecutive features of one destination).  Features 256 .. N-1 (48 of 304 for the
+// car model) keep the row-major form (D2[edge, feature], M = 256 edges, N = n2; the same two smem
+// operands serve both instructions with the A / B roles swapped) and are reduced per destination run
+// with redux.sync.max.f32.  Accumulators are single buffered (256 + n2 columns).
+//
+// Producers (measured, ncu + in-kernel trace): with one thread per edge row every LDG.128 of the
+// gather touched 32 different cache lines = 32 L1 wavefronts, and the L1 wavefront rate (~1 us of
+// effective load latency, 500+ cycles per k-step) - not the tensor pipe - paced the kernel.  Here four
+// lanes share a row: lane (rr, c) loads the 16-byte slice c of the k-step for rows rr, rr+8, rr+16,
+// rr+24 of its warp, so an LDG.128 covers 8 rows x 64 contiguous bytes (8 lines).  Per-row context
+// (relative coordinates, source vertex) is computed once per tile by the row's owner thread and
+// passed through a small shared-memory table that only the owning warp reads.
+constexpr int kSegStages = 4;
+
+struct SegSmem {
+  uint8_t* bres;
+  uint8_t* a;             // kSegStages stages
+  float* w1x;             // [3][kp]
+  int* ids;               // [kEpiWarps][128] destination ids of the edges a warp drains
+  float4* ctx;            // [2 groups][128 rows] {rx, ry, rz, bits(src vertex)} of the tile being produced
+  int* si_next;           // [2 groups][128 rows] src vertex of the row in the NEXT tile
+  uint64_t* bar_full;     // [kSegStages] (leader)
+  uint64_t* bar_empty;    // [kSegStages]
+  uint64_t* bar_tmem_full;
+  uint64_t* bar_tmem_empty;   // (leader)
+  uint64_t* bar_wres;
+  uint32_t* tmem;
+};
+
+__host__ __device__ inline size_t seg_smem_layout(uint8_t* base, int kp, uint32_t part_bytes, SegSmem* m) {
+  size_t off = 0;
+  auto take = [&](size_t bytes) { size_t o = off; off += (bytes + 15) & ~size_t(15); return o; };
+  const size_t o_bres = take(2 * size_t(part_bytes));
+  const size_t o_a = take(size_t(kSegStages) * kStageBytes);
+  const size_t o_w1x = take(size_t(3) * kp * sizeof(float));
+  const size_t o_ids = take(size_t(kEpiWarps) * 128 * sizeof(int));
+  const size_t o_ctx = take(size_t(2) * 128 * sizeof(float4));
+  const size_t o_sin = take(size_t(2) * 128 * sizeof(int));
+  const size_t o_bar = take((2 * kSegStages + 3) * sizeof(uint64_t));
+  const size_t o_tmem = take(16);
+  if (m != nullptr) {
+    m->bres = base + o_bres;
+    m->a = base + o_a;
+    m->w1x = reinterpret_cast<float*>(base + o_w1x);
+    m->ids = reinterpret_cast<int*>(base + o_ids);
+    m->ctx = reinterpret_cast<float4*>(base + o_ctx);
+    m->si_next = reinterpret_cast<int*>(base + o_sin);
+    uint64_t* bars = reinterpret_cast<uint64_t*>(base + o_bar);
+    m->bar_full = bars;
+    m->bar_empty = bars + kSegStages;
+    m->bar_tmem_full = bars + 2 * kSegStages;
+    m->bar_tmem_empty = bars + 2 * kSegStages + 1;
+    m->bar_wres = bars + 2 * kSegStages + 2;
+    m->tmem = reinterpret_cast<uint32_t*>(base + o_tmem);
+  }
+  return off;
+}
+
+__device__ __forceinline__ float redux_max(float v) {
+  float r;
+  asm volatile("redux.sync.max.f32 %0, %1, 0xffffffff;" : "=f"(r) : "f"(v));
+  return r;
+}
+
+// Producers of seg_gemm_tc_kernel.  pt = producer thread 0..255: group g = pt / 128 produces pipeline
+// iterations g, g+2, ...; warp wg of the group owns tile rows 32 wg .. 32 wg + 31.
+__device__ __forceinline__ void seg_producer(const TcParams& p, const SegSmem& sm, int pt, int lane, uint32_t rank,
+                                             int64_t cluster_id, int64_t num_clusters) {
+  const int g = pt >> 7, wg = (pt >> 5) & 3;
+  const int r = pt & 127;                     // the row whose per-tile context this thread computes
+  const int rr = lane >> 2, c = lane & 3;     // production mapping: rows 32 wg + rr + 8 i (i = 0..3), k-slice c
+  float4* ctx = sm.ctx + g * 128;
+  int* sin = sm.si_next + g * 128;
+  const int row0 = wg * 32 + rr;
+  const uint32_t a_off0 = uint32_t(wg * 4) * 256u + uint32_t(c >> 1) * 128u + uint32_t(rr) * 16u + uint32_t(c & 1) * 8u;
+  const int64_t my_tiles = (p.num_pair_tiles - cluster_id + num_clusters - 1) / num_clusters;
+  if (my_tiles <= 0) return;
+  const int ks = p.ks, mid = p.ks >> 1;
+  auto row_of = [&](int64_t j) { return (cluster_id + j * num_clusters) * 256 + int64_t(rank) * kTileRows + r; };
+  auto load_idx = [&](int64_t j, int& si, int& di) {
+    si = 0;
+    di = 0;
+    if (j < my_tiles) {
+      const int64_t row = row_of(j);
+      if (row < p.num_rows) {
+        si = __ldg(p.src + row);
+        di = __ldg(p.dst + row);
+      }
+    }
+  };
+  auto check_idx = [&](int& si, int& di) {
+    if (si < 0 || si >= p.num_src || di < 0 || di >= p.num_dst) {
+      *p.err = 1;
+      si = 0;
+      di = 0;
+    }
+  };
+  auto load_xyz = [&](int si, int di, float (&x)[6]) {
+    const int64_t drow = p.dst_index ? int64_t(p.dst_index[di]) : int64_t(di);
+    const float* a = p.xyz_src + int64_t(si) * 3;
+    const float* b = p.xyz_dst + drow * 3;
+    x[0] = __ldg(a); x[1] = __ldg(a + 1); x[2] = __ldg(a + 2);
+    x[3] = __ldg(b); x[4] = __ldg(b + 1); x[5] = __ldg(b + 2);
+  };
+
+  int64_t j = 0;        // tile (local index) of the iteration to produce next
+  int s = g;            // its k-step
+  uint32_t it = uint32_t(g);
+  int si_n, di_n;       // edge of row r in tile j + 1
+  float nx[6] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
+  {
+    int si, di;
+    load_idx(0, si, di);
+    check_idx(si, di);
+    load_xyz(si, di, nx);
+    ctx[r] = make_float4(nx[0] - nx[3], nx[1] - nx[4], nx[2] - nx[5], __int_as_float(si));
+    load_idx(1, si_n, di_n);
+    check_idx(si_n, di_n);
+    sin[r] = si_n;
+    load_xyz(si_n, di_n, nx);
+  }
+  __syncwarp();
+  auto advance = [&](int64_t& jj, int& ss) {
+    ss += 2;
+    if (ss >= ks) { ss -= ks; ++jj; }
+  };
+  // slice c of k-step ss of the four rows, tile jj in {j, j + 1}
+  auto fetch = [&](float4 (&q)[4], int64_t jj, int ss) {
+    if (jj >= my_tiles) return;
+#pragma unroll
+    for (int i = 0; i < 4; ++i) {
+      const int si = (jj == j) ? __float_as_int(ctx[row0 + 8 * i].w) : sin[row0 + 8 * i];
+      q[i] = ldg_nc_pinned(p.P + int64_t(si) * p.ldp + ss * 16 + c * 4);
+    }
+  };
+  auto step = [&](float4 (&q)[4]) {
+    if (s == mid || s == mid + 1) {   // exactly one own iteration per tile (warp uniform)
+      // row r of tile j + 1: indices were requested at the last tile switch; publish the source vertex for
+      // the cross-tile prefetches (which start at k-step ks - 4 > mid + 1) and request its coordinates
+      check_idx(si_n, di_n);
+      sin[r] = si_n;
+      load_xyz(si_n, di_n, nx);
+      __syncwarp();
+    }
+    const int k0 = s * 16 + c * 4;
+    const float4 wx = *reinterpret_cast<const float4*>(sm.w1x + k0);
+    const float4 wy = *reinterpret_cast<const float4*>(sm.w1x + p.kp + k0);
+    const float4 wz = *reinterpret_cast<const float4*>(sm.w1x + 2 * p.kp + k0);
+    uint2 hi[4], lo[4];
+#pragma unroll
+    for (int i = 0; i < 4; ++i) {
+      const float4 cx = ctx[row0 + 8 * i];
+      const float v0 = fmaxf(fmaf(cx.z, wz.x, fmaf(cx.y, wy.x, fmaf(cx.x, wx.x, q[i].x))), 0.0f);
+      const float v1 = fmaxf(fmaf(cx.z, wz.y, fmaf(cx.y, wy.y, fmaf(cx.x, wx.y, q[i].y))), 0.0f);
+      const float v2 = fmaxf(fmaf(cx.z, wz.z, fmaf(cx.y, wy.z, fmaf(cx.x, wx.z, q[i].z))), 0.0f);
+      const float v3 = fmaxf(fmaf(cx.z, wz.w, fmaf(cx.y, wy.w, fmaf(cx.x, wx.w, q[i].w))), 0.0f);
+      split_bf16x2(v0, v1, &hi[i].x, &lo[i].x);
+      split_bf16x2(v2, v3, &hi[i].y, &lo[i].y);
+    }
+    const uint32_t stage = it & (kSegStages - 1), parity = (it / kSegStages) & 1u;
+    if (pt == 0) PG_TRACE(1 + rank, it >> 1, 0);
+    mbar_wait(&sm.bar_empty[stage], parity ^ 1u);
+    if (pt == 0) PG_TRACE(1 + rank, it >> 1, 1);
+    uint8_t* st = sm.a + stage * kStageBytes + a_off0;
+#pragma unroll
+    for (int i = 0; i < 4; ++i) {
+      *reinterpret_cast<uint2*>(st + i * 256) = hi[i];
+      *reinterpret_cast<uint2*>(st + i * 256 + kStageBytes / 2) = lo[i];
+    }
+    fence_proxy_async_smem();
+    __syncwarp();
+    if (lane == 0) mbar_arrive_cluster(&sm.bar_full[stage], 0);
+    if (pt == 0) PG_TRACE(1 + rank, it >> 1, 2);
+    it += 2;
+    int64_t j1 = j, j2;
+    int s1 = s, s2;
+    advance(j1, s1);
+    j2 = j1;
+    s2 = s1;
+    advance(j2, s2);
+    fetch(q, j2, s2);
+    asm volatile("" ::: "memory");       // the refill stays here, ahead of the next iteration's compute
+    if (j1 != j && j1 < my_tiles) {
+      // tile switch (warp uniform): publish the row's context for tile j1, look one more tile ahead
+      __syncwarp();
+      ctx[r] = make_float4(nx[0] - nx[3], nx[1] - nx[4], nx[2] - nx[5], __int_as_float(si_n));
+      load_idx(j1 + 1, si_n, di_n);      // consumed at the mid-tile step above
+      __syncwarp();
+    }
+    j = j1;
+    s = s1;
+  };
+  float4 qa[4], qb[4];
+  fetch(qa, 0, s);
+  {
+    int64_t j1 = 0;
+    int s1 = s;
+    advance(j1, s1);
+    fetch(qb, j1, s1);
+  }
+  asm volatile("" ::: "memory");
+  while (true) {
+    step(qa);
+    if (j >= my_tiles) break;
+    step(qb);
+    if (j >= my_tiles) break;
+  }
+}
+
 __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kThreads, 1) seg_gemm_tc_kernel(TcParams p) {
   extern __shared__ __align__(128) uint8_t smem_raw[];
-  SmemMap sm;
-  smem_layout(smem_raw, p.kp, p.np, p.part_bytes, &sm, kProd);
-  uint64_t* bar_tmem_empty = &sm.bar_i1_empty[0];
+  SegSmem sm;
+  seg_smem_layout(smem_raw, p.kp, p.part_bytes, &sm);
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const uint32_t rank = cluster_ctarank();
@@ -791,12 +1028,12 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kThreads, 1) seg_gem
   // ---- prologue ------------------------------------------------------------------------------
   for (int i = threadIdx.x; i < 3 * p.kp; i += kThreads) sm.w1x[i] = p.w1x[i];
   if (threadIdx.x == 0) {
-    for (int i = 0; i < kStages; ++i) {
+    for (int i = 0; i < kSegStages; ++i) {
       mbar_init(&sm.bar_full[i], kProdWarps);     // the four warps of one producer group, both CTAs
       mbar_init(&sm.bar_empty[i], 1);
     }
     mbar_init(sm.bar_tmem_full, 1);
-    mbar_init(bar_tmem_empty, 2 * kEpiWarps);
+    mbar_init(sm.bar_tmem_empty, 2 * kEpiWarps);
     mbar_init(sm.bar_wres, 1);
     fence_barrier_init();
   }
@@ -815,9 +1052,9 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kThreads, 1) seg_gem
     // =================================== MMA warp =============================================
     if (lane == 0) {
       mbar_arrive_expect_tx(sm.bar_wres, 2 * p.part_bytes);
-      const uint8_t* g = p.wimg + size_t(rank) * 2 * p.part_bytes;
-      bulk_g2s(sm.bres, g, p.part_bytes, sm.bar_wres);
-      bulk_g2s(sm.bres + p.part_bytes, g + p.part_bytes, p.part_bytes, sm.bar_wres);
+      const uint8_t* gsrc = p.wimg + size_t(rank) * 2 * p.part_bytes;
+      bulk_g2s(sm.bres, gsrc, p.part_bytes, sm.bar_wres);
+      bulk_g2s(sm.bres + p.part_bytes, gsrc + p.part_bytes, p.part_bytes, sm.bar_wres);
       mbar_wait(sm.bar_wres, 0);
     }
     __syncwarp();
@@ -834,14 +1071,15 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kThreads, 1) seg_gem
       const uint64_t w2_off = uint64_t((16u * sbo_b) >> 4);   // rows 128.. of this rank's image = features 256..
       const uint32_t d1 = tmem_u, d2 = tmem_u + kD2Col;
       const bool has2 = p.n2 > 0;
-      uint32_t stage = 0, phase = 0, tile_iter = 0, it = 0;
+      uint32_t tile_iter = 0, it = 0;
       for (int64_t tile = cluster_id; tile < p.num_pair_tiles; tile += num_clusters, ++tile_iter) {
-        mbar_wait(bar_tmem_empty, (tile_iter & 1u) ^ 1u);
+        mbar_wait(sm.bar_tmem_empty, (tile_iter & 1u) ^ 1u);
         tc_fence_after();
         uint64_t kb = 0;
         for (int s = 0; s < p.ks; ++s, kb += 16, ++it) {
+          const uint32_t stage = it & (kSegStages - 1);
           if (lane == 0) PG_TRACE(0, it, 0);
-          mbar_wait(&sm.bar_full[stage], phase);
+          mbar_wait(&sm.bar_full[stage], (it / kSegStages) & 1u);
           if (lane == 0) PG_TRACE(0, it, 1);
           tc_fence_after();
           const uint64_t h_hi = h_hi0 + uint64_t(stage * (kStageBytes >> 4));
@@ -860,7 +1098,6 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kThreads, 1) seg_gem
           }
           __syncwarp();
           if (lane == 0) PG_TRACE(0, it, 2);
-          if (++stage == kStages) { stage = 0; phase ^= 1u; }
         }
         if (elect_one()) mma_commit_2cta(sm.bar_tmem_full, 0x3);
         __syncwarp();
@@ -871,13 +1108,11 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kThreads, 1) seg_gem
     // =================================== epilogue warps =======================================
     cluster_sync();   // [sync A]
     const int quarter = warp & 3, par = warp >> 2;
-    float* scratch = sm.scratch + warp * kScratchFloats;
-    int* ids = reinterpret_cast<int*>(scratch);                // 128 destination ids of this warp's edges
+    int* ids = sm.ids + warp * 128;                            // 128 destination ids of this warp's edges
     const uint32_t lane_base = uint32_t(quarter * 32) << 16;
     const int f = int(rank) * 128 + quarter * 32 + lane;       // D1: this thread's feature
     const bool f_ok = f < p.n;
     const float bias_f = f_ok ? __ldg(p.bias + f) : 0.0f;
-    constexpr int kMaxChunks = 8;
     auto flush = [&](int cur, float m) {
       if (cur >= 0 && f_ok && m > -FLT_MAX && p.act != 99)
         atomicMax(reinterpret_cast<int*>(p.out + int64_t(cur) * p.n + f), __float_as_int(fmaxf(m + bias_f, 0.0f)));
@@ -894,30 +1129,26 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kThreads, 1) seg_gem
         if (d >= p.num_dst || d < -1) { *p.err = 1; d = -1; }
         dd[i] = d;
       }
-      // row-major view for D2: this thread's edge row
+      // row-major view for D2: this thread's edge row and its destination
       const int64_t row = tile * 256 + int64_t(rank) * kTileRows + quarter * 32 + lane;
-      const bool row_ok = row < p.num_rows;
-      const int64_t warp_row0 = tile * 256 + int64_t(rank) * kTileRows + quarter * 32;
-      int row_d = -1;                                  // D2: destination of this thread's edge row
-      if (p.n2 > 0 && row_ok) row_d = __ldg(p.dst + row);
-      __syncwarp();                                   // the previous tile's D2 transposes are done with the scratch
+      int row_d = -1;
+      if (p.n2 > 0 && row < p.num_rows) row_d = __ldg(p.dst + row);
+      __syncwarp();
       *reinterpret_cast<int4*>(ids + lane * 4) = d4;
       __syncwarp();
-      if (warp == 0 && lane == 0) PG_TRACE(3 + rank, tile_iter, 0);
+      if (warp == 0 && lane == 0) PG_TRACE(3 + 2 * rank, tile_iter, 0);
       mbar_wait(sm.bar_tmem_full, tile_iter & 1u);
-      if (warp == 0 && lane == 0) PG_TRACE(3 + rank, tile_iter, 1);
+      if (warp == 0 && lane == 0) PG_TRACE(3 + 2 * rank, tile_iter, 1);
       tc_fence_after();
       // ---- D1: running max along this thread's registers ----------------------------------------
-      // 128 columns = 4 loads of 32, double buffered (the TMEM load latency, not its bandwidth, is what
-      // an epilogue warp waits for).  Destinations are non-decreasing, so a block of 32 edges lies in one
-      // destination iff its first and last ids are equal (warp-uniform test; the common case).
+      // 128 columns = 4 loads of 32, double buffered.  Destinations are non-decreasing, so a block of 32
+      // edges lies in one destination iff no neighbouring ids differ (warp-uniform ballot).
       {
         const uint32_t tbase = tmem + lane_base + uint32_t(par * 128);
         uint32_t va[32], vb[32];
         int cur = -1;
         float m = -FLT_MAX;
         auto block = [&](const uint32_t (&v)[32], int c) {
-          // bit j of `bits` (j >= 1): a new destination starts at edge j of this block (warp uniform)
           const int my = ids[c * 32 + lane];
           const int pv = ids[c * 32 + (lane > 0 ? lane - 1 : 0)];
           const uint32_t bits = __ballot_sync(0xffffffffu, my != pv);
@@ -937,8 +1168,7 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kThreads, 1) seg_gem
             }
             m = fmaxf(m, fmaxf(t0, t1));
           } else {
-            // one masked max per destination run [sb, eb) of the block; runs are few (a destination has
-            // ~150 edges) and the bounds are warp uniform, so no register is indexed dynamically
+            // one masked max per destination run [sb, eb) of the block (bounds are warp uniform)
             int sb = 0;
 #pragma unroll 1
             while (true) {
@@ -970,38 +1200,48 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kThreads, 1) seg_gem
         block(vb, 3);
         flush(cur, m);
       }
-      if (warp == 0 && lane == 0) PG_TRACE(3 + rank, tile_iter, 2);
-      // ---- D2: features 256 .. (row-major accumulator, transposing epilogue) ----------------------
+      if (warp == 0 && lane == 0) PG_TRACE(3 + 2 * rank, tile_iter, 2);
+      // ---- D2: features 256 .. : lanes are edge rows; one redux.sync.max per column and destination run ----
       if (p.n2 > 0) {
-        SegState st{row_d, -1, 0, 0, -1, false};
-        if (st.d < 0 || st.d >= p.num_dst) st.d = -1;
-        const int prev = __shfl_up_sync(0xffffffffu, st.d, 1);
-        const uint32_t bits = __ballot_sync(0xffffffffu, (lane & 15) != 0 && prev != st.d);
-        const uint32_t mine = (bits >> (lane & 16)) & 0xffffu;
-        st.nb = __popc(mine);
-        st.b = mine ? __ffs(mine) - 1 : 16;
-        st.cur0 = __shfl_sync(0xffffffffu, st.d, lane & 16);
-        st.d_b = __shfl_sync(0xffffffffu, st.d, (lane & 16) + (st.b & 15));
-        const int d16 = __shfl_sync(0xffffffffu, st.d, 16);
-        st.pair = bits == 0 && __shfl_sync(0xffffffffu, st.d, 0) == d16;
-        float bias2[kMaxChunks];
+        int d = row_d;
+        if (d < 0 || d >= p.num_dst) d = -1;
+        const int prev = __shfl_up_sync(0xffffffffu, d, 1);
+        const uint32_t bits = __ballot_sync(0xffffffffu, lane != 0 && prev != d);
+        for (int ci = par; ci * 16 < p.n2; ci += 2) {
+          uint32_t v[16];
+          tmem_ld16(tmem + lane_base + kD2Col + uint32_t(ci * 16), v);
+          tmem_ld_wait();
+          const int col = int(kD2Col) + ci * 16 + (lane & 15);
+          const float bias_c = col < p.n ? __ldg(p.bias + col) : 0.0f;
+          int sb = 0;
+#pragma unroll 1
+          while (true) {
+            const uint32_t rest = bits >> (sb + 1);
+            const int eb = rest ? sb + __ffs(rest) : 32;
+            const bool in_run = lane >= sb && lane < eb;
+            const int dst_run = __shfl_sync(0xffffffffu, d, sb);
+            float mine = -FLT_MAX;
 #pragma unroll
-        for (int k = 0; k < kMaxChunks; ++k) {
-          const int c2 = int(kD2Col) + (par + 2 * k) * 16 + (lane & 15);
-          bias2[k] = ((par + 2 * k) * 16 < p.n2 && c2 < p.n) ? __ldg(p.bias + c2) : 0.0f;
+            for (int jc = 0; jc < 16; ++jc) {
+              const float t = redux_max(in_run ? __uint_as_float(v[jc]) : -FLT_MAX);
+              if ((lane & 15) == jc) mine = t;
+            }
+            if (lane < 16 && dst_run >= 0 && col < p.n && mine > -FLT_MAX && p.act != 99)
+              atomicMax(reinterpret_cast<int*>(p.out + int64_t(dst_run) * p.n + col), __float_as_int(fmaxf(mine + bias_c, 0.0f)));
+            if (eb >= 32) break;
+            sb = eb;
+          }
         }
-        epi_section<EPI_SEGMAX, kMaxChunks>(p, tmem + lane_base + kD2Col, int(kD2Col), p.n2, par, scratch, st, lane, row,
-                                            row_ok, warp_row0, bias2);
       }
       tc_fence_before();
       __syncwarp();
-      if (warp == 0 && lane == 0) PG_TRACE(5 + rank, tile_iter, 0);
-      if (lane == 0) mbar_arrive_cluster_relaxed(bar_tmem_empty, 0);
+      if (warp == 0 && lane == 0) PG_TRACE(4 + 2 * rank, tile_iter, 0);
+      if (lane == 0) mbar_arrive_cluster_relaxed(sm.bar_tmem_empty, 0);
     }
   } else {
     // =================================== producer warps =======================================
     cluster_sync();   // [sync A]
-    gnn_rows_producer<kProd>(p, sm, threadIdx.x - (kEpiWarps + 1) * 32, lane, rank, cluster_id, num_clusters);
+    seg_producer(p, sm, threadIdx.x - (kEpiWarps + 1) * 32, lane, rank, cluster_id, num_clusters);
   }
 
   // ---- teardown ------------------------------------------------------------------------------
@@ -1456,8 +1696,8 @@ bool seg_gemm_fits(int k, int n) {
   const int kp = (k + 15) / 16 * 16, np = (n + 15) / 16 * 16;
   const int n2 = std::max(0, np - 256);
   const uint32_t part = uint32_t((256 + n2) / 16) * uint32_t(kp / 8) * 128u;
-  return pg_tc_available() && n >= 8 && n2 <= 256 && kp / 16 > kStages &&
-         smem_layout(nullptr, kp, 256 + n2, part, nullptr, PROD_GNN) <= 227 * 1024;
+  // ks >= 10: the producers publish next-tile source indices half a tile ahead of their first use
+  return pg_tc_available() && n >= 8 && n2 <= 256 && kp / 16 >= 10 && seg_smem_layout(nullptr, kp, part, nullptr) <= 227 * 1024;
 }
 
 int launch_seg_gemm(TcParams& p, const float* w, int k, int n, const float* bias, Temp& t_img, Temp& t_bias,
@@ -1482,9 +1722,9 @@ int launch_seg_gemm(TcParams& p, const float* w, int k, int n, const float* bias
   p.part_bytes = part;
   p.tmem_cols = n2 > 0 ? 512 : 256;
   p.num_pair_tiles = ceil_div(p.num_rows, 2 * kTileRows);
-  const size_t smem = smem_layout(nullptr, kp, p.np, part, nullptr, PROD_GNN);
+  const size_t smem = seg_smem_layout(nullptr, kp, part, nullptr);
   PG_REQUIRE(smem <= 227 * 1024, "tcgen05 kernel needs %zu B of shared memory", smem);
-  PG_CUDA_OK(cudaFuncSetAttribute(seg_gemm_tc_kernel<PROD_GNN>, cudaFuncAttributeMaxDynamicSharedMemorySize, int(smem)));
+  PG_CUDA_OK(cudaFuncSetAttribute(seg_gemm_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, int(smem)));
   if (getenv("PG_TC_NOFLUSH") != nullptr) p.act = 99;       // timing experiment only
   const int clusters = int(std::min<int64_t>(p.num_pair_tiles, num_sms() / 2));
   const char* trace_path = getenv("PG_TC_TRACE");           // debugging aid
@@ -1495,7 +1735,7 @@ int launch_seg_gemm(TcParams& p, const float* w, int k, int n, const float* bias
     PG_CUDA_OK(cudaMemsetAsync(t_trace.ptr, 0, trace_words * 8, s));
     p.trace = t_trace.as<unsigned long long>();
   }
-  seg_gemm_tc_kernel<PROD_GNN><<<2 * clusters, kThreads, smem, s>>>(p);
+  seg_gemm_tc_kernel<<<2 * clusters, kThreads, smem, s>>>(p);
   PG_LAUNCH_CHECK();
   if (trace_path != nullptr) {
     std::vector<unsigned long long> h(trace_words);

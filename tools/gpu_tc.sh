@@ -1,5 +1,6 @@
 #!/bin/bash
 mkdir -p gpurun_out
-timeout 300 ncu --set full --clock-control none --import-source on -k regex:seg_gemm_tc -s 1 -c 1 -o gpurun_out/seg_tc_r1b python tools/prof_edge.py 8 1 1 > gpurun_out/ncu_seg.log 2>&1
-timeout 300 ncu --set full --clock-control none --import-source on -k regex:mlp_chain -s 1 -c 1 -o gpurun_out/chain_tc_r1b python tools/prof_pool.py 8 1 1 > gpurun_out/ncu_chain.log 2>&1
-ls gpurun_out/*.ncu-rep
+timeout 90 python tools/prof_edge.py 8 5 1 > gpurun_out/prof_edge.log 2>&1; echo "rc=$?"; tail -1 gpurun_out/prof_edge.log
+timeout 240 python -m pytest tests/test_gnn_gpu.py -m gpu -x -q 2>&1 | tail -25 > gpurun_out/pytest_tc.log; tail -6 gpurun_out/pytest_tc.log
+PG_TC_TRACE=gpurun_out/trace.txt timeout 90 python tools/prof_edge.py 8 1 1 > gpurun_out/trace_run.log 2>&1
+python tools/trace_seg.py gpurun_out/trace.txt 19 2>&1 | tee gpurun_out/trace_seg.txt

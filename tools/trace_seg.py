@@ -6,13 +6,16 @@ t0 = d[d[:, 2] > 0][:, 2].min()
 def role(r):
     x = d[d[:, 0] == r]
     return x[:, 2:] - t0
-m, tl, e0, e1, f0 = role(0), role(4), role(3), role(4), role(5)
-print('MMA warp per tile (ns): wait tmem_empty | k-loop span | per k-step: wait / issue / loop')
+m, e0, f0, pr = role(0), role(3), role(4), role(1)
+print('MMA warp per tile (ns): k-loop span | per k-step: wait full / issue / loop | gap to next tile')
 for t in range(1, 6):
     k = m[t * ks:(t + 1) * ks]
-    print('  tile %d: empty-wait %5d | k-loop %6d | wait %4d issue %4d other %4d | next tile starts +%d' % (
-        t, tl[t, 1] - tl[t, 0], tl[t, 2] - tl[t, 1], np.mean(k[:, 1] - k[:, 0]), np.mean(k[:, 2] - k[:, 1]),
-        np.mean(k[1:, 0] - k[:-1, 2]), tl[t + 1, 0] - tl[t, 2]))
-print('epilogue warp 0 of rank 0 (ns after tmem_full observed): D1 done, D2 done')
+    print('  tile %d: k-loop %6d | wait %4d issue %4d other %4d | gap %5d' % (
+        t, k[-1, 2] - k[0, 0], np.mean(k[:, 1] - k[:, 0]), np.mean(k[:, 2] - k[:, 1]),
+        np.mean(k[1:, 0] - k[:-1, 2]), m[(t + 1) * ks, 0] - k[-1, 2]))
+print('epilogue warp 0 of rank 0 (ns): waited for tmem_full | D1 | D2')
 for t in range(1, 6):
-    print('  tile %d: waited %5d for tmem_full | D1 +%5d | D2 +%5d' % (t, e0[t, 1] - e0[t, 0], e0[t, 2] - e0[t, 1], f0[t, 0] - e0[t, 1]))
+    print('  tile %d: waited %5d | D1 %5d | D2 %5d' % (t, e0[t, 1] - e0[t, 0], e0[t, 2] - e0[t, 1], f0[t, 0] - e0[t, 2]))
+print('producer pt0 rank 0, own iterations (ns): compute | wait empty | publish')
+for i in range(12, 24):
+    print('  %3d: compute %5d wait %5d publish %5d' % (i, pr[i, 0] - pr[i - 1, 2], pr[i, 1] - pr[i, 0], pr[i, 2] - pr[i, 1]))
