@@ -797,6 +797,133 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kThreads, 1) row_gem
   if (warp == kMmaWarp) tmem_dealloc<2>(tmem, p.tmem_cols);
 }
 
+__device__ __forceinline__ float redux_max(float v) {
+  float r;
+  asm volatile("redux.sync.max.f32 %0, %1, 0xffffffff;" : "=f"(r) : "f"(v));
+  return r;
+}
+
+// Segment max of a TRANSPOSED accumulator for ONE warp (lane quarter `quarter` of the CTA's TMEM):
+// D1t[feature lanes, 256 edge columns at column d1_col] -> running max along the thread's registers,
+// eight blocks of 32 columns, TMEM loads double buffered.  Destinations are non-decreasing, so a block
+// lies in one destination iff no neighbouring ids differ (warp-uniform ballot); otherwise one masked
+// max per destination run.  Each flush is one 128-byte coalesced atomicMax.
+// `ids[c]` = destination of edge tile*256 + 32 c + lane (-1 beyond the edge list), loaded by the caller
+// BEFORE it waits for the accumulator so that the latency is hidden (segmax_load_ids).
+__device__ __forceinline__ void segmax_load_ids(const TcParams& p, int64_t tile, int lane, int (&ids)[8]) {
+#pragma unroll
+  for (int c = 0; c < 8; ++c) {
+    const int64_t e = tile * 256 + c * 32 + lane;
+    ids[c] = (e < p.num_rows) ? __ldg(p.dst + e) : -1;
+  }
+}
+
+__device__ __forceinline__ void segmax_d1_transposed(const TcParams& p, uint32_t tmem, uint32_t d1_col, uint32_t rank,
+                                                     int quarter, int lane, const int (&ids)[8]) {
+  const uint32_t lane_base = uint32_t(quarter * 32) << 16;
+  const int f = int(rank) * 128 + quarter * 32 + lane;
+  const bool f_ok = f < p.n;
+  const float bias_f = f_ok ? __ldg(p.bias + f) : 0.0f;
+  auto flush = [&](int cur, float m) {
+    if (cur >= 0 && f_ok && m > -FLT_MAX && p.act != 99)
+      atomicMax(reinterpret_cast<int*>(p.out + int64_t(cur) * p.n + f), __float_as_int(fmaxf(m + bias_f, 0.0f)));
+  };
+  {
+    const uint32_t tbase = tmem + lane_base + d1_col;
+    uint32_t va[32], vb[32];
+    int cur = -1;
+    float m = -FLT_MAX;
+    auto block = [&](const uint32_t (&v)[32], int my) {
+      if (my >= p.num_dst || my < -1) { *p.err = 1; my = -1; }
+      const int pv = __shfl_up_sync(0xffffffffu, my, 1);
+      const uint32_t bits = __ballot_sync(0xffffffffu, lane != 0 && my != pv);
+      const int first = __shfl_sync(0xffffffffu, my, 0);
+      if (first != cur) {
+        flush(cur, m);
+        cur = first;
+        m = -FLT_MAX;
+      }
+      if (bits == 0) {
+        float t0 = fmaxf(__uint_as_float(v[0]), __uint_as_float(v[1]));
+        float t1 = fmaxf(__uint_as_float(v[2]), __uint_as_float(v[3]));
+#pragma unroll
+        for (int j = 4; j < 32; j += 2) {
+          t0 = fmaxf(t0, __uint_as_float(v[j]));
+          t1 = fmaxf(t1, __uint_as_float(v[j + 1]));
+        }
+        m = fmaxf(m, fmaxf(t0, t1));
+      } else {
+        int sb = 0;
+#pragma unroll 1
+        while (true) {
+          const uint32_t rest = bits >> (sb + 1);
+          const int eb = rest ? sb + __ffs(rest) : 32;
+          float t = -FLT_MAX;
+#pragma unroll
+          for (int j = 0; j < 32; ++j) t = fmaxf(t, (j >= sb && j < eb) ? __uint_as_float(v[j]) : -FLT_MAX);
+          m = fmaxf(m, t);
+          if (eb >= 32) break;
+          flush(cur, m);
+          cur = __shfl_sync(0xffffffffu, my, eb);
+          m = -FLT_MAX;
+          sb = eb;
+        }
+      }
+    };
+    tmem_ld32(tbase, va);
+#pragma unroll
+    for (int c = 0; c < 8; c += 2) {
+      tmem_ld_wait();
+      tmem_ld32(tbase + uint32_t((c + 1) * 32), vb);
+      block(va, ids[c]);
+      tmem_ld_wait();
+      if (c + 2 < 8) tmem_ld32(tbase + uint32_t((c + 2) * 32), va);
+      block(vb, ids[c + 1]);
+    }
+    flush(cur, m);
+  }
+}
+
+// Segment max of a ROW-MAJOR accumulator D2[edge lanes, n2 feature columns at column d2_col] (output
+// features 256 ..) for ONE warp: one redux.sync.max.f32 per column and destination run.
+__device__ __forceinline__ void segmax_d2_rowmajor(const TcParams& p, uint32_t tmem, uint32_t d2_col, uint32_t rank,
+                                                   int quarter, int lane, int64_t tile) {
+  const uint32_t lane_base = uint32_t(quarter * 32) << 16;
+  const int64_t e_tile = tile * 256;
+  {
+    const int64_t row = e_tile + int64_t(rank) * kTileRows + quarter * 32 + lane;
+    int d = (row < p.num_rows) ? __ldg(p.dst + row) : -1;
+    if (d < 0 || d >= p.num_dst) d = -1;
+    const int prev = __shfl_up_sync(0xffffffffu, d, 1);
+    const uint32_t bits = __ballot_sync(0xffffffffu, lane != 0 && prev != d);
+    for (int ci = 0; ci * 16 < p.n2; ++ci) {
+      uint32_t v[16];
+      tmem_ld16(tmem + lane_base + d2_col + uint32_t(ci * 16), v);
+      tmem_ld_wait();
+      const int col = 256 + ci * 16 + (lane & 15);
+      const float bias_c = col < p.n ? __ldg(p.bias + col) : 0.0f;
+      int sb = 0;
+#pragma unroll 1
+      while (true) {
+        const uint32_t rest = bits >> (sb + 1);
+        const int eb = rest ? sb + __ffs(rest) : 32;
+        const bool in_run = lane >= sb && lane < eb;
+        const int dst_run = __shfl_sync(0xffffffffu, d, sb);
+        float mine = -FLT_MAX;
+#pragma unroll
+        for (int jc = 0; jc < 16; ++jc) {
+          const float t = redux_max(in_run ? __uint_as_float(v[jc]) : -FLT_MAX);
+          if ((lane & 15) == jc) mine = t;
+        }
+        if (lane < 16 && dst_run >= 0 && col < p.n && mine > -FLT_MAX && p.act != 99)
+          atomicMax(reinterpret_cast<int*>(p.out + int64_t(dst_run) * p.n + col), __float_as_int(fmaxf(mine + bias_c, 0.0f)));
+        if (eb >= 32) break;
+        sb = eb;
+      }
+    }
+  }
+}
+
 // ================================================================================================
 // seg_gemm_tc_kernel - the fused GNN edge layer with the big GEMM TRANSPOSED: D1[feature, edge].
 //
@@ -819,18 +946,22 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kThreads, 1) row_gem
 // (relative coordinates, source vertex) is computed once per tile by the row's owner thread and
 // passed through a small shared-memory table that only the owning warp reads.
 constexpr int kSegStages = 4;
+constexpr int kSegEpiWarps = 4;      // warp w drains TMEM lane quarter w
+constexpr int kSegMmaWarp = 4;
+constexpr int kSegGroups = 3;        // producer groups of four warps; group g produces iterations g, g+3, ...
+constexpr int kSegThreads = (kSegEpiWarps + 1 + 4 * kSegGroups) * 32;   // 544
 
 struct SegSmem {
   uint8_t* bres;
   uint8_t* a;             // kSegStages stages
   float* w1x;             // [3][kp]
-  int* ids;               // [kEpiWarps][128] destination ids of the edges a warp drains
-  float4* ctx;            // [2 groups][128 rows] {rx, ry, rz, bits(src vertex)} of the tile being produced
-  int* si_next;           // [2 groups][128 rows] src vertex of the row in the NEXT tile
+  float4* ctx;            // [groups][128 rows] {rx, ry, rz, bits(src vertex)} of the tile being produced
+  int* si_next;           // [groups][128 rows] src vertex of the row in the NEXT tile
   uint64_t* bar_full;     // [kSegStages] (leader)
   uint64_t* bar_empty;    // [kSegStages]
   uint64_t* bar_tmem_full;
-  uint64_t* bar_tmem_empty;   // (leader)
+  uint64_t* bar_d1_empty;     // (leader) D1 of the previous tile has been drained
+  uint64_t* bar_d2_empty;     // [2] (leader) D2 buffer b has been drained
   uint64_t* bar_wres;
   uint32_t* tmem;
 };
@@ -841,37 +972,32 @@ __host__ __device__ inline size_t seg_smem_layout(uint8_t* base, int kp, uint32_
   const size_t o_bres = take(2 * size_t(part_bytes));
   const size_t o_a = take(size_t(kSegStages) * kStageBytes);
   const size_t o_w1x = take(size_t(3) * kp * sizeof(float));
-  const size_t o_ids = take(size_t(kEpiWarps) * 128 * sizeof(int));
-  const size_t o_ctx = take(size_t(2) * 128 * sizeof(float4));
-  const size_t o_sin = take(size_t(2) * 128 * sizeof(int));
-  const size_t o_bar = take((2 * kSegStages + 3) * sizeof(uint64_t));
+  const size_t o_ctx = take(size_t(kSegGroups) * 128 * sizeof(float4));
+  const size_t o_sin = take(size_t(kSegGroups) * 128 * sizeof(int));
+  const size_t o_bar = take((2 * kSegStages + 5) * sizeof(uint64_t));
   const size_t o_tmem = take(16);
   if (m != nullptr) {
     m->bres = base + o_bres;
     m->a = base + o_a;
     m->w1x = reinterpret_cast<float*>(base + o_w1x);
-    m->ids = reinterpret_cast<int*>(base + o_ids);
     m->ctx = reinterpret_cast<float4*>(base + o_ctx);
     m->si_next = reinterpret_cast<int*>(base + o_sin);
     uint64_t* bars = reinterpret_cast<uint64_t*>(base + o_bar);
     m->bar_full = bars;
     m->bar_empty = bars + kSegStages;
     m->bar_tmem_full = bars + 2 * kSegStages;
-    m->bar_tmem_empty = bars + 2 * kSegStages + 1;
-    m->bar_wres = bars + 2 * kSegStages + 2;
+    m->bar_d1_empty = bars + 2 * kSegStages + 1;
+    m->bar_d2_empty = bars + 2 * kSegStages + 2;
+    m->bar_wres = bars + 2 * kSegStages + 4;
     m->tmem = reinterpret_cast<uint32_t*>(base + o_tmem);
   }
   return off;
 }
 
-__device__ __forceinline__ float redux_max(float v) {
-  float r;
-  asm volatile("redux.sync.max.f32 %0, %1, 0xffffffff;" : "=f"(r) : "f"(v));
-  return r;
-}
-
-// Producers of seg_gemm_tc_kernel.  pt = producer thread 0..255: group g = pt / 128 produces pipeline
-// iterations g, g+2, ...; warp wg of the group owns tile rows 32 wg .. 32 wg + 31.
+// Producers of seg_gemm_tc_kernel.  pt = producer thread 0..383: group g = pt / 128 produces pipeline
+// iterations g, g+3, ... (measured: a producer warp is instruction-latency bound at ~350 ns per
+// k-step it produces, so three groups are needed to stay ahead of the ~270 ns the tensor core takes);
+// warp wg of the group owns tile rows 32 wg .. 32 wg + 31.
 __device__ __forceinline__ void seg_producer(const TcParams& p, const SegSmem& sm, int pt, int lane, uint32_t rank,
                                              int64_t cluster_id, int64_t num_clusters) {
   const int g = pt >> 7, wg = (pt >> 5) & 3;
@@ -913,7 +1039,7 @@ __device__ __forceinline__ void seg_producer(const TcParams& p, const SegSmem& s
 
   int64_t j = 0;        // tile (local index) of the iteration to produce next
   int s = g;            // its k-step
-  uint32_t it = uint32_t(g);
+  uint32_t it = uint32_t(g);   // global pipeline iteration (stage = it % kSegStages)
   int si_n, di_n;       // edge of row r in tile j + 1
   float nx[6] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
   {
@@ -929,7 +1055,7 @@ __device__ __forceinline__ void seg_producer(const TcParams& p, const SegSmem& s
   }
   __syncwarp();
   auto advance = [&](int64_t& jj, int& ss) {
-    ss += 2;
+    ss += kSegGroups;
     if (ss >= ks) { ss -= ks; ++jj; }
   };
   // slice c of k-step ss of the four rows, tile jj in {j, j + 1}
@@ -942,9 +1068,9 @@ __device__ __forceinline__ void seg_producer(const TcParams& p, const SegSmem& s
     }
   };
   auto step = [&](float4 (&q)[4]) {
-    if (s == mid || s == mid + 1) {   // exactly one own iteration per tile (warp uniform)
+    if (s >= mid && s < mid + kSegGroups) {   // exactly one own iteration per tile (warp uniform)
       // row r of tile j + 1: indices were requested at the last tile switch; publish the source vertex for
-      // the cross-tile prefetches (which start at k-step ks - 4 > mid + 1) and request its coordinates
+      // the cross-tile prefetches (which start at k-step ks - 2 * kSegGroups >= mid) and request its coordinates
       check_idx(si_n, di_n);
       sin[r] = si_n;
       load_xyz(si_n, di_n, nx);
@@ -966,9 +1092,9 @@ __device__ __forceinline__ void seg_producer(const TcParams& p, const SegSmem& s
       split_bf16x2(v2, v3, &hi[i].y, &lo[i].y);
     }
     const uint32_t stage = it & (kSegStages - 1), parity = (it / kSegStages) & 1u;
-    if (pt == 0) PG_TRACE(1 + rank, it >> 1, 0);
+    if (pt == 0) PG_TRACE(1 + rank, it / kSegGroups, 0);
     mbar_wait(&sm.bar_empty[stage], parity ^ 1u);
-    if (pt == 0) PG_TRACE(1 + rank, it >> 1, 1);
+    if (pt == 0) PG_TRACE(1 + rank, it / kSegGroups, 1);
     uint8_t* st = sm.a + stage * kStageBytes + a_off0;
 #pragma unroll
     for (int i = 0; i < 4; ++i) {
@@ -978,8 +1104,8 @@ __device__ __forceinline__ void seg_producer(const TcParams& p, const SegSmem& s
     fence_proxy_async_smem();
     __syncwarp();
     if (lane == 0) mbar_arrive_cluster(&sm.bar_full[stage], 0);
-    if (pt == 0) PG_TRACE(1 + rank, it >> 1, 2);
-    it += 2;
+    if (pt == 0) PG_TRACE(1 + rank, it / kSegGroups, 2);
+    it += kSegGroups;
     int64_t j1 = j, j2;
     int s1 = s, s2;
     advance(j1, s1);
@@ -1015,7 +1141,7 @@ __device__ __forceinline__ void seg_producer(const TcParams& p, const SegSmem& s
   }
 }
 
-__global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kThreads, 1) seg_gemm_tc_kernel(TcParams p) {
+__global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kSegThreads, 1) seg_gemm_tc_kernel(TcParams p) {
   extern __shared__ __align__(128) uint8_t smem_raw[];
   SegSmem sm;
   seg_smem_layout(smem_raw, p.kp, p.part_bytes, &sm);
@@ -1024,20 +1150,26 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kThreads, 1) seg_gem
   const uint32_t rank = cluster_ctarank();
   const int64_t cluster_id = blockIdx.x >> 1;
   const int64_t num_clusters = gridDim.x >> 1;
+  // D2 (output features 256 ..) is double buffered when two copies fit beside the 256 columns of D1, so
+  // the tensor core restarts as soon as D1 has been drained
+  constexpr uint32_t kD2Col = 256;
+  const uint32_t d2_stride = (p.n2 > 0 && 256 + 2 * p.n2 <= 512) ? uint32_t(p.n2) : 0u;
 
   // ---- prologue ------------------------------------------------------------------------------
-  for (int i = threadIdx.x; i < 3 * p.kp; i += kThreads) sm.w1x[i] = p.w1x[i];
+  for (int i = threadIdx.x; i < 3 * p.kp; i += kSegThreads) sm.w1x[i] = p.w1x[i];
   if (threadIdx.x == 0) {
     for (int i = 0; i < kSegStages; ++i) {
-      mbar_init(&sm.bar_full[i], kProdWarps);     // the four warps of one producer group, both CTAs
+      mbar_init(&sm.bar_full[i], 2 * 4);          // the four warps of one producer group, both CTAs
       mbar_init(&sm.bar_empty[i], 1);
     }
     mbar_init(sm.bar_tmem_full, 1);
-    mbar_init(sm.bar_tmem_empty, 2 * kEpiWarps);
+    mbar_init(sm.bar_d1_empty, 2 * kSegEpiWarps);
+    mbar_init(&sm.bar_d2_empty[0], 2 * kSegEpiWarps);
+    mbar_init(&sm.bar_d2_empty[1], 2 * kSegEpiWarps);
     mbar_init(sm.bar_wres, 1);
     fence_barrier_init();
   }
-  if (warp == kMmaWarp) {
+  if (warp == kSegMmaWarp) {
     tmem_alloc<2>(sm.tmem, p.tmem_cols);
     tmem_relinquish<2>();
   }
@@ -1046,9 +1178,8 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kThreads, 1) seg_gem
   cluster_sync();
   tc_fence_after();
   const uint32_t tmem = *sm.tmem;
-  constexpr uint32_t kD2Col = 256;
 
-  if (warp == kMmaWarp) {
+  if (warp == kSegMmaWarp) {
     // =================================== MMA warp =============================================
     if (lane == 0) {
       mbar_arrive_expect_tx(sm.bar_wres, 2 * p.part_bytes);
@@ -1069,11 +1200,17 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kThreads, 1) seg_gem
       const uint64_t w_hi0 = make_smem_desc(smem_u32(sm.bres), 128, sbo_b);
       const uint64_t w_lo0 = make_smem_desc(smem_u32(sm.bres) + p.part_bytes, 128, sbo_b);
       const uint64_t w2_off = uint64_t((16u * sbo_b) >> 4);   // rows 128.. of this rank's image = features 256..
-      const uint32_t d1 = tmem_u, d2 = tmem_u + kD2Col;
       const bool has2 = p.n2 > 0;
       uint32_t tile_iter = 0, it = 0;
       for (int64_t tile = cluster_id; tile < p.num_pair_tiles; tile += num_clusters, ++tile_iter) {
-        mbar_wait(sm.bar_tmem_empty, (tile_iter & 1u) ^ 1u);
+        const uint32_t buf = d2_stride ? (tile_iter & 1u) : 0u;
+        const uint32_t d1 = tmem_u, d2 = tmem_u + kD2Col + buf * d2_stride;
+        mbar_wait(sm.bar_d1_empty, (tile_iter & 1u) ^ 1u);
+        if (has2) {
+          // completions of d2_empty[buf]: one per tile that used the buffer
+          const uint32_t use = d2_stride ? (tile_iter >> 1) : tile_iter;
+          mbar_wait(&sm.bar_d2_empty[buf], (use & 1u) ^ 1u);
+        }
         tc_fence_after();
         uint64_t kb = 0;
         for (int s = 0; s < p.ks; ++s, kb += 16, ++it) {
@@ -1104,151 +1241,43 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kThreads, 1) seg_gem
       }
     }
     __syncwarp();
-  } else if (warp < kEpiWarps) {
+  } else if (warp < kSegEpiWarps) {
     // =================================== epilogue warps =======================================
     cluster_sync();   // [sync A]
-    const int quarter = warp & 3, par = warp >> 2;
-    int* ids = sm.ids + warp * 128;                            // 128 destination ids of this warp's edges
-    const uint32_t lane_base = uint32_t(quarter * 32) << 16;
-    const int f = int(rank) * 128 + quarter * 32 + lane;       // D1: this thread's feature
-    const bool f_ok = f < p.n;
-    const float bias_f = f_ok ? __ldg(p.bias + f) : 0.0f;
-    auto flush = [&](int cur, float m) {
-      if (cur >= 0 && f_ok && m > -FLT_MAX && p.act != 99)
-        atomicMax(reinterpret_cast<int*>(p.out + int64_t(cur) * p.n + f), __float_as_int(fmaxf(m + bias_f, 0.0f)));
-    };
+    const int quarter = warp;
     uint32_t tile_iter = 0;
     for (int64_t tile = cluster_id; tile < p.num_pair_tiles; tile += num_clusters, ++tile_iter) {
-      // destinations of the 128 edges (D1 columns par*128 ..) this warp drains
-      const int64_t e0 = tile * 256 + int64_t(par) * 128 + lane * 4;
-      int4 d4;
-      int* dd = reinterpret_cast<int*>(&d4);
-#pragma unroll
-      for (int i = 0; i < 4; ++i) {
-        int d = (e0 + i < p.num_rows) ? __ldg(p.dst + e0 + i) : -1;
-        if (d >= p.num_dst || d < -1) { *p.err = 1; d = -1; }
-        dd[i] = d;
-      }
-      // row-major view for D2: this thread's edge row and its destination
-      const int64_t row = tile * 256 + int64_t(rank) * kTileRows + quarter * 32 + lane;
-      int row_d = -1;
-      if (p.n2 > 0 && row < p.num_rows) row_d = __ldg(p.dst + row);
-      __syncwarp();
-      *reinterpret_cast<int4*>(ids + lane * 4) = d4;
-      __syncwarp();
+      const uint32_t buf = d2_stride ? (tile_iter & 1u) : 0u;
+      int ids[8];
+      segmax_load_ids(p, tile, lane, ids);
       if (warp == 0 && lane == 0) PG_TRACE(3 + 2 * rank, tile_iter, 0);
       mbar_wait(sm.bar_tmem_full, tile_iter & 1u);
       if (warp == 0 && lane == 0) PG_TRACE(3 + 2 * rank, tile_iter, 1);
       tc_fence_after();
-      // ---- D1: running max along this thread's registers ----------------------------------------
-      // 128 columns = 4 loads of 32, double buffered.  Destinations are non-decreasing, so a block of 32
-      // edges lies in one destination iff no neighbouring ids differ (warp-uniform ballot).
-      {
-        const uint32_t tbase = tmem + lane_base + uint32_t(par * 128);
-        uint32_t va[32], vb[32];
-        int cur = -1;
-        float m = -FLT_MAX;
-        auto block = [&](const uint32_t (&v)[32], int c) {
-          const int my = ids[c * 32 + lane];
-          const int pv = ids[c * 32 + (lane > 0 ? lane - 1 : 0)];
-          const uint32_t bits = __ballot_sync(0xffffffffu, my != pv);
-          const int first = __shfl_sync(0xffffffffu, my, 0);
-          if (first != cur) {
-            flush(cur, m);
-            cur = first;
-            m = -FLT_MAX;
-          }
-          if (bits == 0) {
-            float t0 = fmaxf(__uint_as_float(v[0]), __uint_as_float(v[1]));
-            float t1 = fmaxf(__uint_as_float(v[2]), __uint_as_float(v[3]));
-#pragma unroll
-            for (int j = 4; j < 32; j += 2) {
-              t0 = fmaxf(t0, __uint_as_float(v[j]));
-              t1 = fmaxf(t1, __uint_as_float(v[j + 1]));
-            }
-            m = fmaxf(m, fmaxf(t0, t1));
-          } else {
-            // one masked max per destination run [sb, eb) of the block (bounds are warp uniform)
-            int sb = 0;
-#pragma unroll 1
-            while (true) {
-              const uint32_t rest = bits >> (sb + 1);
-              const int eb = rest ? sb + __ffs(rest) : 32;
-              float t = -FLT_MAX;
-#pragma unroll
-              for (int j = 0; j < 32; ++j) t = fmaxf(t, (j >= sb && j < eb) ? __uint_as_float(v[j]) : -FLT_MAX);
-              m = fmaxf(m, t);
-              if (eb >= 32) break;
-              flush(cur, m);
-              cur = ids[c * 32 + eb];
-              m = -FLT_MAX;
-              sb = eb;
-            }
-          }
-        };
-        tmem_ld32(tbase, va);
-        tmem_ld_wait();
-        tmem_ld32(tbase + 32, vb);
-        block(va, 0);
-        tmem_ld_wait();
-        tmem_ld32(tbase + 64, va);
-        block(vb, 1);
-        tmem_ld_wait();
-        tmem_ld32(tbase + 96, vb);
-        block(va, 2);
-        tmem_ld_wait();
-        block(vb, 3);
-        flush(cur, m);
-      }
-      if (warp == 0 && lane == 0) PG_TRACE(3 + 2 * rank, tile_iter, 2);
-      // ---- D2: features 256 .. : lanes are edge rows; one redux.sync.max per column and destination run ----
-      if (p.n2 > 0) {
-        int d = row_d;
-        if (d < 0 || d >= p.num_dst) d = -1;
-        const int prev = __shfl_up_sync(0xffffffffu, d, 1);
-        const uint32_t bits = __ballot_sync(0xffffffffu, lane != 0 && prev != d);
-        for (int ci = par; ci * 16 < p.n2; ci += 2) {
-          uint32_t v[16];
-          tmem_ld16(tmem + lane_base + kD2Col + uint32_t(ci * 16), v);
-          tmem_ld_wait();
-          const int col = int(kD2Col) + ci * 16 + (lane & 15);
-          const float bias_c = col < p.n ? __ldg(p.bias + col) : 0.0f;
-          int sb = 0;
-#pragma unroll 1
-          while (true) {
-            const uint32_t rest = bits >> (sb + 1);
-            const int eb = rest ? sb + __ffs(rest) : 32;
-            const bool in_run = lane >= sb && lane < eb;
-            const int dst_run = __shfl_sync(0xffffffffu, d, sb);
-            float mine = -FLT_MAX;
-#pragma unroll
-            for (int jc = 0; jc < 16; ++jc) {
-              const float t = redux_max(in_run ? __uint_as_float(v[jc]) : -FLT_MAX);
-              if ((lane & 15) == jc) mine = t;
-            }
-            if (lane < 16 && dst_run >= 0 && col < p.n && mine > -FLT_MAX && p.act != 99)
-              atomicMax(reinterpret_cast<int*>(p.out + int64_t(dst_run) * p.n + col), __float_as_int(fmaxf(mine + bias_c, 0.0f)));
-            if (eb >= 32) break;
-            sb = eb;
-          }
-        }
-      }
+      segmax_d1_transposed(p, tmem, 0u, rank, quarter, lane, ids);
       tc_fence_before();
       __syncwarp();
+      if (lane == 0) mbar_arrive_cluster_relaxed(sm.bar_d1_empty, 0);
+      if (warp == 0 && lane == 0) PG_TRACE(3 + 2 * rank, tile_iter, 2);
+      if (p.n2 > 0) {
+        segmax_d2_rowmajor(p, tmem, kD2Col + buf * d2_stride, rank, quarter, lane, tile);
+        tc_fence_before();
+        __syncwarp();
+        if (lane == 0) mbar_arrive_cluster_relaxed(&sm.bar_d2_empty[buf], 0);
+      }
       if (warp == 0 && lane == 0) PG_TRACE(4 + 2 * rank, tile_iter, 0);
-      if (lane == 0) mbar_arrive_cluster_relaxed(sm.bar_tmem_empty, 0);
     }
   } else {
     // =================================== producer warps =======================================
     cluster_sync();   // [sync A]
-    seg_producer(p, sm, threadIdx.x - (kEpiWarps + 1) * 32, lane, rank, cluster_id, num_clusters);
+    seg_producer(p, sm, threadIdx.x - (kSegEpiWarps + 1) * 32, lane, rank, cluster_id, num_clusters);
   }
 
   // ---- teardown ------------------------------------------------------------------------------
   tc_fence_before();
   __syncthreads();
   cluster_sync();
-  if (warp == kMmaWarp) tmem_dealloc<2>(tmem, p.tmem_cols);
+  if (warp == kSegMmaWarp) tmem_dealloc<2>(tmem, p.tmem_cols);
 }
 
 // ================================================================================================
@@ -1399,7 +1428,8 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kChainThreads, 1) ml
     }
     for (int i = 0; i < kChainMaxPhases; ++i) {
       mbar_init(&sm.bar_d_full[i], 1);
-      mbar_init(&sm.bar_d_empty[i], 2 * kEpiWarps);
+      // readers of D_i: the eight mid-stage warps, or (last phase) the four producer / final-stage warps
+      mbar_init(&sm.bar_d_empty[i], i == cp.num_phases - 1 ? 2 * kChainProdWarps : 2 * kEpiWarps);
     }
     mbar_init(sm.bar_a0_full, 2 * kChainProdWarps);
     mbar_init(sm.bar_a0_empty, 1);
@@ -1436,6 +1466,7 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kChainThreads, 1) ml
           const ChainPhase& c = cp.ph[ph];
           const uint32_t idesc1 = make_idesc_bf16(256, c.n1);
           const uint32_t idesc2 = make_idesc_bf16(256, c.n2 > 0 ? c.n2 : 16);
+          const uint32_t idesc_t = make_idesc_bf16(256, 256);
           const uint64_t b_hi0 = make_smem_desc(smem_u32(sm.w) + c.b_off, 128, c.sbo);
           const uint64_t b_lo0 = make_smem_desc(smem_u32(sm.w) + c.b_off + c.part_bytes, 128, c.sbo);
           const uint64_t b2_off = uint64_t((uint32_t(c.n1 / 16) * c.sbo) >> 4);
@@ -1459,9 +1490,17 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kChainThreads, 1) ml
             const uint64_t da_lo = da_hi + uint64_t((kStageBytes / 2) >> 4);
             const uint64_t db_hi = b_hi0 + kb, db_lo = b_lo0 + kb;
             if (elect_one()) {
-              mma_bf16<2>(d1, da_hi, db_hi, idesc1, s > 0);
-              mma_bf16<2>(d1, da_lo, db_hi, idesc1, true);
-              mma_bf16<2>(d1, da_hi, db_lo, idesc1, true);
+              if (ph == P - 1) {
+                // last layer TRANSPOSED: D1t[feature, edge] = W^T (A, M = 256 features) x h^T (B, N = 256 edges);
+                // features 256.. stay row-major (M = 256 edges, N = n2)
+                mma_bf16<2>(d1, db_hi, da_hi, idesc_t, s > 0);
+                mma_bf16<2>(d1, db_hi, da_lo, idesc_t, true);
+                mma_bf16<2>(d1, db_lo, da_hi, idesc_t, true);
+              } else {
+                mma_bf16<2>(d1, da_hi, db_hi, idesc1, s > 0);
+                mma_bf16<2>(d1, da_lo, db_hi, idesc1, true);
+                mma_bf16<2>(d1, da_hi, db_lo, idesc1, true);
+              }
               if (c.n2 > 0) {
                 mma_bf16<2>(d2, da_hi, db_hi + b2_off, idesc2, s > 0);
                 mma_bf16<2>(d2, da_lo, db_hi + b2_off, idesc2, true);
@@ -1484,24 +1523,11 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kChainThreads, 1) ml
     // ============================ mid stages + final epilogue ==================================
     cluster_sync();   // [sync A]
     const int quarter = warp & 3, par = warp >> 2;
-    float* scratch = sm.scratch + warp * kScratchFloats;
     const uint32_t lane_base = uint32_t(quarter * 32) << 16;
     const int r = quarter * 32 + lane;                       // tile row of this thread (TMEM lane)
     const uint32_t a_off = uint32_t(r >> 3) * 256u + uint32_t(r & 7) * 16u;
-    constexpr int kMaxChunks = 8;
-    float bias1[kMaxChunks], bias2[kMaxChunks];
-#pragma unroll
-    for (int k = 0; k < kMaxChunks; ++k) {
-      const int c1 = (par + 2 * k) * 16 + (lane & 15);
-      const int c2 = p.n1 + c1;
-      bias1[k] = ((par + 2 * k) * 16 < p.n1 && c1 < p.n) ? __ldg(p.bias + c1) : 0.0f;
-      bias2[k] = ((par + 2 * k) * 16 < p.n2 && c2 < p.n) ? __ldg(p.bias + c2) : 0.0f;
-    }
     uint32_t tile_iter = 0;
     for (int64_t tile = cluster_id; tile < p.num_pair_tiles; tile += num_clusters, ++tile_iter) {
-      const int64_t row = tile * 256 + int64_t(rank) * kTileRows + r;
-      const bool row_ok = row < p.num_rows;
-      const int64_t warp_row0 = tile * 256 + int64_t(rank) * kTileRows + quarter * 32;
       // ---- mid stages: D_ph -> bias, relu -> A operand of phase ph + 1 ---------------------------
       for (int ph = 0; ph + 1 < P; ++ph) {
         const ChainPhase& c = cp.ph[ph];
@@ -1531,46 +1557,21 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kChainThreads, 1) ml
         __syncwarp();
         if (lane == 0) mbar_arrive_cluster_relaxed(&sm.bar_d_empty[ph], 0);
       }
-      // ---- final stage: segment max of the last accumulator ------------------------------------
-      SegState st{-1, -1, 0, 0, -1, false};
-      if (row_ok) {
-        st.d = p.dst[row];
-        if (st.d < 0 || st.d >= p.num_dst) { *p.err = 1; st.d = -1; }
-      }
-      {
-        const int prev = __shfl_up_sync(0xffffffffu, st.d, 1);
-        const uint32_t bits = __ballot_sync(0xffffffffu, (lane & 15) != 0 && prev != st.d);
-        const uint32_t mine = (bits >> (lane & 16)) & 0xffffu;
-        st.nb = __popc(mine);
-        st.b = mine ? __ffs(mine) - 1 : 16;
-        st.cur0 = __shfl_sync(0xffffffffu, st.d, lane & 16);
-        st.d_b = __shfl_sync(0xffffffffu, st.d, (lane & 16) + (st.b & 15));
-        const int d16 = __shfl_sync(0xffffffffu, st.d, 16);
-        st.pair = bits == 0 && __shfl_sync(0xffffffffu, st.d, 0) == d16;
-      }
-      const ChainPhase& cl = cp.ph[P - 1];
-      mbar_wait(&sm.bar_d_full[P - 1], tile_iter & 1u);
-      tc_fence_after();
-      epi_section<EPI_SEGMAX, kMaxChunks>(p, tmem + lane_base + cl.d_col, 0, p.n1, par, scratch, st, lane, row, row_ok,
-                                          warp_row0, bias1);
-      if (p.n2 > 0)
-        epi_section<EPI_SEGMAX, kMaxChunks>(p, tmem + lane_base + cl.d_col + uint32_t(p.n1), p.n1, p.n2, par, scratch, st,
-                                            lane, row, row_ok, warp_row0, bias2);
-      tc_fence_before();
-      __syncwarp();
-      if (lane == 0) mbar_arrive_cluster_relaxed(&sm.bar_d_empty[P - 1], 0);
     }
   } else {
-    // =================================== producer warps =======================================
-    // layer 1 of the point MLP (gnn.py:264-270): e0 = [feature, x_src - x_dst[kp]], h = relu(e0 @ W + b)
+    // =================================== producer / final-stage warps ==========================
+    // layer 1 of the point MLP (gnn.py:264-270): e0 = [feature, x_src - x_dst[kp]], h = relu(e0 @ W + b),
+    // one tile ahead of the tensor core; between two tiles' layer-1 work these four warps (one per TMEM
+    // lane quarter) run the final stage of the tile whose last accumulator just completed.
     cluster_sync();   // [sync A]
     const int r = threadIdx.x - (kEpiWarps + 1) * 32;         // 0..127: tile row
+    const int quarter = warp & 3;                             // TMEM lane quarter this warp may access
     const uint32_t a_off = uint32_t(r >> 3) * 256u + uint32_t(r & 7) * 16u;
     const int k0 = cp.k0;
     const float* w = sm.first;            // [4][k0]
     const float* b = sm.first + 4 * k0;   // [k0]
-    uint32_t tile_iter = 0;
-    for (int64_t tile = cluster_id; tile < p.num_pair_tiles; tile += num_clusters, ++tile_iter) {
+    const uint32_t d_last = cp.ph[P - 1].d_col;
+    auto produce = [&](int64_t tile, uint32_t tile_iter) {
       const int64_t row = tile * 256 + int64_t(rank) * kTileRows + r;
       int sidx = 0, didx = 0;
       if (row < p.num_rows) {
@@ -1601,6 +1602,20 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kChainThreads, 1) ml
       fence_proxy_async_smem();
       __syncwarp();
       if (lane == 0) mbar_arrive_cluster(sm.bar_a0_full, 0);
+    };
+    if (cluster_id < p.num_pair_tiles) produce(cluster_id, 0);
+    uint32_t tile_iter = 0;
+    for (int64_t tile = cluster_id; tile < p.num_pair_tiles; tile += num_clusters, ++tile_iter) {
+      if (tile + num_clusters < p.num_pair_tiles) produce(tile + num_clusters, tile_iter + 1);
+      int ids[8];
+      segmax_load_ids(p, tile, lane, ids);
+      mbar_wait(&sm.bar_d_full[P - 1], tile_iter & 1u);
+      tc_fence_after();
+      segmax_d1_transposed(p, tmem, d_last, rank, quarter, lane, ids);
+      if (p.n2 > 0) segmax_d2_rowmajor(p, tmem, d_last + 256u, rank, quarter, lane, tile);
+      tc_fence_before();
+      __syncwarp();
+      if (lane == 0) mbar_arrive_cluster_relaxed(&sm.bar_d_empty[P - 1], 0);
     }
   }
 
@@ -1696,8 +1711,8 @@ bool seg_gemm_fits(int k, int n) {
   const int kp = (k + 15) / 16 * 16, np = (n + 15) / 16 * 16;
   const int n2 = std::max(0, np - 256);
   const uint32_t part = uint32_t((256 + n2) / 16) * uint32_t(kp / 8) * 128u;
-  // ks >= 10: the producers publish next-tile source indices half a tile ahead of their first use
-  return pg_tc_available() && n >= 8 && n2 <= 256 && kp / 16 >= 10 && seg_smem_layout(nullptr, kp, part, nullptr) <= 227 * 1024;
+  // ks >= 12: the producers publish next-tile source indices half a tile ahead of their first use
+  return pg_tc_available() && n >= 8 && n2 <= 256 && kp / 16 >= 12 && seg_smem_layout(nullptr, kp, part, nullptr) <= 227 * 1024;
 }
 
 int launch_seg_gemm(TcParams& p, const float* w, int k, int n, const float* bias, Temp& t_img, Temp& t_bias,
@@ -1735,7 +1750,7 @@ int launch_seg_gemm(TcParams& p, const float* w, int k, int n, const float* bias
     PG_CUDA_OK(cudaMemsetAsync(t_trace.ptr, 0, trace_words * 8, s));
     p.trace = t_trace.as<unsigned long long>();
   }
-  seg_gemm_tc_kernel<<<2 * clusters, kThreads, smem, s>>>(p);
+  seg_gemm_tc_kernel<<<2 * clusters, kSegThreads, smem, s>>>(p);
   PG_LAUNCH_CHECK();
   if (trace_path != nullptr) {
     std::vector<unsigned long long> h(trace_words);
@@ -1770,15 +1785,18 @@ int pool_chain_launch(const float* features, const float* xyz_src, const float* 
     if (k % 16 != 0 || np > 512 || (ph + 1 < P && n % 16 != 0)) return PG_OK;
     ChainPhase& c = cp.ph[ph];
     c.ks = k / 16;
-    c.n1 = std::min(np, 256);
-    c.n2 = np - c.n1;
+    const bool last = ph + 1 == P;
+    // the last phase is computed transposed for its first 256 features: always a full M = 256 tile
+    c.n1 = last ? 256 : std::min(np, 256);
+    c.n2 = std::max(0, np - 256);
+    const int np_eff = c.n1 + c.n2;
     c.d_col = d_col;
     c.sbo = uint32_t(k / 8) * 128u;
-    c.part_bytes = uint32_t(np / 16) * c.sbo;      // this rank's np/2 rows = np/16 groups of 8
+    c.part_bytes = uint32_t(np_eff / 16) * c.sbo;  // this rank's np_eff/2 rows = np_eff/16 groups of 8
     c.b_off = b_off;
     c.it_off = it_off;
     c.bias_off = bias_off;
-    d_col += uint32_t(np);
+    d_col += uint32_t(np_eff);
     b_off += 2 * c.part_bytes;
     if (ph > 0) it_off += uint32_t(c.ks);      // the ring carries the k-steps of phases >= 1 only
     if (ph + 1 < P) bias_off += uint32_t(np);
