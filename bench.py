@@ -37,6 +37,9 @@ WORKLOADS = {
     'ped_cyl_auto_T3_20k_b8': ('ped_cyl_auto_T3_trainval', 20000, False, 8),
 }
 METRIC = 'KITTI-shape frames/sec (car_auto_T3, graph build + GNN forward)'
+# dram__bytes_read + dram__bytes_write of one seg_gemm_tc_kernel launch at the default workload, from the
+# committed `ncu --set full` capture (profiles/r1_seg_tc_ncu_summary.txt); the 4.5 GB of gathered rows are L2 hits
+EDGE_KERNEL_DRAM_BYTES = 97.3e6
 UNIT = 'frames/s'
 
 
@@ -154,7 +157,7 @@ class ClockSampler(object):
     def start(self):
         try:
             self.proc = subprocess.Popen(
-                ['nvidia-smi', '--query-gpu=' + self.QUERY, '--format=csv,noheader,nounits', '-lms', '100',
+                ['nvidia-smi', '--query-gpu=' + self.QUERY, '--format=csv,noheader,nounits', '-lms', '20',
                  '-i', str(self.gpu)], stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
         except OSError:
             self.proc = None
@@ -360,10 +363,17 @@ def run_gpu(args, rank, world):
             'gpu_launches': launches,
             'clocks': clocks,
             'stages_ms_per_step': {k: v / n_instr for k, v in stage_ms.items() if k != 'edge kernel'},
-            'roofline': {'bound': 'tensor', 'kernel': 'edge_mlp_max (GNN iteration)', 'achieved': achieved,
-                         'peak': peak_tf, 'unit': 'TFLOP/s', 'frac': achieved / peak_tf, 'traffic': None,
-                         'peak_source': peak_src, 'launch_ms': edge_ms / max(edge_launches, 1),
-                         'algorithmic_flops_per_launch': edge_flops / max(edge_launches, 1)},
+            'roofline': {'bound': 'tensor', 'kernel': 'seg_gemm_tc_kernel (fused GNN edge layer: gather + edge MLP + '
+                                                      'segment max; timed as the pg_edge_mlp_max call incl. the hoisted '
+                                                      'per-vertex GEMM and weight packing)',
+                         'achieved': achieved, 'peak': peak_tf, 'unit': 'TFLOP/s', 'frac': achieved / peak_tf,
+                         'traffic': EDGE_KERNEL_DRAM_BYTES, 'peak_source': peak_src,
+                         'launch_ms': edge_ms / max(edge_launches, 1),
+                         'algorithmic_flops_per_launch': edge_flops / max(edge_launches, 1),
+                         # the kernel executes 3 BF16 MMAs per product (BF16x3 split) on the padded 304x304 second
+                         # layer only (the first layer is hoisted to a per-vertex GEMM): executed tensor FLOP/s
+                         'executed_tensor_tflops': achieved * (2 * 3 * 304 * 304) / 361800.0
+                         if cfg_name.startswith('car') else None},
             'cpu_baseline': cpu,
         }
         print(json.dumps(line), flush=True)
@@ -393,13 +403,13 @@ def time_edge_kernel(model, graph_fn, gkw, dev_step, config):
     reps = 5
     prec = pointgnn_b200.get_precision()
     for _ in range(2):
-        _lib.edge_mlp_max(1, feats, coords[1], coords[1], None, src, dst, k, ws, bs, precision=prec)
+        _lib.edge_mlp_max(1, feats, coords[1], coords[1], None, src, dst, k, ws, bs, precision=prec, trusted=True)
     torch.cuda.synchronize()
     a = torch.cuda.Event(enable_timing=True)
     b = torch.cuda.Event(enable_timing=True)
     a.record()
     for _ in range(reps):
-        _lib.edge_mlp_max(1, feats, coords[1], coords[1], None, src, dst, k, ws, bs, precision=prec)
+        _lib.edge_mlp_max(1, feats, coords[1], coords[1], None, src, dst, k, ws, bs, precision=prec, trusted=True)
     b.record()
     b.synchronize()
     dims = [d[0] + 3] + d
@@ -410,7 +420,7 @@ def time_edge_kernel(model, graph_fn, gkw, dev_step, config):
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument('--gpus', type=int, default=1)
-    ap.add_argument('--steps', type=int, default=5)
+    ap.add_argument('--steps', type=int, default=20)
     ap.add_argument('--warmup', type=int, default=3)
     ap.add_argument('--impl', default='ours', choices=['ours', 'reference'])
     ap.add_argument('--workload', default='car_auto_T3_20k', choices=sorted(WORKLOADS))

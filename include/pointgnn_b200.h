@@ -164,8 +164,14 @@ PG_API int pg_fully_connected(const float* x, int64_t m, int32_t k, const float*
  *                W_l is [dims[l], dims[l+1]] row-major, dims[0] = C_in + 3.
  *   dims_host    (host) [num_layers+1]
  *   out          [num_dst, dims[num_layers]]; empty segments get -FLT_MAX.
- *   precision    0 = fp32 FFMA, 1 = tcgen05 BF16x3 for the wide layers.
+ *   precision    0 = fp32 FFMA, 1 = tcgen05 BF16x3 for the wide layers; may be OR-ed with
+ *                PG_FLAG_TRUSTED_INDICES: the caller guarantees src / dst are in range (they come from
+ *                pg_radius_graph, or passed pg_check_edges), so the call skips the device->host
+ *                read-back of the range-error flag and does not synchronise the stream.  Out-of-range
+ *                indices are still clamped on the device (never dereferenced), just not reported.
  */
+#define PG_PRECISION_MASK 0xff
+#define PG_FLAG_TRUSTED_INDICES 0x100
 #define PG_EDGE_POOL 0
 #define PG_EDGE_GNN 1
 PG_API int pg_edge_mlp_max(int32_t mode, const float* features, int32_t num_feature_channels,
@@ -174,6 +180,13 @@ PG_API int pg_edge_mlp_max(int32_t mode, const float* features, int32_t num_feat
                     int64_t num_dst, const float* const* weights_host,
                     const float* const* biases_host, const int32_t* dims_host,
                     int32_t num_layers, float* out, int32_t precision, void* stream);
+
+/*
+ * Range check of an edge list: 0 <= src[e] < num_src and 0 <= dst[e] < num_dst for every e (what TF's
+ * gather / unsorted_segment_max raise InvalidArgumentError for at sess.run, run.py:260).  Synchronises.
+ */
+PG_API int pg_check_edges(const int32_t* src, const int32_t* dst, int64_t num_edges, int64_t num_src,
+                   int64_t num_dst, void* stream);
 
 /* Row-wise softmax, MultiLayerFastLocalGraphModelV2.postprocess (models.py:165-168). */
 PG_API int pg_softmax_rows(const float* logits, int64_t num_rows, int32_t num_classes, float* out,

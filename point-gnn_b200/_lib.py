@@ -44,7 +44,9 @@ SIGNATURES = {
                                        c_i64, ctypes.POINTER(ctypes.c_void_p), ctypes.POINTER(ctypes.c_void_p),
                                        ctypes.POINTER(c_i32), c_i32, c_f32p, c_i32, ctypes.c_void_p]),
     'pg_softmax_rows': (ctypes.c_int, [c_f32p, c_i64, c_i32, c_f32p, ctypes.c_void_p]),
+    'pg_check_edges': (ctypes.c_int, [c_i32p, c_i32p, c_i64, c_i64, c_i64, ctypes.c_void_p]),
 }
+PG_FLAG_TRUSTED_INDICES = 0x100
 
 _lib = None
 
@@ -220,7 +222,17 @@ def fully_connected(x, w, b, relu, residual=None, precision=0):
     return out
 
 
-def edge_mlp_max(mode, features, xyz_src, xyz_dst, dst_index, src, dst, num_dst, weights, biases, precision=0):
+def check_edges(src, dst, num_src, num_dst):
+    """Raise PointGNNError unless 0 <= src < num_src and 0 <= dst < num_dst (one synchronising kernel)."""
+    lib = load()
+    _check(lib.pg_check_edges(_ptr(src, torch.int32, 'src'), _ptr(dst, torch.int32, 'dst'), src.numel(),
+                              int(num_src), int(num_dst), _stream()))
+
+
+def edge_mlp_max(mode, features, xyz_src, xyz_dst, dst_index, src, dst, num_dst, weights, biases, precision=0,
+                 trusted=False):
+    """trusted=True: the caller vouches for the index ranges (graph_gen output / check_edges passed); the call
+    then does not read the range-error flag back and does not synchronise the stream."""
     lib = load()
     num_layers = len(weights)
     dims = [weights[0].shape[0]] + [w.shape[1] for w in weights]
@@ -232,7 +244,8 @@ def edge_mlp_max(mode, features, xyz_src, xyz_dst, dst_index, src, dst, num_dst,
                                _ptr(xyz_src, torch.float32, 'xyz_src'), _ptr(xyz_dst, torch.float32, 'xyz_dst'),
                                _ptr(dst_index, torch.int32, 'dst_index'), _ptr(src, torch.int32, 'src'),
                                _ptr(dst, torch.int32, 'dst'), src.numel(), features.shape[0], int(num_dst), wp, bp,
-                               dm, num_layers, _ptr(out, torch.float32, 'out'), int(precision), _stream()))
+                               dm, num_layers, _ptr(out, torch.float32, 'out'),
+                               int(precision) | (PG_FLAG_TRUSTED_INDICES if trusted else 0), _stream()))
     return out
 
 

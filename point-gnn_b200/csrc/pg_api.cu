@@ -16,6 +16,9 @@ void set_error(const char* fmt, ...) {
   va_end(ap);
 }
 void count_launch(int n) { g_launches.fetch_add(n, std::memory_order_relaxed); }
+static thread_local bool g_trusted = false;
+bool trusted_indices() { return g_trusted; }
+void set_trusted_indices(bool v) { g_trusted = v; }
 }  // namespace pg
 
 extern "C" {

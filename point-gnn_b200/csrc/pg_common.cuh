@@ -11,6 +11,9 @@ namespace pg {
 
 void set_error(const char* fmt, ...);
 void count_launch(int n = 1);
+// true while the current C-ABI call carries PG_FLAG_TRUSTED_INDICES (no range-error read-back, no sync)
+bool trusted_indices();
+void set_trusted_indices(bool v);
 
 #define PG_CUDA_OK(expr)                                                              \
   do {                                                                                \

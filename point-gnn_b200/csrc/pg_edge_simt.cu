@@ -213,8 +213,10 @@ int edge_mlp_max_fp32(int mode, const float* features, int c_in, const float* xy
     PG_LAUNCH_CHECK();
   }
   int h = 0;
-  PG_CUDA_OK(cudaMemcpyAsync(&h, err.ptr, sizeof(int), cudaMemcpyDeviceToHost, s));
-  PG_CUDA_OK(cudaStreamSynchronize(s));
+  if (!trusted_indices()) {   // PG_FLAG_TRUSTED_INDICES: no read-back, no synchronisation
+    PG_CUDA_OK(cudaMemcpyAsync(&h, err.ptr, sizeof(int), cudaMemcpyDeviceToHost, s));
+    PG_CUDA_OK(cudaStreamSynchronize(s));
+  }
   PG_REQUIRE(h == 0, "edge index out of range (src in [0,%lld), dst in [0,%lld))", (long long)num_src,
              (long long)num_dst);
   return PG_OK;
@@ -242,6 +244,11 @@ extern "C" int pg_edge_mlp_max(int32_t mode, const float* features, int32_t num_
   PG_REQUIRE((features && xyz_src && xyz_dst && src && dst) || num_edges == 0, "pg_edge_mlp_max: null input");
   PG_REQUIRE(mode == PG_EDGE_GNN || dst_index != nullptr || num_edges == 0,
              "pg_edge_mlp_max: POOL mode needs keypoint indices");
+  struct TrustedScope {
+    explicit TrustedScope(bool v) { pg::set_trusted_indices(v); }
+    ~TrustedScope() { pg::set_trusted_indices(false); }
+  } scope((precision & PG_FLAG_TRUSTED_INDICES) != 0);
+  precision &= PG_PRECISION_MASK;
   if (precision == 1)
     return edge_mlp_max_tc(mode, features, num_feature_channels, xyz_src, xyz_dst, dst_index, src, dst, num_edges,
                            num_src, num_dst, weights_host, biases_host, dims_host, num_layers, out, s);

@@ -24,6 +24,10 @@ namespace {
 constexpr int kAxisBits = 16;
 constexpr int kAxisMax = (1 << kAxisBits) - 1;
 constexpr double kCellSlack = 1.0001;  // cell edge = radius * slack, keeps +-1 cell search exact
+// device-side error word of one graph call (read back once, together with the result size)
+constexpr int kErrRange = 1;       // cloud extent exceeds the key bits
+constexpr int kErrFramePtr = 2;    // point frame_ptr does not run from 0 to N
+constexpr int kErrCenterPtr = 4;   // centre frame_ptr does not run from 0 to K
 
 __host__ __device__ inline uint64_t make_key(uint32_t frame, uint32_t iz, uint32_t iy, uint32_t ix) {
   return (uint64_t(frame) << 48) | (uint64_t(iz) << 32) | (uint64_t(iy) << 16) | uint64_t(ix);
@@ -54,10 +58,11 @@ __global__ void init_bounds_kernel(uint32_t* __restrict__ bounds, int n) {
   if (i < n) bounds[i] = 0xffffffffu;
 }
 
-__global__ void frame_min_kernel(const float* __restrict__ xyz, const int32_t* __restrict__ frame_ptr,
+__global__ void frame_min_kernel(const float* __restrict__ xyz, const int32_t* __restrict__ frame_ptr, int64_t n,
                                  uint32_t* __restrict__ bounds) {
   const int f = blockIdx.y;
-  const int64_t begin = frame_ptr[f], end = frame_ptr[f + 1];
+  // clamped: a malformed partition is reported through the error word, it must not read out of bounds
+  const int64_t begin = max(int64_t(frame_ptr[f]), int64_t(0)), end = min(int64_t(frame_ptr[f + 1]), n);
   float mx = FLT_MAX, my = FLT_MAX, mz = FLT_MAX;
   for (int64_t i = begin + blockIdx.x * blockDim.x + threadIdx.x; i < end;
        i += int64_t(gridDim.x) * blockDim.x) {
@@ -99,11 +104,13 @@ __global__ void point_keys_kernel(const float* __restrict__ xyz, const int32_t* 
                                   int32_t* __restrict__ vals, int* __restrict__ range_error) {
   int64_t i = int64_t(blockIdx.x) * blockDim.x + threadIdx.x;
   if (i >= n) return;
+  // the caller's frame partition must run from 0 to n (checked here instead of with a host round trip)
+  if (i == 0 && (frame_ptr[0] != 0 || int64_t(frame_ptr[num_frames]) != n)) atomicOr(range_error, kErrFramePtr);
   const int f = find_frame(frame_ptr, num_frames, i);
   long long ix, iy, iz;
   cell_of(g, bounds, f, xyz[3 * i], xyz[3 * i + 1], xyz[3 * i + 2], &ix, &iy, &iz);
   if (ix < 0 || iy < 0 || iz < 0 || ix > kAxisMax || iy > kAxisMax || iz > kAxisMax) {
-    *range_error = 1;
+    atomicOr(range_error, kErrRange);
     ix = iy = iz = 0;
   }
   keys[i] = make_key(uint32_t(f), uint32_t(iz), uint32_t(iy), uint32_t(ix));
@@ -149,14 +156,15 @@ struct SortedGrid {
   const uint64_t* cell_key;   // [num_cells]
   const int32_t* cell_start;  // [num_cells+1]
   const float4* pts;          // [n] sorted (x,y,z,orig idx)
-  int num_cells;
+  const int32_t* num_cells;   // device scalar (= last element of the head-flag scan): no host round trip
 };
 
 // point range covering cells (f, iz, iy, ix_lo..ix_hi); indices already clamped to [0, kAxisMax]
 __device__ inline void row_range(const SortedGrid& g, uint32_t f, uint32_t iz, uint32_t iy, uint32_t ix_lo,
                                  uint32_t ix_hi, int* begin, int* end) {
-  const int a = lower_bound_u64(g.cell_key, g.num_cells, make_key(f, iz, iy, ix_lo));
-  const int b = lower_bound_u64(g.cell_key, g.num_cells, make_key(f, iz, iy, ix_hi) + 1ull);
+  const int nc = __ldg(g.num_cells);
+  const int a = lower_bound_u64(g.cell_key, nc, make_key(f, iz, iy, ix_lo));
+  const int b = lower_bound_u64(g.cell_key, nc, make_key(f, iz, iy, ix_hi) + 1ull);
   *begin = g.cell_start[a];
   *end = g.cell_start[b];
 }
@@ -170,9 +178,9 @@ __device__ inline double dist2_rn(double ax, double ay, double az, float bx, flo
 
 // ---- voxel keypoints: centroid (fp64, ascending point order) + exact nearest original point ----
 __global__ void voxel_keypoint_kernel(SortedGrid g, GridSpec spec, const uint32_t* __restrict__ bounds,
-                                      int32_t* __restrict__ out_idx) {
+                                      int32_t* __restrict__ out_idx, int64_t capacity) {
   const int v = blockIdx.x * blockDim.x + threadIdx.x;
-  if (v >= g.num_cells) return;
+  if (v >= __ldg(g.num_cells)) return;
   const int s = g.cell_start[v], e = g.cell_start[v + 1];
   double sx = 0.0, sy = 0.0, sz = 0.0;
   for (int i = s; i < e; ++i) {  // sorted by (key, original index): ascending point order
@@ -217,14 +225,14 @@ __global__ void voxel_keypoint_kernel(SortedGrid g, GridSpec spec, const uint32_
       }
     }
   }
-  out_idx[v] = best_idx;
+  if (v < capacity) out_idx[v] = best_idx;
 }
 
-__global__ void frame_ranges_kernel(const uint64_t* __restrict__ cell_key, int num_cells, int num_frames,
-                                    int32_t* __restrict__ out_frame_ptr) {
+__global__ void frame_ranges_kernel(const uint64_t* __restrict__ cell_key, const int32_t* __restrict__ num_cells,
+                                    int num_frames, int32_t* __restrict__ out_frame_ptr) {
   const int f = blockIdx.x * blockDim.x + threadIdx.x;
   if (f > num_frames) return;
-  out_frame_ptr[f] = lower_bound_u64(cell_key, num_cells, uint64_t(f) << 48);
+  out_frame_ptr[f] = lower_bound_u64(cell_key, __ldg(num_cells), uint64_t(f) << 48);
 }
 
 // ---- radius graph ----------------------------------------------------------------------------
@@ -239,10 +247,14 @@ template <bool kFill>
 __global__ void __launch_bounds__(256) radius_query_kernel(
     SortedGrid g, GridSpec spec, const uint32_t* __restrict__ bounds, const float* __restrict__ centers,
     const int32_t* __restrict__ center_frame_ptr, int num_frames, int64_t num_centers, double r2,
-    int32_t* __restrict__ counts, const int32_t* __restrict__ row_ptr, int32_t* __restrict__ out_src) {
+    int32_t* __restrict__ counts, const int32_t* __restrict__ row_ptr, int32_t* __restrict__ out_src,
+    int* __restrict__ err) {
   const int lane = threadIdx.x & 31;
   const int64_t c = (int64_t(blockIdx.x) * blockDim.x + threadIdx.x) >> 5;
   if (c >= num_centers) return;
+  if (!kFill && c == 0 && lane == 0 &&
+      (center_frame_ptr[0] != 0 || int64_t(center_frame_ptr[num_frames]) != num_centers))
+    atomicOr(err, kErrCenterPtr);
   const int f = find_frame(center_frame_ptr, num_frames, c);
   const float cxf = centers[3 * c], cyf = centers[3 * c + 1], czf = centers[3 * c + 2];
   const double cx = double(cxf), cy = double(cyf), cz = double(czf);
@@ -282,15 +294,50 @@ __global__ void __launch_bounds__(256) radius_query_kernel(
 // i^j): with every comparator ascending, virtual +inf padding at the tail never moves, so rows of
 // any length sort in place.
 constexpr int kRowSortMax = 8192;
+constexpr int kWarpRowMax = 1024;   // rows up to this length are sorted by one warp (sort_rows_warp_kernel)
+
+// One warp per CSR row: classic bitonic network in the warp's private slice of shared memory, padded with
+// INT_MAX to a power of two, __syncwarp between stages (no block barrier: KITTI-shape rows have ~100-600
+// entries, and the block-per-row version spent its time in 36+ __syncthreads per row).  Also expands dst.
+__global__ void __launch_bounds__(256) sort_rows_warp_kernel(const int32_t* __restrict__ row_ptr, int64_t num_rows,
+                                                              int32_t* __restrict__ src, int32_t* __restrict__ dst) {
+  __shared__ int32_t srows[8][kWarpRowMax];
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  int32_t* a = srows[warp];
+  for (int64_t r = int64_t(blockIdx.x) * 8 + warp; r < num_rows; r += int64_t(gridDim.x) * 8) {
+    const int b = row_ptr[r], e = row_ptr[r + 1];
+    const int len = e - b;
+    if (dst != nullptr)
+      for (int i = lane; i < len; i += 32) dst[b + i] = int32_t(r);
+    if (len <= 1 || len > kWarpRowMax) continue;      // long rows: sort_rows_kernel
+    int n = 2;
+    while (n < len) n <<= 1;
+    __syncwarp();
+    for (int i = lane; i < n; i += 32) a[i] = i < len ? src[b + i] : 0x7fffffff;
+    __syncwarp();
+    for (int k = 2; k <= n; k <<= 1) {
+      for (int j = k >> 1; j > 0; j >>= 1) {
+        for (int t = lane; t < (n >> 1); t += 32) {
+          const int i = 2 * t - (t & (j - 1));          // lower index of the pair (bit j clear)
+          const int x = a[i], y = a[i + j];
+          const bool up = (i & k) == 0;                 // ascending block of the bitonic merge
+          if ((x > y) == up) { a[i] = y; a[i + j] = x; }
+        }
+        __syncwarp();
+      }
+    }
+    for (int i = lane; i < len; i += 32) src[b + i] = a[i];
+  }
+}
+
 __global__ void __launch_bounds__(256) sort_rows_kernel(const int32_t* __restrict__ row_ptr, int64_t num_rows,
                                                          int32_t* __restrict__ src, int32_t* __restrict__ dst) {
   extern __shared__ int32_t srow[];
   for (int64_t r = blockIdx.x; r < num_rows; r += gridDim.x) {
     const int b = row_ptr[r], e = row_ptr[r + 1];
     const int len = e - b;
-    if (dst != nullptr)
-      for (int i = threadIdx.x; i < len; i += blockDim.x) dst[b + i] = int32_t(r);
-    if (len <= 1) continue;
+    if (len <= kWarpRowMax) continue;                   // sorted (and dst expanded) by sort_rows_warp_kernel
+
     int n = 1;
     while (n < len) n <<= 1;
     const bool in_smem = len <= kRowSortMax;
@@ -322,7 +369,6 @@ __global__ void __launch_bounds__(256) sort_rows_kernel(const int32_t* __restric
 // ---- host-side building blocks ----------------------------------------------------------------
 struct BuiltGrid {
   Temp bounds, keys_a, keys_b, vals_a, vals_b, sorted_pts, head, head_scan, cell_key, cell_start, cub_tmp, err;
-  int num_cells = 0;
   SortedGrid view{};
 };
 
@@ -347,7 +393,7 @@ int build_grid(const float* xyz, const int32_t* frame_ptr, int num_frames, int64
   init_bounds_kernel<<<ceil_div(3 * num_frames, 256), 256, 0, s>>>(bounds, 3 * num_frames);
   PG_LAUNCH_CHECK();
   const int blocks_per_frame = int(std::min<int64_t>(std::max<int64_t>(1, ceil_div(n / num_frames, 1024)), 64));
-  frame_min_kernel<<<dim3(blocks_per_frame, num_frames), 256, 0, s>>>(xyz, frame_ptr, bounds);
+  frame_min_kernel<<<dim3(blocks_per_frame, num_frames), 256, 0, s>>>(xyz, frame_ptr, n, bounds);
   PG_LAUNCH_CHECK();
   point_keys_kernel<<<ceil_div(n, 256), 256, 0, s>>>(xyz, frame_ptr, num_frames, n, spec, bounds,
                                                       out->keys_a.as<uint64_t>(), out->vals_a.as<int32_t>(),
@@ -374,30 +420,29 @@ int build_grid(const float* xyz, const int32_t* frame_ptr, int num_frames, int64
   cell_table_kernel<<<ceil_div(n, 256), 256, 0, s>>>(out->keys_b.as<uint64_t>(), out->head_scan.as<int32_t>(), n,
                                                       out->cell_key.as<uint64_t>(), out->cell_start.as<int32_t>());
   PG_LAUNCH_CHECK();
-  int h_cells = 0, h_err = 0;
-  PG_CUDA_OK(cudaMemcpyAsync(&h_cells, out->head_scan.as<int32_t>() + (n - 1), sizeof(int), cudaMemcpyDeviceToHost, s));
-  PG_CUDA_OK(cudaMemcpyAsync(&h_err, out->err.ptr, sizeof(int), cudaMemcpyDeviceToHost, s));
-  PG_CUDA_OK(cudaStreamSynchronize(s));
-  if (h_err) {
-    set_error("point cloud extent exceeds %d grid cells per axis", kAxisMax + 1);
-    return PG_ERR_RANGE;
-  }
-  out->num_cells = h_cells;
+  // no host round trip here: the cell count stays on the device, the error word is read back by the caller
+  // together with the size of its result
   out->view.cell_key = out->cell_key.as<uint64_t>();
   out->view.cell_start = out->cell_start.as<int32_t>();
   out->view.pts = out->sorted_pts.as<float4>();
-  out->view.num_cells = h_cells;
+  out->view.num_cells = out->head_scan.as<int32_t>() + (n - 1);
   return PG_OK;
 }
 
-int check_frames_host(const int32_t* frame_ptr_dev, int num_frames, int64_t n, cudaStream_t s, const char* what) {
-  // cheap sanity check of the caller's frame_ptr (first/last entries)
-  int32_t ends[2] = {0, 0};
-  PG_CUDA_OK(cudaMemcpyAsync(&ends[0], frame_ptr_dev, sizeof(int32_t), cudaMemcpyDeviceToHost, s));
-  PG_CUDA_OK(cudaMemcpyAsync(&ends[1], frame_ptr_dev + num_frames, sizeof(int32_t), cudaMemcpyDeviceToHost, s));
-  PG_CUDA_OK(cudaStreamSynchronize(s));
-  PG_REQUIRE(ends[0] == 0 && ends[1] == n, "%s frame_ptr must run from 0 to %lld (got %d..%d)", what,
-             (long long)n, ends[0], ends[1]);
+// Decode the device-side error word of a graph call.
+int graph_error(int err) {
+  if (err & kErrFramePtr) {
+    set_error("point frame_ptr must run from 0 to the number of points");
+    return PG_ERR_INVALID_ARGUMENT;
+  }
+  if (err & kErrCenterPtr) {
+    set_error("center frame_ptr must run from 0 to the number of centers");
+    return PG_ERR_INVALID_ARGUMENT;
+  }
+  if (err & kErrRange) {
+    set_error("point cloud extent exceeds %d grid cells per axis", kAxisMax + 1);
+    return PG_ERR_RANGE;
+  }
   return PG_OK;
 }
 
@@ -428,7 +473,6 @@ extern "C" int pg_voxel_keypoints(const float* xyz, const int32_t* frame_ptr, in
   PG_REQUIRE(xyz && frame_ptr && voxel_size_host && out_keypoint_idx && out_kp_frame_ptr && out_num_keypoints_host,
              "pg_voxel_keypoints: null argument");
   PG_REQUIRE(voxel_size_host[0] > 0 && voxel_size_host[1] > 0 && voxel_size_host[2] > 0, "voxel size must be positive");
-  if (int rc = check_frames_host(frame_ptr, num_frames, num_points, s, "point")) return rc;
   GridSpec spec;
   spec.cell[0] = voxel_size_host[0];
   spec.cell[1] = voxel_size_host[1];
@@ -436,18 +480,24 @@ extern "C" int pg_voxel_keypoints(const float* xyz, const int32_t* frame_ptr, in
   spec.origin_off = 0.5;  // Open3D: voxel_min_bound = min_bound - voxel_size * 0.5
   BuiltGrid grid;
   if (int rc = build_grid(xyz, frame_ptr, num_frames, num_points, spec, s, &grid)) return rc;
-  *out_num_keypoints_host = grid.num_cells;
-  if (grid.num_cells > capacity) {
-    set_error("keypoint buffer too small: need %d, capacity %lld", grid.num_cells, (long long)capacity);
-    return PG_ERR_CAPACITY;
-  }
-  voxel_keypoint_kernel<<<ceil_div(grid.num_cells, 128), 128, 0, s>>>(grid.view, spec, grid.bounds.as<uint32_t>(),
-                                                                        out_keypoint_idx);
+  // K = number of occupied voxels <= N is only known on the device: launch for N, surplus threads exit;
+  // a keypoint is only written when it fits the caller's buffer
+  voxel_keypoint_kernel<<<ceil_div(num_points, 128), 128, 0, s>>>(grid.view, spec, grid.bounds.as<uint32_t>(),
+                                                                    out_keypoint_idx, capacity);
   PG_LAUNCH_CHECK();
-  frame_ranges_kernel<<<ceil_div(num_frames + 1, 128), 128, 0, s>>>(grid.view.cell_key, grid.num_cells, num_frames,
+  frame_ranges_kernel<<<ceil_div(num_frames + 1, 128), 128, 0, s>>>(grid.view.cell_key, grid.view.num_cells, num_frames,
                                                                      out_kp_frame_ptr);
   PG_LAUNCH_CHECK();
+  int32_t h[2] = {0, 0};   // the one host round trip of this call: K and the error word
+  PG_CUDA_OK(cudaMemcpyAsync(&h[0], grid.view.num_cells, sizeof(int32_t), cudaMemcpyDeviceToHost, s));
+  PG_CUDA_OK(cudaMemcpyAsync(&h[1], grid.err.ptr, sizeof(int32_t), cudaMemcpyDeviceToHost, s));
   PG_CUDA_OK(cudaStreamSynchronize(s));
+  if (int rc = graph_error(h[1])) return rc;
+  *out_num_keypoints_host = h[0];
+  if (h[0] > capacity) {
+    set_error("keypoint buffer too small: need %d, capacity %lld", h[0], (long long)capacity);
+    return PG_ERR_CAPACITY;
+  }
   return PG_OK;
 }
 
@@ -458,17 +508,19 @@ static int radius_count_impl(RadiusPlan& plan, const float* centers, const int32
   PG_CUDA_OK(cudaMemsetAsync(counts.ptr, 0, sizeof(int32_t) * (num_centers + 1), s));
   radius_query_kernel<false><<<ceil_div(num_centers * 32, 256), 256, 0, s>>>(
       plan.grid.view, plan.spec, plan.grid.bounds.as<uint32_t>(), centers, center_frame_ptr, num_frames, num_centers,
-      plan.r2, counts.as<int32_t>(), nullptr, nullptr);
+      plan.r2, counts.as<int32_t>(), nullptr, nullptr, plan.grid.err.as<int>());
   PG_LAUNCH_CHECK();
   size_t bytes = 0;
   PG_CUDA_OK(cub::DeviceScan::ExclusiveSum(nullptr, bytes, counts.as<int32_t>(), out_row_ptr, int(num_centers + 1), s));
   PG_CUDA_OK(tmp.alloc(bytes, s));
   PG_CUDA_OK(cub::DeviceScan::ExclusiveSum(tmp.ptr, bytes, counts.as<int32_t>(), out_row_ptr, int(num_centers + 1), s));
   count_launch(2);
-  int32_t e = 0;
-  PG_CUDA_OK(cudaMemcpyAsync(&e, out_row_ptr + num_centers, sizeof(int32_t), cudaMemcpyDeviceToHost, s));
+  int32_t h[2] = {0, 0};   // the one host round trip of the graph build: E and the error word
+  PG_CUDA_OK(cudaMemcpyAsync(&h[0], out_row_ptr + num_centers, sizeof(int32_t), cudaMemcpyDeviceToHost, s));
+  PG_CUDA_OK(cudaMemcpyAsync(&h[1], plan.grid.err.ptr, sizeof(int32_t), cudaMemcpyDeviceToHost, s));
   PG_CUDA_OK(cudaStreamSynchronize(s));
-  *out_num_edges_host = e;
+  if (int rc = graph_error(h[1])) return rc;
+  *out_num_edges_host = h[0];
   return PG_OK;
 }
 
@@ -477,9 +529,13 @@ static int radius_fill_impl(RadiusPlan& plan, const float* centers, const int32_
                             cudaStream_t s) {
   radius_query_kernel<true><<<ceil_div(num_centers * 32, 256), 256, 0, s>>>(
       plan.grid.view, plan.spec, plan.grid.bounds.as<uint32_t>(), centers, center_frame_ptr, num_frames, num_centers,
-      plan.r2, nullptr, row_ptr, out_src);
+      plan.r2, nullptr, row_ptr, out_src, nullptr);
   PG_LAUNCH_CHECK();
-  const int blocks = int(std::min<int64_t>(num_centers, int64_t(num_sms()) * 16));
+  const int wblocks = int(std::min<int64_t>(ceil_div(num_centers, 8), int64_t(num_sms()) * 6));
+  sort_rows_warp_kernel<<<wblocks, 256, 0, s>>>(row_ptr, num_centers, out_src, out_dst);
+  PG_LAUNCH_CHECK();
+  // rows longer than kWarpRowMax (dense full-360 clouds): one block per row
+  const int blocks = int(std::min<int64_t>(num_centers, int64_t(num_sms()) * 4));
   sort_rows_kernel<<<blocks, 256, kRowSortMax * sizeof(int32_t), s>>>(row_ptr, num_centers, out_src, out_dst);
   PG_LAUNCH_CHECK();
   return PG_OK;
@@ -493,8 +549,6 @@ extern "C" int pg_radius_graph_count(const float* points, const int32_t* point_f
   PG_REQUIRE(points && point_frame_ptr && centers && center_frame_ptr && out_row_ptr && out_num_edges_host,
              "pg_radius_graph_count: null argument");
   PG_REQUIRE(num_centers >= 1 && num_centers < (int64_t(1) << 31) - 1, "num_centers out of range");
-  if (int rc = check_frames_host(point_frame_ptr, num_frames, num_points, s, "point")) return rc;
-  if (int rc = check_frames_host(center_frame_ptr, num_frames, num_centers, s, "center")) return rc;
   RadiusPlan plan;
   if (int rc = radius_prepare(points, point_frame_ptr, num_frames, num_points, radius, s, &plan)) return rc;
   return radius_count_impl(plan, centers, center_frame_ptr, num_frames, num_centers, out_row_ptr, out_num_edges_host, s);
@@ -521,8 +575,6 @@ extern "C" int pg_radius_graph(const float* points, const int32_t* point_frame_p
   PG_REQUIRE(points && point_frame_ptr && centers && center_frame_ptr && out_row_ptr && out_num_edges_host,
              "pg_radius_graph: null argument");
   PG_REQUIRE(num_centers >= 1 && num_centers < (int64_t(1) << 31) - 1, "num_centers out of range");
-  if (int rc = check_frames_host(point_frame_ptr, num_frames, num_points, s, "point")) return rc;
-  if (int rc = check_frames_host(center_frame_ptr, num_frames, num_centers, s, "center")) return rc;
   RadiusPlan plan;
   if (int rc = radius_prepare(points, point_frame_ptr, num_frames, num_points, radius, s, &plan)) return rc;
   if (int rc = radius_count_impl(plan, centers, center_frame_ptr, num_frames, num_centers, out_row_ptr,

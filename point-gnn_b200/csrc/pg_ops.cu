@@ -136,6 +136,14 @@ __global__ void __launch_bounds__(256) fc_fp32_kernel(const float* __restrict__ 
   }
 }
 
+__global__ void check_edges_kernel(const int32_t* __restrict__ src, const int32_t* __restrict__ dst, int64_t n,
+                                   int64_t num_src, int64_t num_dst, int* __restrict__ err) {
+  for (int64_t i = int64_t(blockIdx.x) * blockDim.x + threadIdx.x; i < n; i += int64_t(gridDim.x) * blockDim.x) {
+    const int a = src[i], b = dst[i];
+    if (a < 0 || a >= num_src || b < 0 || b >= num_dst) *err = 1;
+  }
+}
+
 __global__ void softmax_rows_kernel(const float* __restrict__ logits, int64_t num_rows, int num_classes,
                                     float* __restrict__ out) {
   const int64_t r = int64_t(blockIdx.x) * blockDim.x + threadIdx.x;
@@ -212,6 +220,25 @@ extern "C" int pg_fully_connected(const float* x, int64_t m, int32_t k, const fl
   if (precision == 1) return fc_tc_bf16x3(x, m, k, w, bias, n, act, residual, out, s);
   PG_REQUIRE(precision == 0, "pg_fully_connected: unknown precision %d", precision);
   return fc_fp32_launch(x, m, k, w, bias, n, act, residual, out, n, s);
+}
+
+extern "C" int pg_check_edges(const int32_t* src, const int32_t* dst, int64_t num_edges, int64_t num_src,
+                              int64_t num_dst, void* stream) {
+  cudaStream_t s = static_cast<cudaStream_t>(stream);
+  if (num_edges == 0) return PG_OK;
+  PG_REQUIRE(src && dst && num_edges > 0, "pg_check_edges: bad argument");
+  Temp err;
+  PG_CUDA_OK(err.alloc(sizeof(int), s));
+  PG_CUDA_OK(cudaMemsetAsync(err.ptr, 0, sizeof(int), s));
+  const int blocks = int(std::min<int64_t>(ceil_div(num_edges, 256), int64_t(num_sms()) * 8));
+  check_edges_kernel<<<blocks, 256, 0, s>>>(src, dst, num_edges, num_src, num_dst, err.as<int>());
+  PG_LAUNCH_CHECK();
+  int h = 0;
+  PG_CUDA_OK(cudaMemcpyAsync(&h, err.ptr, sizeof(int), cudaMemcpyDeviceToHost, s));
+  PG_CUDA_OK(cudaStreamSynchronize(s));
+  PG_REQUIRE(h == 0, "edge index out of range (src in [0,%lld), dst in [0,%lld))", (long long)num_src,
+             (long long)num_dst);   // TF: InvalidArgumentError
+  return PG_OK;
 }
 
 extern "C" int pg_softmax_rows(const float* logits, int64_t num_rows, int32_t num_classes, float* out, void* stream) {

@@ -1864,8 +1864,10 @@ int pool_chain_launch(const float* features, const float* xyz_src, const float* 
   PG_LAUNCH_CHECK();
   g_tc_launches[0].fetch_add(1, std::memory_order_relaxed);
   int h = 0;
-  PG_CUDA_OK(cudaMemcpyAsync(&h, t_err.ptr, sizeof(int), cudaMemcpyDeviceToHost, s));
-  PG_CUDA_OK(cudaStreamSynchronize(s));
+  if (!trusted_indices()) {   // PG_FLAG_TRUSTED_INDICES: no read-back, no synchronisation
+    PG_CUDA_OK(cudaMemcpyAsync(&h, t_err.ptr, sizeof(int), cudaMemcpyDeviceToHost, s));
+    PG_CUDA_OK(cudaStreamSynchronize(s));
+  }
   PG_REQUIRE(h == 0, "set index out of range (point in [0,%lld), keypoint in [0,%lld))", (long long)num_src,
              (long long)num_dst);
   return PG_OK;
@@ -1942,8 +1944,10 @@ int edge_mlp_max_tc(int mode, const float* features, int c_in, const float* xyz_
     p.err = t_err.as<int>();
     if (int rc = launch_row_gemm<PROD_POOL, EPI_SEGMAX>(p, t, weights[3], dims[3], n, biases[3], t_img, t_bias, s)) return rc;
     int h = 0;
-    PG_CUDA_OK(cudaMemcpyAsync(&h, t_err.ptr, sizeof(int), cudaMemcpyDeviceToHost, s));
-    PG_CUDA_OK(cudaStreamSynchronize(s));
+    if (!trusted_indices()) {   // PG_FLAG_TRUSTED_INDICES: no read-back, no synchronisation
+      PG_CUDA_OK(cudaMemcpyAsync(&h, t_err.ptr, sizeof(int), cudaMemcpyDeviceToHost, s));
+      PG_CUDA_OK(cudaStreamSynchronize(s));
+    }
     PG_REQUIRE(h == 0, "set index out of range (point in [0,%lld), keypoint in [0,%lld))", (long long)num_src,
                (long long)num_dst);
     return PG_OK;
@@ -2012,8 +2016,10 @@ int edge_mlp_max_tc(int mode, const float* features, int c_in, const float* xyz_
     return rc;
   }
   int h = 0;
-  PG_CUDA_OK(cudaMemcpyAsync(&h, t_err.ptr, sizeof(int), cudaMemcpyDeviceToHost, s));
-  PG_CUDA_OK(cudaStreamSynchronize(s));
+  if (!trusted_indices()) {   // PG_FLAG_TRUSTED_INDICES: no read-back, no synchronisation
+    PG_CUDA_OK(cudaMemcpyAsync(&h, t_err.ptr, sizeof(int), cudaMemcpyDeviceToHost, s));
+    PG_CUDA_OK(cudaStreamSynchronize(s));
+  }
   PG_REQUIRE(h == 0, "edge index out of range (src in [0,%lld), dst in [0,%lld))", (long long)num_src,
              (long long)num_dst);
   return PG_OK;

@@ -57,6 +57,7 @@ class _Ctx(threading.local):
         self.store = None
         self.scope = []
         self.counters = {}
+        self.trusted_edges = False     # set by model.predict once an edge list has been range-checked
 
 
 _ctx = _Ctx()
@@ -224,7 +225,7 @@ class PointSetPooling(object):
                 set_features = _lib.edge_mlp_max(
                     _PG_EDGE_POOL, point_features.contiguous(), point_coordinates.contiguous(),
                     point_coordinates.contiguous(), _i32(keypoint_indices.reshape(-1)), _i32(src), _i32(dst),
-                    num_keypoints, ws, bs, precision=get_precision())
+                    num_keypoints, ws, bs, precision=get_precision(), trusted=_ctx.trusted_edges)
             else:
                 # op-by-op composition, gnn.py:256-277
                 psf = _lib.gather_rows(point_features.contiguous(), _i32(src))
@@ -287,7 +288,8 @@ class GraphNetAutoCenter(object):
                 ws, bs = _take_mlp_weights(len(edge_MLP_depth_list))
                 aggregated_edge_features = _lib.edge_mlp_max(
                     _PG_EDGE_GNN, input_vertex_features.contiguous(), source_coordinates, dest_coordinates,
-                    None, _i32(src), _i32(dst), num_vertices, ws, bs, precision=get_precision())
+                    None, _i32(src), _i32(dst), num_vertices, ws, bs, precision=get_precision(),
+                    trusted=_ctx.trusted_edges)
             else:
                 # op-by-op composition, gnn.py:338-365
                 s_feat = _lib.gather_rows(input_vertex_features.contiguous(), _i32(src))

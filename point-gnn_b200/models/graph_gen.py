@@ -107,7 +107,10 @@ def _radius_edges(points, point_fp, centers, center_fp, radius, num_neighbors,
         points = (points / s).contiguous()          # graph_gen.py:203-206
         centers = (centers / s).contiguous()
     _, edges = _lib.radius_graph(points, point_fp, centers, center_fp, radius)
-    return edges.t()      # [E,2] view whose columns (src, dst) are contiguous
+    edges = edges.t()     # [E,2] view whose columns (src, dst) are contiguous
+    # index ranges are guaranteed by construction: lets model.predict skip the per-layer range check
+    edges._pg_trusted = (int(points.shape[0]), int(centers.shape[0]))
+    return edges
 
 
 def gen_disjointed_rnn_local_graph_v3(points_xyz, center_xyz, radius, num_neighbors,

@@ -82,19 +82,29 @@ class MultiLayerFastLocalGraphModelV2(object):
         coords = [self._to_device(c, torch.float32).contiguous() for c in t_vertex_coord_list]
         keypoints = [None if k is None else self._to_device(k, torch.int32) for k in t_keypoint_indices_list]
         edges = []
-        for e in t_edges_list:
+        trusted = []
+        for level, e in enumerate(t_edges_list):
+            stamp = getattr(e, '_pg_trusted', None)         # set by models.graph_gen on its own output
             e = self._to_device(e, torch.int32)
             if e.stride(0) != 1:                 # make the (src, dst) columns contiguous
                 e = e.t().contiguous().t()
+            ranges = (coords[level].shape[0], coords[level + 1].shape[0]) if level + 1 < len(coords) else None
+            if ranges is not None and stamp != ranges and e.shape[0] > 0:
+                # foreign edge list: one range check here (TF raises InvalidArgumentError at sess.run)
+                # instead of a synchronising check inside every layer
+                _lib.check_edges(e[:, 0], e[:, 1], ranges[0], ranges[1])
             edges.append(e)
+            trusted.append(ranges is not None)
         with gnn.variable_session(self._store):
             for idx in range(len(self._layer_configs) - 1):
                 layer_config = self._layer_configs[idx]
                 graph_level = layer_config['graph_level']
                 with gnn.variable_scope(layer_config['scope']):
                     flgn = self._default_layers_type[layer_config['type']]
+                    gnn._ctx.trusted_edges = trusted[graph_level]
                     tfeatures = flgn.apply_regular(tfeatures, coords[graph_level], keypoints[graph_level],
                                                    edges[graph_level], **layer_config['kwargs'])
+            gnn._ctx.trusted_edges = False
             predictor_config = self._layer_configs[-1]
             assert predictor_config['type'] in ('classaware_predictor', 'classaware_predictor_128',
                                                 'classaware_separated_predictor')

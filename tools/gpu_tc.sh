@@ -1,7 +1,4 @@
 #!/bin/bash
 mkdir -p gpurun_out
-timeout 60 python tools/prof_edge.py 8 5 1 > gpurun_out/prof_edge.log 2>&1; echo "rc=$?"; tail -1 gpurun_out/prof_edge.log
-timeout 60 python tools/prof_pool.py 8 5 1 > gpurun_out/prof_pool.log 2>&1; echo "rc=$?"; tail -1 gpurun_out/prof_pool.log
-timeout 200 python -m pytest tests/test_gnn_gpu.py -m gpu -x -q 2>&1 | tail -25 > gpurun_out/pytest_tc.log; tail -6 gpurun_out/pytest_tc.log
-PG_TC_TRACE=gpurun_out/trace.txt timeout 60 python tools/prof_edge.py 8 1 1 > gpurun_out/trace_run.log 2>&1
-python tools/trace_seg.py gpurun_out/trace.txt 19 2>&1 | tee gpurun_out/trace_seg.txt
+timeout 600 python -m pytest tests -m gpu -x -q 2>&1 | tail -25 > gpurun_out/pytest_gpu.log; tail -6 gpurun_out/pytest_gpu.log
+timeout 300 python bench.py --steps 20 --warmup 3 --no-cpu-baseline > gpurun_out/bench_quick.log 2>&1; tail -1 gpurun_out/bench_quick.log | cut -c1-2200
