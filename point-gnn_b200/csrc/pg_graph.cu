@@ -300,7 +300,8 @@ constexpr int kWarpRowMax = 1024;   // rows up to this length are sorted by one 
 // INT_MAX to a power of two, __syncwarp between stages (no block barrier: KITTI-shape rows have ~100-600
 // entries, and the block-per-row version spent its time in 36+ __syncthreads per row).  Also expands dst.
 __global__ void __launch_bounds__(256) sort_rows_warp_kernel(const int32_t* __restrict__ row_ptr, int64_t num_rows,
-                                                              int32_t* __restrict__ src, int32_t* __restrict__ dst) {
+                                                              int32_t* __restrict__ src, int32_t* __restrict__ dst,
+                                                              int* __restrict__ has_long_rows) {
   __shared__ int32_t srows[8][kWarpRowMax];
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   int32_t* a = srows[warp];
@@ -309,6 +310,7 @@ __global__ void __launch_bounds__(256) sort_rows_warp_kernel(const int32_t* __re
     const int len = e - b;
     if (dst != nullptr)
       for (int i = lane; i < len; i += 32) dst[b + i] = int32_t(r);
+    if (len > kWarpRowMax && lane == 0) *has_long_rows = 1;   // tells sort_rows_kernel there is work for it
     if (len <= 1 || len > kWarpRowMax) continue;      // long rows: sort_rows_kernel
     int n = 2;
     while (n < len) n <<= 1;
@@ -331,8 +333,10 @@ __global__ void __launch_bounds__(256) sort_rows_warp_kernel(const int32_t* __re
 }
 
 __global__ void __launch_bounds__(256) sort_rows_kernel(const int32_t* __restrict__ row_ptr, int64_t num_rows,
-                                                         int32_t* __restrict__ src, int32_t* __restrict__ dst) {
+                                                         int32_t* __restrict__ src, int32_t* __restrict__ dst,
+                                                         const int* __restrict__ has_long_rows) {
   extern __shared__ int32_t srow[];
+  if (*has_long_rows == 0) return;                      // the usual case: every row was sorted by a warp
   for (int64_t r = blockIdx.x; r < num_rows; r += gridDim.x) {
     const int b = row_ptr[r], e = row_ptr[r + 1];
     const int len = e - b;
@@ -532,11 +536,15 @@ static int radius_fill_impl(RadiusPlan& plan, const float* centers, const int32_
       plan.r2, nullptr, row_ptr, out_src, nullptr);
   PG_LAUNCH_CHECK();
   const int wblocks = int(std::min<int64_t>(ceil_div(num_centers, 8), int64_t(num_sms()) * 6));
-  sort_rows_warp_kernel<<<wblocks, 256, 0, s>>>(row_ptr, num_centers, out_src, out_dst);
+  Temp has_long;
+  PG_CUDA_OK(has_long.alloc(sizeof(int), s));
+  PG_CUDA_OK(cudaMemsetAsync(has_long.ptr, 0, sizeof(int), s));
+  sort_rows_warp_kernel<<<wblocks, 256, 0, s>>>(row_ptr, num_centers, out_src, out_dst, has_long.as<int>());
   PG_LAUNCH_CHECK();
   // rows longer than kWarpRowMax (dense full-360 clouds): one block per row
   const int blocks = int(std::min<int64_t>(num_centers, int64_t(num_sms()) * 4));
-  sort_rows_kernel<<<blocks, 256, kRowSortMax * sizeof(int32_t), s>>>(row_ptr, num_centers, out_src, out_dst);
+  sort_rows_kernel<<<blocks, 256, kRowSortMax * sizeof(int32_t), s>>>(row_ptr, num_centers, out_src, out_dst,
+                                                                      has_long.as<int>());
   PG_LAUNCH_CHECK();
   return PG_OK;
 }

@@ -1,9 +1,9 @@
 #!/bin/bash
-# One GPU session: tests, smoke, bench.  Everything lands in gpurun_out/.
+# One GPU session: tests, smoke, bench (+ reference arm).  Everything lands in gpurun_out/.
 mkdir -p gpurun_out
 nvidia-smi --query-gpu=name,clocks.sm,clocks.max.sm,power.draw,memory.used --format=csv > gpurun_out/smi.txt 2>&1
-lscpu | head -20 > gpurun_out/cpu.txt; nproc >> gpurun_out/cpu.txt
 timeout 900 python -m pytest tests -m gpu -x -q 2>&1 | tail -40 > gpurun_out/pytest_gpu.log
 timeout 300 python -c "import __graft_entry__ as g; g.smoke()" > gpurun_out/smoke.log 2>&1
-timeout 600 python bench.py --steps 5 --warmup 3 > gpurun_out/bench.log 2>&1
-tail -5 gpurun_out/pytest_gpu.log; tail -3 gpurun_out/smoke.log; tail -2 gpurun_out/bench.log
+timeout 600 python bench.py > gpurun_out/bench.log 2>&1
+timeout 300 python bench.py --impl reference --steps 2 --warmup 1 > gpurun_out/bench_ref.log 2>&1
+tail -3 gpurun_out/pytest_gpu.log; tail -2 gpurun_out/smoke.log; tail -1 gpurun_out/bench.log | cut -c1-2600; tail -1 gpurun_out/bench_ref.log | cut -c1-300
