@@ -231,6 +231,57 @@ def test_device_resident_predict_and_batch(car):
         assert np.abs(boxes[sl].cpu().numpy() - b1).max() < 1e-4
 
 
+@pytest.mark.parametrize('precision', PRECISIONS)
+def test_full_size_properties(car, precision):
+    """BASELINE config sizes (20 000-point frames, ~490 k edges per frame, thousands of tiles, segments that
+    straddle tiles and CTA pairs), checked through size-independent properties instead of the slow oracle:
+    * batch invariance: a 3-frame batch (batch_data layout) == the three single-frame results,
+    * precision agreement: the tensor-core path == the fp32 FFMA path within the 1e-3 budget,
+    * aggregation identity: the fused gather/MLP/segment-max layer == the op-by-op composition
+      (gather_rows -> fully_connected -> scatter_max) of the same layer on the same edges."""
+    import pointgnn_b200
+    from pointgnn_b200 import _lib
+    from pointgnn_b200.models import gnn, graph_gen
+    clouds = [synth.lidar_frame(i, 20000) for i in (40, 41, 42)]
+    xyz = torch.from_numpy(np.vstack([c[0] for c in clouds])).cuda()
+    inten = torch.from_numpy(np.vstack([c[1] for c in clouds])).cuda()
+    fp = torch.tensor([0, 20000, 40000, 60000], dtype=torch.int32, device='cuda')
+    coords, kp, edges, fps = graph_gen.gen_multi_level_local_graph_v3(xyz, frame_ptr=fp, return_frame_ptr=True,
+                                                                     **car.graph_kwargs)
+    assert edges[1].shape[0] > 1_000_000
+    logits, boxes, _ = _predict(car, car.layer_configs, precision, (inten, coords, kp, edges))
+    ref_l, ref_b, _ = _predict(car, car.layer_configs, 'fp32', (inten, coords, kp, edges))
+    assert float((logits - ref_l).abs().max()) < 1e-3 and float((boxes - ref_b).abs().max()) < 1e-3
+    bounds = [int(v) for v in fps[1].cpu()]
+    for i, (c, it) in enumerate(clouds):
+        g1 = graph_gen.gen_multi_level_local_graph_v3(torch.from_numpy(c).cuda(), **car.graph_kwargs)
+        l1, b1, _ = _predict(car, car.layer_configs, precision, (torch.from_numpy(it).cuda(),) + tuple(g1))
+        sl = slice(bounds[i], bounds[i + 1])
+        assert l1.shape[0] == bounds[i + 1] - bounds[i]
+        assert float((logits[sl] - l1).abs().max()) < 2e-4
+        assert float((boxes[sl] - b1).abs().max()) < 2e-4
+    # fused layer == op-by-op composition on the full-size keypoint graph (layer 2 weights)
+    pointgnn_b200.set_precision(precision)
+    k = coords[1].shape[0]
+    feats = torch.rand((k, 300), device='cuda') * 0.5
+    sc = 'layer2/extract_vertex_features/fully_connected'
+    ws = [torch.from_numpy(car.weights[sc + '/weights']).cuda(), torch.from_numpy(car.weights[sc + '_1/weights']).cuda()]
+    bs = [torch.from_numpy(car.weights[sc + '/biases']).cuda(), torch.from_numpy(car.weights[sc + '_1/biases']).cuda()]
+    src, dst = edges[1][:, 0].contiguous(), edges[1][:, 1].contiguous()
+    fused = _lib.edge_mlp_max(1, feats, coords[1], coords[1], None, src, dst, k, ws, bs,
+                              precision=pointgnn_b200.get_precision())
+    e0 = 400_000                                   # a prefix of the edge list keeps the [E, 303] tensor small
+    d_last = int(dst[e0 - 1])
+    e0 = int((dst <= d_last).sum())                # whole destination segments only
+    x = torch.cat([_lib.gather_rows(feats, src[:e0]),
+                   _lib.gather_rows(coords[1], src[:e0]) - _lib.gather_rows(coords[1], dst[:e0])], dim=1).contiguous()
+    h = _lib.fully_connected(x, ws[0], bs[0], True, precision=0)
+    h = _lib.fully_connected(h, ws[1], bs[1], True, precision=0)
+    ref = _lib.scatter_max(h, dst[:e0], d_last + 1)
+    assert float((fused[:d_last + 1] - ref).abs().max()) < 2e-4
+    pointgnn_b200.set_precision('fp32')
+
+
 def test_errors_are_python_exceptions(car):
     from pointgnn_b200 import _lib
     from pointgnn_b200.models import gnn, models
