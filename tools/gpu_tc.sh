@@ -1,5 +1,6 @@
 #!/bin/bash
 mkdir -p gpurun_out
-timeout 300 python -m pytest tests/test_gnn_gpu.py -m gpu -x -q -k "full_size" 2>&1 | tail -15 > gpurun_out/pytest_full.log; tail -5 gpurun_out/pytest_full.log
-timeout 200 python bench.py --steps 5 --warmup 3 --no-cpu-baseline --workload car_auto_T3_120k > gpurun_out/bench_120k.log 2>&1; tail -1 gpurun_out/bench_120k.log | cut -c1-900
-timeout 200 python bench.py --steps 5 --warmup 3 --no-cpu-baseline --workload ped_cyl_auto_T3_20k_b8 > gpurun_out/bench_ped.log 2>&1; tail -1 gpurun_out/bench_ped.log | cut -c1-900
+timeout 60 python tools/prof_edge.py 8 5 1 > gpurun_out/prof_edge.log 2>&1; echo "rc=$?"; tail -1 gpurun_out/prof_edge.log
+timeout 200 python -m pytest tests/test_gnn_gpu.py -m gpu -x -q -k "tc_edge or full_size or layers_vs" 2>&1 | tail -25 > gpurun_out/pytest_tc.log; tail -4 gpurun_out/pytest_tc.log
+PG_TC_TRACE=gpurun_out/trace.txt timeout 60 python tools/prof_edge.py 8 1 1 > gpurun_out/trace_run.log 2>&1
+python tools/trace_seg.py gpurun_out/trace.txt 19 2>&1 | head -8 | tee gpurun_out/trace_seg.txt
