@@ -1007,11 +1007,11 @@ __device__ __forceinline__ void seg_producer(const TcParams& p, const SegSmem& s
   int* sin = sm.si_next + g * 128;
   const int row0 = wg * 32 + rr;
   const uint32_t a_off0 = uint32_t(wg * 4) * 256u + uint32_t(c >> 1) * 128u + uint32_t(rr) * 16u + uint32_t(c & 1) * 8u;
-  const int64_t my_tiles = (p.num_pair_tiles - cluster_id + num_clusters - 1) / num_clusters;
+  const int my_tiles = int((p.num_pair_tiles - cluster_id + num_clusters - 1) / num_clusters);   // < 2^31 by far
   if (my_tiles <= 0) return;
   const int ks = p.ks, mid = p.ks >> 1;
-  auto row_of = [&](int64_t j) { return (cluster_id + j * num_clusters) * 256 + int64_t(rank) * kTileRows + r; };
-  auto load_idx = [&](int64_t j, int& si, int& di) {
+  auto row_of = [&](int j) { return (cluster_id + int64_t(j) * num_clusters) * 256 + int64_t(rank) * kTileRows + r; };
+  auto load_idx = [&](int j, int& si, int& di) {
     si = 0;
     di = 0;
     if (j < my_tiles) {
@@ -1037,7 +1037,7 @@ __device__ __forceinline__ void seg_producer(const TcParams& p, const SegSmem& s
     x[3] = __ldg(b); x[4] = __ldg(b + 1); x[5] = __ldg(b + 2);
   };
 
-  int64_t j = 0;        // tile (local index) of the iteration to produce next
+  int j = 0;            // tile (local index) of the iteration to produce next
   int s = g;            // its k-step
   uint32_t it = uint32_t(g);   // global pipeline iteration (stage = it % kSegStages)
   int si_n, di_n;       // edge of row r in tile j + 1
@@ -1054,17 +1054,18 @@ __device__ __forceinline__ void seg_producer(const TcParams& p, const SegSmem& s
     load_xyz(si_n, di_n, nx);
   }
   __syncwarp();
-  auto advance = [&](int64_t& jj, int& ss) {
+  auto advance = [&](int& jj, int& ss) {
     ss += kSegGroups;
     if (ss >= ks) { ss -= ks; ++jj; }
   };
   // slice c of k-step ss of the four rows, tile jj in {j, j + 1}
-  auto fetch = [&](float4 (&q)[4], int64_t jj, int ss) {
+  const float* pbase = p.P + c * 4;
+  auto fetch = [&](float4 (&q)[4], int jj, int ss) {
     if (jj >= my_tiles) return;
 #pragma unroll
     for (int i = 0; i < 4; ++i) {
       const int si = (jj == j) ? __float_as_int(ctx[row0 + 8 * i].w) : sin[row0 + 8 * i];
-      q[i] = ldg_nc_pinned(p.P + int64_t(si) * p.ldp + ss * 16 + c * 4);
+      q[i] = ldg_nc_pinned(pbase + uint32_t(si * p.ldp + ss * 16));   // element offset < 2^31 (checked at launch)
     }
   };
   auto step = [&](float4 (&q)[4]) {
@@ -1088,13 +1089,11 @@ __device__ __forceinline__ void seg_producer(const TcParams& p, const SegSmem& s
       const float v1 = fmaxf(fmaf(cx.z, wz.y, fmaf(cx.y, wy.y, fmaf(cx.x, wx.y, q[i].y))), 0.0f);
       const float v2 = fmaxf(fmaf(cx.z, wz.z, fmaf(cx.y, wy.z, fmaf(cx.x, wx.z, q[i].z))), 0.0f);
       const float v3 = fmaxf(fmaf(cx.z, wz.w, fmaf(cx.y, wy.w, fmaf(cx.x, wx.w, q[i].w))), 0.0f);
-      split_bf16x2(v0, v1, &hi[i].x, &lo[i].x);
-      split_bf16x2(v2, v3, &hi[i].y, &lo[i].y);
+      split_bf16x2_trunc(v0, v1, &hi[i].x, &lo[i].x);
+      split_bf16x2_trunc(v2, v3, &hi[i].y, &lo[i].y);
     }
     const uint32_t stage = it & (kSegStages - 1), parity = (it / kSegStages) & 1u;
-    if (pt == 0) PG_TRACE(1 + rank, it / kSegGroups, 0);
     mbar_wait(&sm.bar_empty[stage], parity ^ 1u);
-    if (pt == 0) PG_TRACE(1 + rank, it / kSegGroups, 1);
     uint8_t* st = sm.a + stage * kStageBytes + a_off0;
 #pragma unroll
     for (int i = 0; i < 4; ++i) {
@@ -1104,9 +1103,8 @@ __device__ __forceinline__ void seg_producer(const TcParams& p, const SegSmem& s
     fence_proxy_async_smem();
     __syncwarp();
     if (lane == 0) mbar_arrive_cluster(&sm.bar_full[stage], 0);
-    if (pt == 0) PG_TRACE(1 + rank, it / kSegGroups, 2);
     it += kSegGroups;
-    int64_t j1 = j, j2;
+    int j1 = j, j2;
     int s1 = s, s2;
     advance(j1, s1);
     j2 = j1;
@@ -1127,7 +1125,7 @@ __device__ __forceinline__ void seg_producer(const TcParams& p, const SegSmem& s
   float4 qa[4], qb[4];
   fetch(qa, 0, s);
   {
-    int64_t j1 = 0;
+    int j1 = 0;
     int s1 = s;
     advance(j1, s1);
     fetch(qb, j1, s1);
@@ -1737,6 +1735,7 @@ int launch_seg_gemm(TcParams& p, const float* w, int k, int n, const float* bias
   p.part_bytes = part;
   p.tmem_cols = n2 > 0 ? 512 : 256;
   p.num_pair_tiles = ceil_div(p.num_rows, 2 * kTileRows);
+  PG_REQUIRE(p.num_src * int64_t(p.ldp) < (int64_t(1) << 31), "vertex table too large for 32-bit element offsets");
   const size_t smem = seg_smem_layout(nullptr, kp, part, nullptr);
   PG_REQUIRE(smem <= 227 * 1024, "tcgen05 kernel needs %zu B of shared memory", smem);
   PG_CUDA_OK(cudaFuncSetAttribute(seg_gemm_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, int(smem)));

@@ -218,5 +218,18 @@ __device__ __forceinline__ void split_bf16x2(float a, float b, uint32_t* hi, uin
   *lo = *reinterpret_cast<const uint32_t*>(&l);
 }
 
+// Cheaper split for the hot producers: hi = x TRUNCATED to BF16 (its fp32 image is one LOP3, the packed pair
+// one PRMT), lo = bf16_rn(x - hi).  |lo| can be twice as large as with a rounded hi, so the split keeps ~2^-17
+// instead of ~2^-18 relative - below the 2^-16 of the dropped lo*lo' term; 6 instead of 8 SASS instructions
+// per pair of values.
+__device__ __forceinline__ void split_bf16x2_trunc(float a, float b, uint32_t* hi, uint32_t* lo) {
+  const uint32_t ua = __float_as_uint(a), ub = __float_as_uint(b);
+  *hi = __byte_perm(ua, ub, 0x7632);                       // {hi16(a), hi16(b)}: a in the low half
+  const float la = a - __uint_as_float(ua & 0xffff0000u);
+  const float lb = b - __uint_as_float(ub & 0xffff0000u);
+  const __nv_bfloat162 l = __floats2bfloat162_rn(la, lb);
+  *lo = *reinterpret_cast<const uint32_t*>(&l);
+}
+
 }  // namespace umma
 }  // namespace pg
