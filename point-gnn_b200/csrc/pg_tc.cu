@@ -104,6 +104,7 @@ struct TcParams {
   const float* residual;  // STORE: optional [num_rows, n]
   int* err;
   int64_t num_pair_tiles;
+  int contig;                  // seg_gemm: contiguous tile chunks per cluster instead of round robin
   unsigned long long* trace;   // optional (PG_TC_TRACE): [role 0..7][slot 0..127][3] globaltimer ns, cluster 0 only
 };
 
@@ -1007,10 +1008,15 @@ __device__ __forceinline__ void seg_producer(const TcParams& p, const SegSmem& s
   int* sin = sm.si_next + g * 128;
   const int row0 = wg * 32 + rr;
   const uint32_t a_off0 = uint32_t(wg * 4) * 256u + uint32_t(c >> 1) * 128u + uint32_t(rr) * 16u + uint32_t(c & 1) * 8u;
-  const int my_tiles = int((p.num_pair_tiles - cluster_id + num_clusters - 1) / num_clusters);   // < 2^31 by far
+  // tile schedule: contiguous chunk per cluster (p.contig) or round robin
+  const int64_t tpc = (p.num_pair_tiles + num_clusters - 1) / num_clusters;
+  const int64_t tile0 = p.contig ? cluster_id * tpc : cluster_id;
+  const int64_t tstride = p.contig ? 1 : num_clusters;
+  const int my_tiles = p.contig ? int(max(int64_t(0), min(tpc, p.num_pair_tiles - tile0)))
+                                : int((p.num_pair_tiles - cluster_id + num_clusters - 1) / num_clusters);
   if (my_tiles <= 0) return;
   const int ks = p.ks, mid = p.ks >> 1;
-  auto row_of = [&](int j) { return (cluster_id + int64_t(j) * num_clusters) * 256 + int64_t(rank) * kTileRows + r; };
+  auto row_of = [&](int j) { return (tile0 + int64_t(j) * tstride) * 256 + int64_t(rank) * kTileRows + r; };
   auto load_idx = [&](int j, int& si, int& di) {
     si = 0;
     di = 0;
@@ -1148,6 +1154,11 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kSegThreads, 1) seg_
   const uint32_t rank = cluster_ctarank();
   const int64_t cluster_id = blockIdx.x >> 1;
   const int64_t num_clusters = gridDim.x >> 1;
+  // tile schedule: a contiguous chunk of the (destination-sorted) edge list per cluster, or round robin
+  const int64_t tpc = (p.num_pair_tiles + num_clusters - 1) / num_clusters;
+  const int64_t tile0 = p.contig ? cluster_id * tpc : cluster_id;
+  const int64_t tstride = p.contig ? 1 : num_clusters;
+  const int64_t tile_end = p.contig ? min(tile0 + tpc, p.num_pair_tiles) : p.num_pair_tiles;
   // D2 (output features 256 ..) is double buffered when two copies fit beside the 256 columns of D1, so
   // the tensor core restarts as soon as D1 has been drained
   constexpr uint32_t kD2Col = 256;
@@ -1200,7 +1211,7 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kSegThreads, 1) seg_
       const uint64_t w2_off = uint64_t((16u * sbo_b) >> 4);   // rows 128.. of this rank's image = features 256..
       const bool has2 = p.n2 > 0;
       uint32_t tile_iter = 0, it = 0;
-      for (int64_t tile = cluster_id; tile < p.num_pair_tiles; tile += num_clusters, ++tile_iter) {
+      for (int64_t tile = tile0; tile < tile_end; tile += tstride, ++tile_iter) {
         const uint32_t buf = d2_stride ? (tile_iter & 1u) : 0u;
         const uint32_t d1 = tmem_u, d2 = tmem_u + kD2Col + buf * d2_stride;
         mbar_wait(sm.bar_d1_empty, (tile_iter & 1u) ^ 1u);
@@ -1244,7 +1255,7 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kSegThreads, 1) seg_
     cluster_sync();   // [sync A]
     const int quarter = warp;
     uint32_t tile_iter = 0;
-    for (int64_t tile = cluster_id; tile < p.num_pair_tiles; tile += num_clusters, ++tile_iter) {
+    for (int64_t tile = tile0; tile < tile_end; tile += tstride, ++tile_iter) {
       const uint32_t buf = d2_stride ? (tile_iter & 1u) : 0u;
       int ids[8];
       segmax_load_ids(p, tile, lane, ids);
@@ -1740,6 +1751,7 @@ int launch_seg_gemm(TcParams& p, const float* w, int k, int n, const float* bias
   PG_REQUIRE(smem <= 227 * 1024, "tcgen05 kernel needs %zu B of shared memory", smem);
   PG_CUDA_OK(cudaFuncSetAttribute(seg_gemm_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, int(smem)));
   if (getenv("PG_TC_NOFLUSH") != nullptr) p.act = 99;       // timing experiment only
+  p.contig = getenv("PG_TC_CONTIG") != nullptr ? 1 : 0;   // experiment: measured slower (1.95 vs 1.78 ms), round robin keeps the clusters on neighbouring vertices
   const int clusters = int(std::min<int64_t>(p.num_pair_tiles, num_sms() / 2));
   const char* trace_path = getenv("PG_TC_TRACE");           // debugging aid
   Temp t_trace;
