@@ -252,12 +252,22 @@ def run_gpu(args, rank, world):
             stage_ms['gnn inference'] += ev[1].elapsed_time(ev[2])
         return probs, boxes, kp[0].shape[0], edges[0].shape[0], edges[1].shape[0]
 
+    # end-to-end arm: pinned host buffers on both sides (inputs above; outputs here, sized for the worst case of
+    # one keypoint per point), asynchronous copies on the compute stream, ONE synchronisation per step
+    n_cls = config['num_classes']
+    out_probs = torch.empty((frames_per_step * num_points, n_cls), dtype=torch.float32).pin_memory()
+    out_boxes = torch.empty((frames_per_step * num_points, n_cls, 7), dtype=torch.float32).pin_memory()
+
     def step_e2e(hx, hi, hfp):
         xyz = hx.to(dev, non_blocking=True)
         inten = hi.to(dev, non_blocking=True)
         fp = hfp.to(dev, non_blocking=True)
         probs, boxes, k, e0, e1 = step_device(xyz, inten, fp)
-        return probs.cpu(), boxes.cpu()
+        hp, hb = out_probs[:k], out_boxes[:k]
+        hp.copy_(probs, non_blocking=True)
+        hb.copy_(boxes, non_blocking=True)
+        torch.cuda.current_stream().synchronize()
+        return hp, hb
 
     def barrier():
         if world > 1:
