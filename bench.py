@@ -326,6 +326,12 @@ def run_gpu(args, rank, world):
     for s in range(n_instr):
         step_device(*dev_steps[(args.warmup + s) % pool], instrument=True)
     edge_ms, edge_flops, edge_launches = time_edge_kernel(model, graph_fn, gkw, dev_steps[args.warmup % pool], config)
+    sm_ms, sm_bytes = (0.0, 0.0)
+    if rank == 0:
+        d_model = [l for l in config['model_kwargs']['layer_configs'] if 'edge_MLP_depth_list' in l['kwargs']]
+        if d_model:
+            sm_ms, sm_bytes = time_scatter_max(graph_fn, gkw, dev_steps[args.warmup % pool],
+                                               d_model[0]['kwargs']['edge_MLP_depth_list'][-1])
 
     # ---- reduce over ranks: the only collective of the job is this all-gather of counters --------
     _, summary = sharding.gather_counters(
@@ -384,6 +390,15 @@ def run_gpu(args, rank, world):
                          # layer only (the first layer is hoisted to a per-vertex GEMM): executed tensor FLOP/s
                          'executed_tensor_tflops': achieved * (2 * 3 * 304 * 304) / 361800.0
                          if cfg_name.startswith('car') else None},
+            # BASELINE.json's "scatter-max GB/s vs roofline": the stand-alone segment-max op (the fused path above
+            # never materialises its [E, D] input; this is the op as the reference calls it)
+            'roofline_scatter_max': {
+                'bound': 'hbm', 'kernel': 'scatter_max_kernel (pg_scatter_max = graph_scatter_max_fn, stand-alone)',
+                'achieved': (sm_bytes / (sm_ms * 1e-3) / 1e9) if sm_ms > 0 else None,
+                'peak': peaks.get('hbm_gbs', 6650.0), 'unit': 'GB/s',
+                'frac': (sm_bytes / (sm_ms * 1e-3) / 1e9 / peaks.get('hbm_gbs', 6650.0)) if sm_ms > 0 else None,
+                'peak_source': 'measured (MEASURED_PEAKS.json hbm_gbs)' if peaks else 'fallback 6.65 TB/s',
+                'launch_ms': sm_ms, 'algorithmic_bytes_per_launch': sm_bytes, 'traffic': None},
             'cpu_baseline': cpu,
         }
         print(json.dumps(line), flush=True)
@@ -425,6 +440,32 @@ def time_edge_kernel(model, graph_fn, gkw, dev_step, config):
     dims = [d[0] + 3] + d
     per_edge = sum(2 * x * y for x, y in zip(dims[:-1], dims[1:]))
     return a.elapsed_time(b), float(src.numel()) * per_edge * reps, reps
+
+
+def time_scatter_max(graph_fn, gkw, dev_step, channels):
+    """BASELINE.json's second roofline: the stand-alone graph_scatter_max_fn op (gnn.py:106-109) on the [E1, D]
+    edge-feature tensor the reference materialises, against the measured HBM copy bandwidth.  Algorithmic bytes
+     = E*C*4 (features) + E*4 (ids) + K*C*4 (output).  Returns (ms per call, bytes per call)."""
+    import torch
+    from pointgnn_b200 import _lib
+    xyz, inten, fp = dev_step
+    coords, kp, edges = graph_fn(xyz, frame_ptr=fp, **gkw)
+    dst = edges[1][:, 1].contiguous()
+    e, k = int(dst.numel()), int(coords[1].shape[0])
+    feats = torch.rand((e, channels), device=xyz.device)          # 4.7 GB at the default workload: >> L2
+    for _ in range(2):
+        _lib.scatter_max(feats, dst, k)
+    torch.cuda.synchronize()
+    reps = 5
+    a = torch.cuda.Event(enable_timing=True)
+    b = torch.cuda.Event(enable_timing=True)
+    a.record()
+    for _ in range(reps):
+        _lib.scatter_max(feats, dst, k)
+    b.record()
+    b.synchronize()
+    del feats
+    return a.elapsed_time(b) / reps, float(e) * channels * 4 + float(e) * 4 + float(k) * channels * 4
 
 
 def main():

@@ -62,6 +62,60 @@ __global__ void __launch_bounds__(256) scatter_max_kernel(const float* __restric
   }
 }
 
+// Vectorised variant (C % 4 == 0, C / 4 <= 256): a thread owns FOUR channels of one edge stream; a block of
+// 256 threads runs 256 / (C/4) streams side by side (C = 300: 3 streams x 75 threads), every stream walks its
+// own 64-edge chunks, and the loads of 8 consecutive edges (8 independent LDG.128 per thread, 2 x C*4 bytes of
+// fully used lines per edge) are issued before they are consumed.  HBM-bound: E*C*4 bytes are read once.
+__global__ void __launch_bounds__(256) scatter_max_vec4_kernel(const float4* __restrict__ feat,
+                                                                const int32_t* __restrict__ centers,
+                                                                int64_t num_edges, int vecs_per_row, int64_t num_centers,
+                                                                float* __restrict__ out) {
+  const int streams = 256 / vecs_per_row;
+  const int s = threadIdx.x / vecs_per_row, v = threadIdx.x - s * vecs_per_row;
+  if (s >= streams) return;
+  const int num_channels = vecs_per_row * 4;
+  const int64_t num_chunks = (num_edges + kScatterChunk - 1) / kScatterChunk;
+  auto flush = [&](int cur, const float4& m) {
+    if (cur >= 0 && cur < num_centers) {
+      float* o = out + int64_t(cur) * num_channels + 4 * v;
+      atomic_max_float(o + 0, m.x);
+      atomic_max_float(o + 1, m.y);
+      atomic_max_float(o + 2, m.z);
+      atomic_max_float(o + 3, m.w);
+    }
+  };
+  for (int64_t chunk = int64_t(blockIdx.x) * streams + s; chunk < num_chunks; chunk += int64_t(gridDim.x) * streams) {
+    const int64_t e0 = chunk * kScatterChunk;
+    const int64_t e1 = min(e0 + kScatterChunk, num_edges);
+    int cur = -1;
+    float4 m = make_float4(-FLT_MAX, -FLT_MAX, -FLT_MAX, -FLT_MAX);
+    for (int64_t e = e0; e < e1; e += 8) {
+      float4 val[8];
+      int d[8];
+#pragma unroll
+      for (int i = 0; i < 8; ++i) {
+        const bool ok = e + i < e1;
+        d[i] = ok ? __ldg(centers + e + i) : -1;
+        val[i] = ok ? __ldg(feat + (e + i) * vecs_per_row + v) : make_float4(-FLT_MAX, -FLT_MAX, -FLT_MAX, -FLT_MAX);
+      }
+#pragma unroll
+      for (int i = 0; i < 8; ++i) {
+        if (e + i >= e1) break;
+        if (d[i] != cur) {
+          flush(cur, m);
+          cur = d[i];
+          m = make_float4(-FLT_MAX, -FLT_MAX, -FLT_MAX, -FLT_MAX);
+        }
+        m.x = fmaxf(m.x, val[i].x);
+        m.y = fmaxf(m.y, val[i].y);
+        m.z = fmaxf(m.z, val[i].z);
+        m.w = fmaxf(m.w, val[i].w);
+      }
+    }
+    flush(cur, m);
+  }
+}
+
 __global__ void gather_rows_kernel(const float* __restrict__ params, int64_t num_rows, int num_channels,
                                    const int32_t* __restrict__ indices, int64_t num_indices,
                                    float* __restrict__ out, int* __restrict__ err) {
@@ -183,8 +237,16 @@ extern "C" int pg_scatter_max(const float* features, const int32_t* centers, int
   if (int rc = fill_async(out, num_centers * num_channels, -FLT_MAX, s)) return rc;
   if (num_edges == 0) return PG_OK;
   PG_REQUIRE(features && centers, "pg_scatter_max: null input");
-  const int threads = num_channels >= 256 ? 256 : (num_channels >= 128 ? 128 : (num_channels >= 64 ? 64 : 32));
   const int64_t chunks = ceil_div(num_edges, kScatterChunk);
+  if ((num_channels & 3) == 0 && num_channels / 4 <= 256 && (reinterpret_cast<uintptr_t>(features) & 15) == 0) {
+    const int vecs = num_channels / 4, streams = 256 / vecs;
+    const int blocks = int(std::min<int64_t>(ceil_div(chunks, streams), int64_t(num_sms()) * 8));
+    scatter_max_vec4_kernel<<<blocks, 256, 0, s>>>(reinterpret_cast<const float4*>(features), centers, num_edges, vecs,
+                                                   num_centers, out);
+    PG_LAUNCH_CHECK();
+    return PG_OK;
+  }
+  const int threads = num_channels >= 256 ? 256 : (num_channels >= 128 ? 128 : (num_channels >= 64 ? 64 : 32));
   dim3 grid(ceil_div(num_channels, threads), int(std::min<int64_t>(chunks, 65535)));
   scatter_max_kernel<<<grid, threads, 0, s>>>(features, centers, num_edges, num_channels, num_centers, out);
   PG_LAUNCH_CHECK();

@@ -1,5 +1,5 @@
 #!/bin/bash
 mkdir -p gpurun_out
-timeout 60 python tools/prof_edge.py 8 5 1 > gpurun_out/prof_edge.log 2>&1; echo "rc=$?"; tail -1 gpurun_out/prof_edge.log
-PG_TC_ROUNDROBIN=1 timeout 60 python tools/prof_edge.py 8 5 1 > gpurun_out/prof_edge_rr.log 2>&1; echo "rc=$?"; tail -1 gpurun_out/prof_edge_rr.log
-timeout 200 python -m pytest tests/test_gnn_gpu.py -m gpu -x -q -k "tc_edge or full_size or layers_vs or golden" 2>&1 | tail -25 > gpurun_out/pytest_tc.log; tail -4 gpurun_out/pytest_tc.log
+timeout 300 python bench.py --steps 10 --warmup 3 --no-cpu-baseline > gpurun_out/bench_quick.log 2>&1; tail -1 gpurun_out/bench_quick.log | python -c "
+import sys, json
+d = json.loads(sys.stdin.read()); print(d['value'], d['e2e']['value'], d['roofline']['frac'], json.dumps(d['roofline_scatter_max']))"
