@@ -34,10 +34,11 @@ class Golden(object):
 
     def __init__(self, name):
         self.name = name
+        graph_name = name if name.startswith('ped') else 'car_auto_T3_train'   # car checkpoints share one graph
         with open(os.path.join(GOLDEN, 'config_%s.json' % name)) as f:
             self.config = json.load(f)
         self.weights = dict(np.load(os.path.join(GOLDEN, 'weights_%s.npz' % name)))
-        self.graph = dict(np.load(os.path.join(GOLDEN, 'graph_%s.npz' % name)))
+        self.graph = dict(np.load(os.path.join(GOLDEN, 'graph_%s.npz' % graph_name)))
         self.gnn = dict(np.load(os.path.join(GOLDEN, 'gnn_%s.npz' % name)))
 
     @property
@@ -66,6 +67,10 @@ def load_golden(name):
     if name not in _cache:
         _cache[name] = Golden(name)
     return _cache[name]
+
+
+ALL_CHECKPOINTS = ['car_auto_T0_train', 'car_auto_T1_train', 'car_auto_T2_train', 'car_auto_T3_train',
+                   'car_auto_T3_trainval', 'car_fixed_T3_train', 'ped_cyl_auto_T3_trainval']
 
 
 @pytest.fixture(scope='session')

@@ -7,10 +7,14 @@
   and the edge lists produced by the REFERENCE's own models/graph_gen.py
   (gen_disjointed_rnn_local_graph_v3, scikit-learn ball tree) on those vertices, in canonical
   (dst, src) order -> pins oracle/graph.py and the CUDA radius kernels to the reference.
-* gnn_<cfg>.npz : logits / box encodings / per-layer features of oracle/gnn.py (fp32) on that
-  graph with the real weights.  TensorFlow 1.15 cannot run here, so these are regression
-  vectors of the restatement, not outputs of the reference ("parity unpinned").
+* gnn_<cfg>.npz : logits / box encodings / class probabilities / per-layer features obtained by
+  executing the REFERENCE'S OWN saved TensorFlow graph (checkpoints/<cfg>/model-N.meta, the
+  MetaGraphDef train.py wrote) with the NumPy GraphDef interpreter oracle/graphdef.py on that
+  frame with the real weights -> pins oracle/gnn.py and the CUDA kernels to the graph the
+  reference built (op order, concat order, gather indices, segment ids), for all seven shipped
+  checkpoints.  The script asserts that oracle/gnn.py reproduces those vectors to <= 1e-5.
 """
+import glob
 import json
 import os
 import sys
@@ -20,13 +24,19 @@ import numpy as np
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 sys.path.insert(0, ROOT)
 
-from oracle import gnn, graph, reference_graph, synth  # noqa: E402
+from oracle import gnn, graph, graphdef, reference_graph, synth  # noqa: E402
 from pointgnn_b200.utils import tf_checkpoint  # noqa: E402
 
 GOLDEN = os.path.join(ROOT, 'tests', 'golden')
 CONFIGS = {
-    'car_auto_T3_train': dict(num_points=3000, frame=7),
-    'ped_cyl_auto_T3_trainval': dict(num_points=3000, frame=8),
+    'car_auto_T3_train': dict(num_points=3000, frame=7, graph='car_auto_T3_train'),
+    'ped_cyl_auto_T3_trainval': dict(num_points=3000, frame=8, graph='ped_cyl_auto_T3_trainval'),
+    # the other shipped checkpoints share car_auto_T3_train's graph settings (and its graph fixture)
+    'car_auto_T0_train': dict(num_points=3000, frame=7, graph='car_auto_T3_train'),
+    'car_auto_T1_train': dict(num_points=3000, frame=7, graph='car_auto_T3_train'),
+    'car_auto_T2_train': dict(num_points=3000, frame=7, graph='car_auto_T3_train'),
+    'car_auto_T3_trainval': dict(num_points=3000, frame=7, graph='car_auto_T3_train'),
+    'car_fixed_T3_train': dict(num_points=3000, frame=7, graph='car_auto_T3_train'),
 }
 
 
@@ -53,17 +63,32 @@ def main():
             e = graph.canonical_edges(e)
             assert np.array_equal(e, edges[lvl]), 'oracle radius graph != reference graph_gen'
             ref_edges.append(e.astype(np.int32))
-        np.savez_compressed(
-            os.path.join(GOLDEN, 'graph_%s.npz' % name), xyz=xyz, intensity=intensity,
-            keypoint_idx=keypoints[0][:, 0].astype(np.int32),
-            edges0=ref_edges[0], edges1=ref_edges[1])
+        if spec['graph'] == name:
+            np.savez_compressed(
+                os.path.join(GOLDEN, 'graph_%s.npz' % name), xyz=xyz, intensity=intensity,
+                keypoint_idx=keypoints[0][:, 0].astype(np.int32),
+                edges0=ref_edges[0], edges1=ref_edges[1])
+        # the reference's own saved graph, interpreted op by op
+        meta = sorted(glob.glob(os.path.join(ckpt_dir, 'model-*.meta')))[-1]
+        nodes = graphdef.load_meta_graph(meta)
+        pool_node = 'layer1/combined_features/fully_connected_1/Relu'
+        last_node = nodes['output/predictor/cls/fully_connected/MatMul'].inputs[0]
+        all_vars = tf_checkpoint.load_checkpoint(ckpt_dir)
+        out = graphdef.run_forward(meta, all_vars, intensity, coords, keypoints, edges,
+                                   extra_nodes=(pool_node, last_node))
+        np.savez_compressed(os.path.join(GOLDEN, 'gnn_%s.npz' % name), logits=out['logits'], boxes=out['boxes'],
+                            probs=out['probs'], features_pool=out[pool_node], features_last=out[last_node])
+        with open(os.path.join(GOLDEN, 'graphdef_ops_%s.json' % name), 'w') as f:
+            json.dump({'meta': os.path.basename(meta), 'nodes_total': len(nodes), 'ops_executed': out['ops']},
+                      f, indent=1, sort_keys=True)
         logits, boxes, feats = gnn.predict(weights, config['model_kwargs']['layer_configs'],
                                            config['num_classes'], 7, intensity, coords, keypoints, edges,
                                            return_features=True)
-        np.savez_compressed(os.path.join(GOLDEN, 'gnn_%s.npz' % name), logits=logits, boxes=boxes,
-                            features_pool=feats[1], features_last=feats[-1])
+        err = max(np.abs(logits - out['logits']).max(), np.abs(boxes - out['boxes']).max(),
+                  np.abs(feats[1] - out[pool_node]).max(), np.abs(feats[-1] - out[last_node]).max())
+        assert err <= 1e-5, 'oracle/gnn.py differs from the reference graph by %g' % err
         print(name, 'K=%d E0=%d E1=%d' % (len(keypoints[0]), len(edges[0]), len(edges[1])),
-              'logits', logits.shape, float(np.abs(logits).max()))
+              'logits', logits.shape, float(np.abs(logits).max()), 'restatement-vs-graphdef %g' % err)
 
 
 if __name__ == '__main__':
