@@ -214,6 +214,11 @@ def fully_connected(x, w, b, relu, residual=None, precision=0):
     if w.shape[0] != k:
         raise ValueError('fully_connected: input width %d != weight rows %d' % (k, w.shape[0]))
     n = w.shape[1]
+    if b.numel() != n:
+        raise ValueError('fully_connected: bias has %d entries, layer width is %d' % (b.numel(), n))
+    if residual is not None and tuple(residual.shape) != (m, n):
+        # the reference's tf add raises a shape error here (gnn.py:346, 372)
+        raise ValueError('fully_connected: residual shape %s != output shape (%d, %d)' % (tuple(residual.shape), m, n))
     out = torch.empty((m, n), dtype=torch.float32, device=x.device)
     _check(lib.pg_fully_connected(_ptr(x, torch.float32, 'x'), m, k, _ptr(w, torch.float32, 'w'),
                                   _ptr(b, torch.float32, 'b'), n, 1 if relu else 0,

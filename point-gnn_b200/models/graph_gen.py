@@ -82,8 +82,9 @@ def _downsampling_select(cloud, base_voxel_size, levels, add_rnd3d):
             # same scale (a gnn layer): identity, graph_gen.py:76-81
             vertex_coord_list.append(base_points)
             frame_ptr_list.append(frame_ptr_list[-1])
-            keypoint_indices_list.append(
-                torch.arange(base_points.shape[0], dtype=torch.int32, device=base_points.device)[:, None])
+            kidx = torch.arange(base_points.shape[0], dtype=torch.int32, device=base_points.device)[:, None]
+            kidx._pg_trusted = (int(base_points.shape[0]), kidx._version)
+            keypoint_indices_list.append(kidx)
         else:
             # graph_gen.py:41-45 voxelises the ORIGINAL cloud, :84-88 snaps to the previous level.
             # All shipped configs have one distinct scale, where previous level == original cloud.
@@ -92,7 +93,9 @@ def _downsampling_select(cloud, base_voxel_size, levels, add_rnd3d):
             idx, kp_fp = _lib.voxel_keypoints(cloud.xyz, cloud.frame_ptr, _voxel_vector(base_voxel_size, level))
             vertex_coord_list.append(_lib.gather_rows(cloud.xyz, idx))
             frame_ptr_list.append(kp_fp)
-            keypoint_indices_list.append(idx[:, None])
+            kidx = idx[:, None]
+            kidx._pg_trusted = (int(cloud.xyz.shape[0]), kidx._version)      # rows of the level it was snapped to
+            keypoint_indices_list.append(kidx)
         last_level = level
     return vertex_coord_list, keypoint_indices_list, frame_ptr_list
 
@@ -109,7 +112,7 @@ def _radius_edges(points, point_fp, centers, center_fp, radius, num_neighbors,
     _, edges = _lib.radius_graph(points, point_fp, centers, center_fp, radius)
     edges = edges.t()     # [E,2] view whose columns (src, dst) are contiguous
     # index ranges are guaranteed by construction: lets model.predict skip the per-layer range check
-    edges._pg_trusted = (int(points.shape[0]), int(centers.shape[0]))
+    edges._pg_trusted = (int(points.shape[0]), int(centers.shape[0]), edges._version)
     return edges
 
 

@@ -72,6 +72,12 @@ class MultiLayerFastLocalGraphModelV2(object):
             return t if t.dtype == dtype else t.to(dtype)
         return torch.from_numpy(np.ascontiguousarray(x)).cuda().to(dtype)
 
+    @staticmethod
+    def _stamp(t, ranges):
+        """What models.graph_gen attaches to the index tensors it produces: the ranges they were built for and
+        the tensor's version counter, so that an in-place edit (manual batching offsets) invalidates the stamp."""
+        return tuple(int(r) for r in ranges) + (getattr(t, '_version', None),)
+
     def predict(self, t_initial_vertex_features, t_vertex_coord_list, t_keypoint_indices_list,
                 t_edges_list, is_training=False):
         """models.py:79-163.  -> (logits [K, C], box_encodings [K, C, box_encoding_len])."""
@@ -81,17 +87,34 @@ class MultiLayerFastLocalGraphModelV2(object):
         tfeatures = self._to_device(t_initial_vertex_features, torch.float32).contiguous()
         coords = [self._to_device(c, torch.float32).contiguous() for c in t_vertex_coord_list]
         keypoints = [None if k is None else self._to_device(k, torch.int32) for k in t_keypoint_indices_list]
+        # Shape / range contract of the index inputs.  The reference gets these checks from TF at sess.run
+        # (tf.gather and unsorted_segment_max raise InvalidArgumentError, run.py:260); here they are made ONCE
+        # per predict call so that the fused kernels may skip their per-layer read-back of the error flag.
+        if tfeatures.shape[0] != coords[0].shape[0]:
+            raise ValueError('features have %d rows, level-0 coordinates %d' % (tfeatures.shape[0], coords[0].shape[0]))
+        for level, k in enumerate(keypoints):
+            if k is None or level + 1 >= len(coords):
+                continue
+            if k.shape[0] != coords[level + 1].shape[0]:
+                raise ValueError('keypoint_indices[%d] has %d rows, level-%d coordinates %d'
+                                 % (level, k.shape[0], level + 1, coords[level + 1].shape[0]))
+            if getattr(t_keypoint_indices_list[level], '_pg_trusted', None) != self._stamp(
+                    t_keypoint_indices_list[level], (coords[level].shape[0],)) and k.numel() > 0:
+                kk = k.reshape(-1).contiguous()
+                _lib.check_edges(kk, kk, coords[level].shape[0], coords[level].shape[0])
         edges = []
         trusted = []
         for level, e in enumerate(t_edges_list):
             stamp = getattr(e, '_pg_trusted', None)         # set by models.graph_gen on its own output
+            ranges = (coords[level].shape[0], coords[level + 1].shape[0]) if level + 1 < len(coords) else None
+            fresh = ranges is not None and stamp == self._stamp(e, ranges)
             e = self._to_device(e, torch.int32)
+            if e.dim() != 2 or e.shape[1] != 2:
+                raise ValueError('edges[%d] must be [E, 2] (source, destination), got %s' % (level, tuple(e.shape)))
             if e.stride(0) != 1:                 # make the (src, dst) columns contiguous
                 e = e.t().contiguous().t()
-            ranges = (coords[level].shape[0], coords[level + 1].shape[0]) if level + 1 < len(coords) else None
-            if ranges is not None and stamp != ranges and e.shape[0] > 0:
-                # foreign edge list: one range check here (TF raises InvalidArgumentError at sess.run)
-                # instead of a synchronising check inside every layer
+            if ranges is not None and not fresh and e.shape[0] > 0:
+                # foreign (or edited) edge list: one synchronising range check here
                 _lib.check_edges(e[:, 0], e[:, 1], ranges[0], ranges[1])
             edges.append(e)
             trusted.append(ranges is not None)
@@ -108,6 +131,9 @@ class MultiLayerFastLocalGraphModelV2(object):
             predictor_config = self._layer_configs[-1]
             assert predictor_config['type'] in ('classaware_predictor', 'classaware_predictor_128',
                                                 'classaware_separated_predictor')
+            if predictor_config['type'] not in self._default_layers_type:
+                raise NotImplementedError('layer type %r (models.py:65-71) is used by no shipped config and is not '
+                                          'built' % predictor_config['type'])
             predictor = self._default_layers_type[predictor_config['type']]
             with gnn.variable_scope(predictor_config['scope']):
                 logits, box_encodings = predictor.apply_regular(

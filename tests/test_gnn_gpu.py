@@ -8,6 +8,7 @@ import numpy as np
 import pytest
 import torch
 
+from conftest import ALL_CHECKPOINTS, load_golden
 from oracle import gnn as ognn
 from oracle import graph as ograph
 from oracle import synth
@@ -48,14 +49,20 @@ def test_scatter_max_vs_oracle():
     assert np.array_equal(out, ognn.graph_scatter_max_fn(f, ids, 5))
 
 
-@pytest.mark.parametrize('precision', ['fp32'])
+@pytest.mark.parametrize('precision', PRECISIONS)
 def test_fully_connected_vs_oracle(precision):
+    """pg_fully_connected alone (NumPy fp32 as the checker): odd shapes, row tails (m % 256 != 0), K not a
+    multiple of 16, N < 8 heads, bias / ReLU / residual combinations - for the FFMA kernel and for the
+    tcgen05 BF16x3 dense kernel (which must really run for the wide shapes)."""
+    _need(precision)
     import pointgnn_b200
     from pointgnn_b200 import _lib
     pointgnn_b200.set_precision(precision)
     rng = np.random.default_rng(1)
+    tol = 1e-4 if precision == 'fp32' else 3e-4
+    dense0 = _lib.tc_launch_count(1)
     for m, k, n in ((1, 1, 1), (257, 300, 300), (1000, 303, 300), (77, 64, 3), (513, 4, 32), (130, 512, 256),
-                    (64, 300, 7)):
+                    (64, 300, 7), (255, 256, 256), (256, 300, 64), (4099, 300, 320), (33, 128, 300)):
         x = rng.standard_normal((m, k)).astype(np.float32)
         w = (rng.standard_normal((k, n)) / np.sqrt(k)).astype(np.float32)
         b = rng.standard_normal(n).astype(np.float32)
@@ -69,7 +76,9 @@ def test_fully_connected_vs_oracle(precision):
                     want = want + res
                 got = _lib.fully_connected(_cuda(x), _cuda(w), _cuda(b), relu, residual=None if res is None else _cuda(res),
                                            precision=pointgnn_b200.get_precision()).cpu().numpy()
-                assert np.abs(got - want).max() < 1e-4, (m, k, n, relu)
+                assert got.shape == want.shape and np.abs(got - want).max() < tol, (m, k, n, relu)
+    if precision == 'bf16x3':
+        assert _lib.tc_launch_count(1) - dense0 >= 6 * 4      # the wide shapes went through tcgen05
     pointgnn_b200.set_precision('fp32')
 
 
@@ -194,6 +203,65 @@ def test_predict_matches_golden(name, precision, request):
     assert np.array_equal(probs.argmax(1), ognn.postprocess(g.gnn['logits']).argmax(1))
 
 
+@pytest.mark.parametrize('name', ALL_CHECKPOINTS)
+@pytest.mark.parametrize('precision', PRECISIONS)
+def test_every_checkpoint_matches_the_reference_graph(name, precision):
+    """All seven shipped checkpoints (T0..T3, trainval, car_fixed = auto_offset False, ped_cyl) against
+    tests/golden/gnn_<cfg>.npz = the outputs of the reference's own saved TensorFlow graph
+    (checkpoints/<cfg>/model-N.meta interpreted by oracle/graphdef.py): logits, box encodings, class
+    probabilities within the 1e-3 budget of north_star."""
+    _need(precision)
+    g = load_golden(name)
+    coords, keypoints, edges = g.graph_tuple()
+    logits, boxes, probs = _predict(g, g.layer_configs, precision, (g.graph['intensity'], coords, keypoints, edges))
+    assert logits.shape == g.gnn['logits'].shape and boxes.shape == g.gnn['boxes'].shape
+    assert np.abs(logits - g.gnn['logits']).max() < TOL, name
+    assert np.abs(boxes - g.gnn['boxes']).max() < TOL, name
+    assert np.abs(probs - g.gnn['probs']).max() < 1e-4, name
+
+
+# (checkpoint, points per frame, full 360, frames batched, precisions): the BASELINE.json configurations at
+# FULL size, checked against the CPU oracle port (oracle/cpu_reference.predict, itself checked against
+# oracle/gnn.py and so against the reference's saved graph in the CPU suite)
+FULL_SIZE = [
+    ('car_auto_T3_train', 20000, False, 1, ('fp32', 'bf16x3')),       # C2
+    ('car_auto_T3_train', 120000, True, 1, ('bf16x3',)),              # C3
+    ('ped_cyl_auto_T3_trainval', 20000, False, 8, ('bf16x3',)),       # C4: batch of 8 (batch_data layout)
+    ('car_auto_T0_train', 20000, False, 1, ('bf16x3',)),
+    ('car_auto_T2_train', 20000, False, 1, ('bf16x3',)),
+    ('car_fixed_T3_train', 20000, False, 1, ('bf16x3',)),
+]
+
+
+@pytest.mark.parametrize('name,num_points,full_360,frames,precisions', FULL_SIZE,
+                         ids=['C2_car_T3_20k', 'C3_car_T3_120k', 'C4_ped_b8', 'car_T0_20k', 'car_T2_20k', 'car_fixed_20k'])
+def test_full_size_vs_oracle(name, num_points, full_360, frames, precisions):
+    """CUDA vs the oracle at BASELINE sizes: the graph is built on the GPU (edge lists of the first frame are
+    compared with the oracle's graph builder bit-exactly), the forward pass runs on the GPU and on the CPU
+    oracle from the SAME vertex / edge arrays, outputs within 1e-3."""
+    from oracle import cpu_reference
+    from pointgnn_b200.models import graph_gen
+    g = load_golden(name)
+    clouds = [synth.lidar_frame(70 + i, num_points, full_360) for i in range(frames)]
+    xyz = np.vstack([c[0] for c in clouds])
+    inten = np.vstack([c[1] for c in clouds])
+    fp = np.arange(frames + 1, dtype=np.int32) * num_points
+    coords, kp, edges = graph_gen.gen_multi_level_local_graph_v3(xyz, frame_ptr=fp, **g.graph_kwargs)
+    if num_points <= 20000:
+        co, ko, eo = ograph.gen_multi_level_local_graph_v3(clouds[0][0], **g.graph_kwargs)
+        k0, (n0, n1) = len(ko[0]), (len(eo[0]), len(eo[1]))
+        assert np.array_equal(kp[0][:k0], ko[0])
+        assert np.array_equal(edges[0][:n0], eo[0]) and np.array_equal(edges[1][:n1], eo[1])
+    want_l, want_b, want_p = cpu_reference.predict(g.weights, g.layer_configs, g.config['num_classes'], 7, inten,
+                                                   coords, kp, edges)
+    for precision in precisions:
+        _need(precision)
+        logits, boxes, probs = _predict(g, g.layer_configs, precision, (inten, coords, kp, edges))
+        err = max(np.abs(logits - want_l).max(), np.abs(boxes - want_b).max())
+        assert err < TOL, (name, precision, err)
+        assert np.abs(probs - want_p).max() < 1e-4
+
+
 @pytest.mark.parametrize('precision', PRECISIONS)
 def test_car_auto_T1_end_to_end(car, precision):
     """BASELINE config 1: car_auto_T1 (pool + 1 GNN iteration + predictor), graph built on the GPU,
@@ -306,6 +374,38 @@ def test_errors_are_python_exceptions(car):
             gnn.multi_layer_neural_network_fn(torch.zeros((2, 3), device='cuda'), Ks=(4,), normalization_type='NONE')
     with pytest.raises(NotImplementedError):
         gnn.multi_layer_neural_network_fn(torch.zeros((2, 3), device='cuda'), Ks=(4,))   # default BN: not built
+    with pytest.raises(ValueError):     # residual of the wrong shape (the reference's tf.add raises)
+        _lib.fully_connected(torch.zeros((2, 4), device='cuda'), w, b, True, residual=torch.zeros((2, 3), device='cuda'))
+
+
+def test_index_contract_of_predict(car):
+    """The trusted-index fast path must not read out of bounds on inconsistent inputs (TF raises
+    InvalidArgumentError at sess.run for each of these): feature / keypoint tensors whose row counts do not
+    match the coordinate lists, keypoint indices out of range, and graph_gen edge tensors edited in place."""
+    from pointgnn_b200 import _lib
+    from pointgnn_b200.models import graph_gen, models
+    m = models.get_model('multi_layer_fast_local_graph_model_v2')(num_classes=4, box_encoding_len=7, mode='test',
+                                                                  **car.config['model_kwargs'])
+    m.load_weights(car.weights)
+    xyz, inten = synth.lidar_frame(5, 2000)
+    xyz_t, inten_t = torch.from_numpy(xyz).cuda(), torch.from_numpy(inten).cuda()
+    coords, kp, edges = graph_gen.gen_multi_level_local_graph_v3(xyz_t, **car.graph_kwargs)
+    good_l, _ = m.predict(inten_t, coords, kp, edges)
+    with pytest.raises(ValueError):
+        m.predict(inten_t[:-1], coords, kp, edges)                       # features shorter than coords[0]
+    with pytest.raises(ValueError):
+        m.predict(inten_t, coords, [kp[0][:-1], kp[1]], edges)           # keypoints shorter than coords[1]
+    bad_kp = kp[0].clone()
+    bad_kp[0, 0] = xyz.shape[0] + 7
+    with pytest.raises(_lib.PointGNNError):
+        m.predict(inten_t, coords, [bad_kp, kp[1]], edges)               # keypoint index out of range
+    edited = edges[1]
+    edited[:, 0] += coords[1].shape[0]                                   # in-place edit keeps the attribute ...
+    with pytest.raises(_lib.PointGNNError):                              # ... but the version stamp differs
+        m.predict(inten_t, coords, kp, [edges[0], edited])
+    edited[:, 0] -= coords[1].shape[0]
+    again_l, _ = m.predict(inten_t, coords, kp, [edges[0], edited])      # re-checked, in range again
+    assert torch.equal(good_l, again_l)
 
 
 @pytest.mark.parametrize('d,c_in', [(300, 300), (256, 256), (64, 32), (128, 300)])

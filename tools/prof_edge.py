@@ -10,6 +10,8 @@ ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 sys.path.insert(0, ROOT)
 from oracle import synth  # noqa: E402
 from pointgnn_b200 import _lib  # noqa: E402
+if os.environ.get('PG_USE_LAB_LIB'):      # lab build (make -C point-gnn_b200/csrc lab): in-kernel tracing via PG_TC_TRACE
+    _lib.LIB_PATH = os.path.join(os.path.dirname(_lib.LIB_PATH), 'libpointgnn_b200_lab.so')
 from pointgnn_b200.models import graph_gen  # noqa: E402
 
 frames = int(sys.argv[1]) if len(sys.argv) > 1 else 8
