@@ -188,6 +188,56 @@ PG_API int pg_edge_mlp_max(int32_t mode, const float* features, int32_t num_feat
 PG_API int pg_check_edges(const int32_t* src, const int32_t* dst, int64_t num_edges, int64_t num_src,
                    int64_t num_dst, void* stream);
 
+/* ------------------------------------------------------------------------ *
+ * Prepared layers.  The reference creates its variables once (tf.variable_scope +
+ * slim.fully_connected at graph-build time, gnn.py:63-80, models.py:113-163) and
+ * restores them once (run.py:192-202); every sess.run then only computes.  The
+ * equivalent here: pg_layer_create packs everything that depends on the weights
+ * only (BF16 hi / lo tensor-core operand images, padded biases, the hoisted first
+ * edge layer, the concatenated predictor heads) into an opaque handle; the
+ * pg_layer_* calls below launch compute kernels only.  The handle keeps the
+ * caller's weight pointers (the fp32 FFMA paths read them directly): they must
+ * outlive it.  Handles are immutable after creation and may be shared by streams.
+ *
+ *   kind PG_LAYER_MLP        num_layers fully-connected layers (gnn.py:34-104),
+ *                            dims_host [num_layers + 1].
+ *   kind PG_LAYER_EDGE_POOL  PointSetPooling's point MLP + max (gnn.py:256-277)
+ *   kind PG_LAYER_EDGE_GNN   GraphNetAutoCenter's edge MLP + max (gnn.py:338-365)
+ *                            dims_host [num_layers + 1], dims[0] = C_in + 3 (as pg_edge_mlp_max).
+ *   kind PG_LAYER_PREDICTOR  ClassAwarePredictor (gnn.py:133-163, models.py:60-64):
+ *                            dims_host = {D, H, C, box_len}; layers in the order the
+ *                            reference creates them: cls fc (D->H), cls fc_1 (H->C), then
+ *                            for every class c: loc fc (D->H), fc_1 (H->H), fc_2 (H->box_len);
+ *                            num_layers = 2 + 3 C.
+ *   precision 0 = fp32 FFMA, 1 = tcgen05 BF16x3 wherever the shapes allow.
+ * ------------------------------------------------------------------------ */
+typedef struct pg_layer pg_layer;
+#define PG_LAYER_MLP 0
+#define PG_LAYER_EDGE_POOL 1
+#define PG_LAYER_EDGE_GNN 2
+#define PG_LAYER_PREDICTOR 3
+PG_API int pg_layer_create(int32_t kind, const float* const* weights_host, const float* const* biases_host,
+                    const int32_t* dims_host, int32_t num_layers, int32_t precision, void* stream,
+                    pg_layer** out_layer);
+PG_API int pg_layer_destroy(pg_layer* layer);
+
+/* multi_layer_neural_network_fn / multi_layer_fc_fn (gnn.py:34-104) on a prepared chain:
+ * ReLU after every layer except - when last_linear != 0 (is_logits=True) - the last;
+ * `residual` [m, dims[last]] (optional) is added to the last layer's output (gnn.py:346, 372). */
+PG_API int pg_layer_mlp(const pg_layer* layer, const float* x, int64_t m, int32_t last_linear,
+                 const float* residual, float* out, void* stream);
+
+/* pg_edge_mlp_max on a prepared edge layer; flags: 0 or PG_FLAG_TRUSTED_INDICES. */
+PG_API int pg_layer_edge_mlp_max(const pg_layer* layer, const float* features, const float* xyz_src,
+                          const float* xyz_dst, const int32_t* dst_index, const int32_t* src,
+                          const int32_t* dst, int64_t num_edges, int64_t num_src, int64_t num_dst,
+                          float* out, int32_t flags, void* stream);
+
+/* ClassAwarePredictor.apply_regular (gnn.py:133-163) + postprocess (models.py:165-168):
+ * logits [m, C], boxes [m, C, box_len], probs [m, C] (probs may be NULL). */
+PG_API int pg_layer_predictor(const pg_layer* layer, const float* x, int64_t m, float* logits, float* boxes,
+                       float* probs, void* stream);
+
 /* Row-wise softmax, MultiLayerFastLocalGraphModelV2.postprocess (models.py:165-168). */
 PG_API int pg_softmax_rows(const float* logits, int64_t num_rows, int32_t num_classes, float* out,
                     void* stream);

@@ -45,7 +45,16 @@ SIGNATURES = {
                                        ctypes.POINTER(c_i32), c_i32, c_f32p, c_i32, ctypes.c_void_p]),
     'pg_softmax_rows': (ctypes.c_int, [c_f32p, c_i64, c_i32, c_f32p, ctypes.c_void_p]),
     'pg_check_edges': (ctypes.c_int, [c_i32p, c_i32p, c_i64, c_i64, c_i64, ctypes.c_void_p]),
+    'pg_layer_create': (ctypes.c_int, [c_i32, ctypes.POINTER(ctypes.c_void_p), ctypes.POINTER(ctypes.c_void_p),
+                                       ctypes.POINTER(c_i32), c_i32, c_i32, ctypes.c_void_p,
+                                       ctypes.POINTER(ctypes.c_void_p)]),
+    'pg_layer_destroy': (ctypes.c_int, [ctypes.c_void_p]),
+    'pg_layer_mlp': (ctypes.c_int, [ctypes.c_void_p, c_f32p, c_i64, c_i32, c_f32p, c_f32p, ctypes.c_void_p]),
+    'pg_layer_edge_mlp_max': (ctypes.c_int, [ctypes.c_void_p, c_f32p, c_f32p, c_f32p, c_i32p, c_i32p, c_i32p, c_i64,
+                                             c_i64, c_i64, c_f32p, c_i32, ctypes.c_void_p]),
+    'pg_layer_predictor': (ctypes.c_int, [ctypes.c_void_p, c_f32p, c_i64, c_f32p, c_f32p, c_f32p, ctypes.c_void_p]),
 }
+PG_LAYER_MLP, PG_LAYER_EDGE_POOL, PG_LAYER_EDGE_GNN, PG_LAYER_PREDICTOR = 0, 1, 2, 3
 PG_FLAG_TRUSTED_INDICES = 0x100
 
 _lib = None
@@ -260,3 +269,71 @@ def softmax_rows(logits):
     _check(lib.pg_softmax_rows(_ptr(logits, torch.float32, 'logits'), logits.shape[0], logits.shape[1],
                                _ptr(out, torch.float32, 'out'), _stream()))
     return out
+
+
+# ---------------------------------------------------------------------------------------------
+# prepared layers (weights packed once; the calls below launch compute kernels only)
+# ---------------------------------------------------------------------------------------------
+class PreparedLayer(object):
+    """Owner of one ``pg_layer`` handle.  Keeps the weight tensors alive: the C side stores their pointers."""
+
+    def __init__(self, kind, weights, biases, dims, precision=0):
+        lib = load()
+        n = len(weights)
+        self.kind = int(kind)
+        self.dims = [int(d) for d in dims]
+        self._keep = (list(weights), list(biases))
+        wp = (ctypes.c_void_p * n)(*[_ptr(w, torch.float32, 'weight').value for w in weights])
+        bp = (ctypes.c_void_p * n)(*[_ptr(b, torch.float32, 'bias').value for b in biases])
+        dm = (c_i32 * len(self.dims))(*self.dims)
+        handle = ctypes.c_void_p()
+        self._handle = None
+        _check(lib.pg_layer_create(self.kind, wp, bp, dm, n, int(precision), _stream(), ctypes.byref(handle)))
+        self._handle = handle
+
+    def __del__(self):
+        if getattr(self, '_handle', None) is not None and _lib is not None:
+            _lib.pg_layer_destroy(self._handle)
+            self._handle = None
+
+    # multi_layer_neural_network_fn / multi_layer_fc_fn (gnn.py:34-104)
+    def mlp(self, x, last_linear, residual=None):
+        m, k = x.shape
+        if k != self.dims[0]:
+            raise ValueError('fully_connected: input width %d != weight rows %d' % (k, self.dims[0]))
+        n = self.dims[-1]
+        if residual is not None and tuple(residual.shape) != (m, n):
+            raise ValueError('fully_connected: residual shape %s != output shape (%d, %d)'
+                             % (tuple(residual.shape), m, n))
+        out = torch.empty((m, n), dtype=torch.float32, device=x.device)
+        _check(load().pg_layer_mlp(self._handle, _ptr(x, torch.float32, 'x'), m, 1 if last_linear else 0,
+                                   _ptr(residual, torch.float32, 'residual'), _ptr(out, torch.float32, 'out'),
+                                   _stream()))
+        return out
+
+    # fused gather -> edge MLP -> segment max (gnn.py:256-277, 338-365)
+    def edge_mlp_max(self, features, xyz_src, xyz_dst, dst_index, src, dst, num_dst, trusted=False):
+        if features.shape[1] + 3 != self.dims[0]:
+            raise ValueError('edge layer: %d feature channels + 3 != first weight rows %d'
+                             % (features.shape[1], self.dims[0]))
+        out = torch.empty((int(num_dst), self.dims[-1]), dtype=torch.float32, device=features.device)
+        _check(load().pg_layer_edge_mlp_max(
+            self._handle, _ptr(features, torch.float32, 'features'), _ptr(xyz_src, torch.float32, 'xyz_src'),
+            _ptr(xyz_dst, torch.float32, 'xyz_dst'), _ptr(dst_index, torch.int32, 'dst_index'),
+            _ptr(src, torch.int32, 'src'), _ptr(dst, torch.int32, 'dst'), src.numel(), features.shape[0],
+            int(num_dst), _ptr(out, torch.float32, 'out'), PG_FLAG_TRUSTED_INDICES if trusted else 0, _stream()))
+        return out
+
+    # ClassAwarePredictor (gnn.py:133-163) + softmax (models.py:165-168)
+    def predictor(self, x):
+        d, h, c, box = self.dims
+        m = x.shape[0]
+        if x.shape[1] != d:
+            raise ValueError('predictor: input width %d != %d' % (x.shape[1], d))
+        logits = torch.empty((m, c), dtype=torch.float32, device=x.device)
+        probs = torch.empty((m, c), dtype=torch.float32, device=x.device)
+        boxes = torch.empty((m, c, box), dtype=torch.float32, device=x.device)
+        _check(load().pg_layer_predictor(self._handle, _ptr(x, torch.float32, 'x'), m,
+                                         _ptr(logits, torch.float32, 'logits'), _ptr(boxes, torch.float32, 'boxes'),
+                                         _ptr(probs, torch.float32, 'probs'), _stream()))
+        return logits, boxes, probs

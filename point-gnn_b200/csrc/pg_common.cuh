@@ -45,6 +45,7 @@ struct Temp {
   Temp() {}
   Temp(const Temp&) = delete;
   Temp& operator=(const Temp&) = delete;
+  Temp(Temp&& o) noexcept : ptr(o.ptr), stream(o.stream) { o.ptr = nullptr; }
   cudaError_t alloc(size_t bytes, cudaStream_t s) {
     stream = s;
     if (bytes == 0) bytes = 16;

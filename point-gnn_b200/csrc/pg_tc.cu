@@ -70,9 +70,7 @@ constexpr int kTileRows = 128;                               // rows (edges) per
 constexpr int kScratchStride = 36;                           // floats per scratch column: 32 rows + pad, 16 B aligned
 constexpr int kScratchFloats = 16 * kScratchStride;          // per epilogue warp: 16 columns x 32 rows
 
-enum { PROD_GNN = 0, PROD_ROWS = 1, PROD_POOL = 2 };
-constexpr int kPoolC1 = 32, kPoolC2 = 64, kPoolC3 = 128;   // point MLP widths the pooling producer is built for
-constexpr int kPoolWFloats = 4 * kPoolC1 + kPoolC1 + kPoolC1 * kPoolC2 + kPoolC2 + kPoolC2 * kPoolC3 + kPoolC3;
+enum { PROD_GNN = 0, PROD_ROWS = 1 };
 enum { EPI_SEGMAX = 0, EPI_STORE = 1 };
 
 struct TcParams {
@@ -88,15 +86,19 @@ struct TcParams {
   int64_t num_rows;       // edges (GNN) or matrix rows (ROWS)
   int64_t num_src, num_dst;
   const float* w1x;       // [3, kp] zero padded (GNN)
-  const float* pool_w;    // POOL: packed [W1 4x32 | b1 | W2 32x64 | b2 | W3 64x128 | b3] (fp32)
-  const float* pool_feat; // POOL: point features [num_src, 1]
   // GEMM shape
   const float* bias;      // [np] zero padded
   int kp, ks;             // padded K, k-steps (kp / 16)
   int n, np, n1, n2;      // real N, padded N, instruction split
-  const uint8_t* wimg;    // per rank: [hi part | lo part], each part_bytes
+  const uint8_t* wimg;    // per rank: [hi part | lo part], each part_bytes   (seg_gemm: [lo part | hi part of instruction 2])
   uint32_t part_bytes;
   uint32_t tmem_cols;
+  // seg_gemm_tc_kernel only
+  const uint32_t* wtm;    // per rank: W hi image for TENSOR MEMORY, [kp / 2 columns][128 lanes] packed BF16 pairs
+  uint32_t hi2_bytes;     // bytes of the hi part of instruction 2's rows (0 when n2 == 0)
+  uint32_t tm_w_col;      // TMEM column where the W hi image lives
+  uint32_t d2_stride;     // TMEM column distance between the two D2 buffers (0 = single buffered)
+  int nstages;            // depth of the A-stage ring
   // epilogue
   float* out;             // SEGMAX: [num_dst, n] pre-filled with -FLT_MAX;  STORE: [num_rows, ldo]
   int ldo;
@@ -127,7 +129,7 @@ __device__ __forceinline__ unsigned long long gtime() {
 // B operand rows are OUTPUT features (N), K-major.  Rank r of the pair holds rows
 // [r*N1/2, (r+1)*N1/2) of instruction 1 followed by [N1 + r*N2/2, ...) of instruction 2, as 8-row
 // groups g: core(g, kc) at g*sbo + kc*128, element (row%8)*16 + (k%8)*2.  hi / lo = BF16 split.
-__global__ void pack_w2_kernel(const float* __restrict__ w2, int k, int n, int kp, int n1, int n2,
+__global__ void pack_w2_kernel(const float* __restrict__ w2, int k, int n, int ld, int kp, int n1, int n2,
                                uint8_t* __restrict__ img, uint32_t part_bytes, uint32_t rank_stride) {
   const int rows_per_rank = (n1 + n2) / 2;
   const int total = 2 * rows_per_rank * kp;
@@ -140,13 +142,43 @@ __global__ void pack_w2_kernel(const float* __restrict__ w2, int k, int n, int k
     int feature;
     if (lr < n1 / 2) feature = rank * (n1 / 2) + lr;
     else feature = n1 + rank * (n2 / 2) + (lr - n1 / 2);
-    const float v = (feature < n && kk < k) ? w2[int64_t(kk) * n + feature] : 0.0f;
+    const float v = (feature < n && kk < k) ? w2[int64_t(kk) * ld + feature] : 0.0f;   // W is [k, n], row stride ld
     const __nv_bfloat16 hi = __float2bfloat16_rn(v);
     const __nv_bfloat16 lo = __float2bfloat16_rn(v - __bfloat162float(hi));
     const uint32_t off = uint32_t(lr / 8) * sbo + uint32_t(kk / 8) * 128u + uint32_t(lr % 8) * 16u + uint32_t(kk % 8) * 2u;
     uint8_t* base = img + size_t(rank) * rank_stride;
     *reinterpret_cast<__nv_bfloat16*>(base + off) = hi;
     *reinterpret_cast<__nv_bfloat16*>(base + part_bytes + off) = lo;
+  }
+}
+
+// Weight images of seg_gemm_tc_kernel.  Rank r owns output features [128 r, 128 r + 128) (transposed
+// instruction, M = features) and [256 + r n2/2, ...) (row-major instruction 2).  Per rank:
+//   shared-memory image  [lo part: all 128 + n2/2 rows][hi part: the n2/2 rows of instruction 2], K-major
+//                        core matrices as above (row group g at g * sbo);
+//   tensor-memory image  hi part of the 128 transposed rows as the MMA A operand from TMEM: lane = row,
+//                        32-bit column c = BF16 elements k = 2c (low half), 2c + 1; stored [kp/2][128 lanes].
+__global__ void pack_seg_kernel(const float* __restrict__ w2, int k, int n, int kp, int n2, uint8_t* __restrict__ img,
+                                uint32_t part_bytes, uint32_t rank_stride, __nv_bfloat16* __restrict__ tm_img) {
+  const int rows_per_rank = 128 + n2 / 2;
+  const int total = 2 * rows_per_rank * kp;
+  const uint32_t sbo = uint32_t(kp / 8) * 128u;
+  for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < total; i += gridDim.x * blockDim.x) {
+    const int rank = i / (rows_per_rank * kp);
+    const int rem = i - rank * rows_per_rank * kp;
+    const int lr = rem / kp;
+    const int kk = rem - lr * kp;
+    const int feature = lr < 128 ? rank * 128 + lr : 256 + rank * (n2 / 2) + (lr - 128);
+    const float v = (feature < n && kk < k) ? w2[int64_t(kk) * n + feature] : 0.0f;
+    const __nv_bfloat16 hi = __float2bfloat16_rn(v);
+    const __nv_bfloat16 lo = __float2bfloat16_rn(v - __bfloat162float(hi));
+    const uint32_t in_core = uint32_t(kk / 8) * 128u + uint32_t(lr % 8) * 16u + uint32_t(kk % 8) * 2u;
+    uint8_t* base = img + size_t(rank) * rank_stride;
+    *reinterpret_cast<__nv_bfloat16*>(base + uint32_t(lr / 8) * sbo + in_core) = lo;
+    if (lr >= 128)
+      *reinterpret_cast<__nv_bfloat16*>(base + part_bytes + uint32_t((lr - 128) / 8) * sbo + in_core) = hi;
+    else
+      tm_img[((size_t(rank) * (kp / 2) + kk / 2) * 128 + lr) * 2 + (kk & 1)] = hi;
   }
 }
 
@@ -178,7 +210,7 @@ __host__ __device__ inline size_t smem_layout(uint8_t* base, int kp, int np, uin
   auto take = [&](size_t bytes) { size_t o = off; off += (bytes + 15) & ~size_t(15); return o; };
   const size_t o_bres = take(2 * size_t(part_bytes));
   const size_t o_a = take(size_t(kStages) * kStageBytes);
-  const size_t o_w1x = take((prod == PROD_POOL ? size_t(kPoolWFloats) : size_t(3) * kp) * sizeof(float));
+  const size_t o_w1x = take(size_t(3) * kp * sizeof(float));
   const size_t o_scr = take(size_t(kEpiWarps) * kScratchFloats * sizeof(float));
   const size_t o_bar = take((2 * kStages + 5) * sizeof(uint64_t));
   const size_t o_tmem = take(16);
@@ -541,13 +573,10 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kThreads, 1) row_gem
   // ---- prologue ------------------------------------------------------------------------------
   if (kProd == PROD_GNN)
     for (int i = threadIdx.x; i < 3 * p.kp; i += kThreads) sm.w1x[i] = p.w1x[i];
-  if (kProd == PROD_POOL)
-    for (int i = threadIdx.x; i < kPoolWFloats; i += kThreads) sm.w1x[i] = p.pool_w[i];
   if (threadIdx.x == 0) {
     for (int i = 0; i < kStages; ++i) {
-      // arrivals per stage: every producer warp of both CTAs (POOL), or the four warps of the one
-      // producer group that owns the k-step, in both CTAs (GNN / ROWS)
-      mbar_init(&sm.bar_full[i], kProd == PROD_POOL ? 2 * kProdWarps : kProdWarps);
+      // arrivals per stage: the four warps of the one producer group that owns the k-step, in both CTAs
+      mbar_init(&sm.bar_full[i], kProdWarps);
       mbar_init(&sm.bar_empty[i], 1);
     }
     mbar_init(sm.bar_tmem_full, 1);
@@ -700,100 +729,7 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kThreads, 1) row_gem
     // =================================== producer warps =======================================
     cluster_sync();   // [sync A]
     const int pt = threadIdx.x - (kEpiWarps + 1) * 32;   // 0..255
-    if (kProd != PROD_POOL) {
-      gnn_rows_producer<kProd>(p, sm, pt, lane, rank, cluster_id, num_clusters);
-    } else {
-      const int r = pt & 127;                              // tile row
-      const int kc = pt >> 7;                              // which 8-wide K chunk of the k-step
-      const uint32_t a_off = uint32_t(r >> 3) * 256u + uint32_t(kc) * 128u + uint32_t(r & 7) * 16u;
-      uint32_t it = 0, stage = 0, phase = 0;
-      for (int64_t tile = cluster_id; tile < p.num_pair_tiles; tile += num_clusters) {
-        const int64_t row = tile * 256 + int64_t(rank) * kTileRows + r;
-        bool valid = row < p.num_rows;
-        int sidx = 0, didx = 0;
-        if (valid) {
-          sidx = p.src[row];
-          didx = p.dst[row];
-          if (sidx < 0 || sidx >= p.num_src || didx < 0 || didx >= p.num_dst) { *p.err = 1; valid = false; sidx = 0; didx = 0; }
-        }
-        const int64_t drow = p.dst_index ? int64_t(p.dst_index[didx]) : int64_t(didx);
-        const float rx = p.xyz_src[int64_t(sidx) * 3 + 0] - p.xyz_dst[drow * 3 + 0];
-        const float ry = p.xyz_src[int64_t(sidx) * 3 + 1] - p.xyz_dst[drow * 3 + 1];
-        const float rz = p.xyz_src[int64_t(sidx) * 3 + 2] - p.xyz_dst[drow * 3 + 2];
-        // hand one k-step (8 values of this thread's row) to the tensor core
-        auto publish = [&](const float (&h)[8]) {
-          uint4 hi, lo;
-          split_bf16x2(h[0], h[1], &hi.x, &lo.x);
-          split_bf16x2(h[2], h[3], &hi.y, &lo.y);
-          split_bf16x2(h[4], h[5], &hi.z, &lo.z);
-          split_bf16x2(h[6], h[7], &hi.w, &lo.w);
-          mbar_wait(&sm.bar_empty[stage], phase ^ 1u);
-          uint8_t* st = sm.a + stage * kStageBytes + a_off;
-          *reinterpret_cast<uint4*>(st) = hi;
-          *reinterpret_cast<uint4*>(st + kStageBytes / 2) = lo;
-          fence_proxy_async_smem();
-          __syncwarp();
-          if (lane == 0) mbar_arrive_cluster(&sm.bar_full[stage], 0);
-          ++it;
-          if (++stage == kStages) { stage = 0; phase ^= 1u; }
-        };
-        // per-edge point MLP 4 -> 32 -> 64 (registers), then 64 -> 128 eight outputs per k-step;
-        // weights are warp-uniform shared-memory broadcasts.  gnn.py:264-274 (layers 1-3 of 4).
-        const float* w1 = sm.w1x;
-        const float* b1 = w1 + 4 * kPoolC1;
-        const float* w2 = b1 + kPoolC1;
-        const float* b2 = w2 + kPoolC1 * kPoolC2;
-        const float* w3 = b2 + kPoolC2;
-        const float* b3 = w3 + kPoolC2 * kPoolC3;
-        const float f0 = p.pool_feat[sidx];
-        float h2[kPoolC2];
-#pragma unroll
-        for (int j = 0; j < kPoolC2; ++j) h2[j] = b2[j];
-#pragma unroll 4
-        for (int i = 0; i < kPoolC1; ++i) {
-          float t = b1[i];
-          t = fmaf(f0, w1[i], t);
-          t = fmaf(rx, w1[kPoolC1 + i], t);
-          t = fmaf(ry, w1[2 * kPoolC1 + i], t);
-          t = fmaf(rz, w1[3 * kPoolC1 + i], t);
-          t = fmaxf(t, 0.0f);
-          const float4* wr = reinterpret_cast<const float4*>(w2 + i * kPoolC2);
-#pragma unroll
-          for (int j4 = 0; j4 < kPoolC2 / 4; ++j4) {
-            const float4 q = wr[j4];
-            h2[4 * j4 + 0] = fmaf(t, q.x, h2[4 * j4 + 0]);
-            h2[4 * j4 + 1] = fmaf(t, q.y, h2[4 * j4 + 1]);
-            h2[4 * j4 + 2] = fmaf(t, q.z, h2[4 * j4 + 2]);
-            h2[4 * j4 + 3] = fmaf(t, q.w, h2[4 * j4 + 3]);
-          }
-        }
-#pragma unroll
-        for (int j = 0; j < kPoolC2; ++j) h2[j] = fmaxf(h2[j], 0.0f);
-        for (int s = 0; s < p.ks; ++s) {
-          const int k0 = s * 16 + kc * 8;
-          float acc[8];
-#pragma unroll
-          for (int j = 0; j < 8; ++j) acc[j] = b3[k0 + j];
-#pragma unroll
-          for (int i = 0; i < kPoolC2; ++i) {
-            const float4 q0 = *reinterpret_cast<const float4*>(w3 + i * kPoolC3 + k0);
-            const float4 q1 = *reinterpret_cast<const float4*>(w3 + i * kPoolC3 + k0 + 4);
-            acc[0] = fmaf(h2[i], q0.x, acc[0]);
-            acc[1] = fmaf(h2[i], q0.y, acc[1]);
-            acc[2] = fmaf(h2[i], q0.z, acc[2]);
-            acc[3] = fmaf(h2[i], q0.w, acc[3]);
-            acc[4] = fmaf(h2[i], q1.x, acc[4]);
-            acc[5] = fmaf(h2[i], q1.y, acc[5]);
-            acc[6] = fmaf(h2[i], q1.z, acc[6]);
-            acc[7] = fmaf(h2[i], q1.w, acc[7]);
-          }
-          float h[8];
-#pragma unroll
-          for (int j = 0; j < 8; ++j) h[j] = fmaxf(acc[j], 0.0f);   // rows past the end are dropped by the epilogue
-          publish(h);
-        }
-      }
-    }
+    gnn_rows_producer<kProd>(p, sm, pt, lane, rank, cluster_id, num_clusters);
   }
 
   // ---- teardown ------------------------------------------------------------------------------
@@ -951,7 +887,7 @@ __device__ __forceinline__ void segmax_d2_rowmajor(const TcParams& p, uint32_t t
 // rr+24 of its warp, so an LDG.128 covers 8 rows x 64 contiguous bytes (8 lines).  Per-row context
 // (relative coordinates, source vertex) is computed once per tile by the row's owner thread and
 // passed through a small shared-memory table that only the owning warp reads.
-constexpr int kSegStages = 4;
+constexpr int kSegMaxStages = 16;
 constexpr int kSegEpiWarps = 4;
 constexpr int kSegGroups = 3;        // producer groups of four warps; group g produces iterations g, g+3, ...
 // Warp roles, LOWEST priority first: the SM's issue arbiter prefers the highest warp id among the eligible
@@ -964,13 +900,13 @@ constexpr int kSegMmaWarp = kSegEpiWarp0 + kSegEpiWarps;   // warp 16
 constexpr int kSegThreads = (kSegEpiWarps + 1 + 4 * kSegGroups) * 32;   // 544
 
 struct SegSmem {
-  uint8_t* bres;
-  uint8_t* a;             // kSegStages stages
+  uint8_t* bres;          // resident weights: [lo part, all rows of this rank | hi part of instruction 2's rows]
+  uint8_t* a;             // nstages stages
   float* w1x;             // [3][kp]
   float4* ctx;            // [groups][128 rows] {rx, ry, rz, bits(src vertex)} of the tile being produced
   int* si_next;           // [groups][128 rows] src vertex of the row in the NEXT tile
-  uint64_t* bar_full;     // [kSegStages] (leader)
-  uint64_t* bar_empty;    // [kSegStages]
+  uint64_t* bar_full;     // [nstages] (leader)
+  uint64_t* bar_empty;    // [nstages]
   uint64_t* bar_tmem_full;
   uint64_t* bar_d1_empty;     // (leader) D1 of the previous tile has been drained
   uint64_t* bar_d2_empty;     // [2] (leader) D2 buffer b has been drained
@@ -978,15 +914,16 @@ struct SegSmem {
   uint32_t* tmem;
 };
 
-__host__ __device__ inline size_t seg_smem_layout(uint8_t* base, int kp, uint32_t part_bytes, SegSmem* m) {
+__host__ __device__ inline size_t seg_smem_layout(uint8_t* base, int kp, uint32_t part_bytes, uint32_t hi2_bytes,
+                                                  int nstages, SegSmem* m) {
   size_t off = 0;
   auto take = [&](size_t bytes) { size_t o = off; off += (bytes + 15) & ~size_t(15); return o; };
-  const size_t o_bres = take(2 * size_t(part_bytes));
-  const size_t o_a = take(size_t(kSegStages) * kStageBytes);
+  const size_t o_bres = take(size_t(part_bytes) + hi2_bytes);
+  const size_t o_a = take(size_t(nstages) * kStageBytes);
   const size_t o_w1x = take(size_t(3) * kp * sizeof(float));
   const size_t o_ctx = take(size_t(kSegGroups) * 128 * sizeof(float4));
   const size_t o_sin = take(size_t(kSegGroups) * 128 * sizeof(int));
-  const size_t o_bar = take((2 * kSegStages + 5) * sizeof(uint64_t));
+  const size_t o_bar = take((2 * size_t(nstages) + 5) * sizeof(uint64_t));
   const size_t o_tmem = take(16);
   if (m != nullptr) {
     m->bres = base + o_bres;
@@ -996,11 +933,11 @@ __host__ __device__ inline size_t seg_smem_layout(uint8_t* base, int kp, uint32_
     m->si_next = reinterpret_cast<int*>(base + o_sin);
     uint64_t* bars = reinterpret_cast<uint64_t*>(base + o_bar);
     m->bar_full = bars;
-    m->bar_empty = bars + kSegStages;
-    m->bar_tmem_full = bars + 2 * kSegStages;
-    m->bar_d1_empty = bars + 2 * kSegStages + 1;
-    m->bar_d2_empty = bars + 2 * kSegStages + 2;
-    m->bar_wres = bars + 2 * kSegStages + 4;
+    m->bar_empty = bars + nstages;
+    m->bar_tmem_full = bars + 2 * nstages;
+    m->bar_d1_empty = bars + 2 * nstages + 1;
+    m->bar_d2_empty = bars + 2 * nstages + 2;
+    m->bar_wres = bars + 2 * nstages + 4;
     m->tmem = reinterpret_cast<uint32_t*>(base + o_tmem);
   }
   return off;
@@ -1055,7 +992,8 @@ __device__ __forceinline__ void seg_producer(const TcParams& p, const SegSmem& s
 
   int j = 0;            // tile (local index) of the iteration to produce next
   int s = g;            // its k-step
-  uint32_t it = uint32_t(g);   // global pipeline iteration (stage = it % kSegStages)
+  uint32_t stage = uint32_t(g), phase = 0;   // ring position of the iteration to produce next
+  const uint32_t nst = uint32_t(p.nstages);
   int si_n, di_n;       // edge of row r in tile j + 1
   float nx[6] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
   {
@@ -1108,8 +1046,7 @@ __device__ __forceinline__ void seg_producer(const TcParams& p, const SegSmem& s
       split_bf16x2_trunc(v0, v1, &hi[i].x, &lo[i].x);
       split_bf16x2_trunc(v2, v3, &hi[i].y, &lo[i].y);
     }
-    const uint32_t stage = it & (kSegStages - 1), parity = (it / kSegStages) & 1u;
-    mbar_wait(&sm.bar_empty[stage], parity ^ 1u);
+    mbar_wait(&sm.bar_empty[stage], phase ^ 1u);
     uint8_t* st = sm.a + stage * kStageBytes + a_off0;
 #pragma unroll
     for (int i = 0; i < 4; ++i) {
@@ -1119,7 +1056,8 @@ __device__ __forceinline__ void seg_producer(const TcParams& p, const SegSmem& s
     fence_proxy_async_smem();
     __syncwarp();
     if (lane == 0) mbar_arrive_cluster(&sm.bar_full[stage], 0);
-    it += kSegGroups;
+    stage += kSegGroups;
+    if (stage >= nst) { stage -= nst; phase ^= 1u; }
     int j1 = j, j2;
     int s1 = s, s2;
     advance(j1, s1);
@@ -1158,7 +1096,7 @@ __device__ __forceinline__ void seg_producer(const TcParams& p, const SegSmem& s
 __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kSegThreads, 1) seg_gemm_tc_kernel(TcParams p) {
   extern __shared__ __align__(128) uint8_t smem_raw[];
   SegSmem sm;
-  seg_smem_layout(smem_raw, p.kp, p.part_bytes, &sm);
+  seg_smem_layout(smem_raw, p.kp, p.part_bytes, p.hi2_bytes, p.nstages, &sm);
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const uint32_t rank = cluster_ctarank();
@@ -1167,15 +1105,15 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kSegThreads, 1) seg_
   const int64_t tile0 = cluster_id;          // round-robin tile schedule (see seg_producer)
   const int64_t tstride = num_clusters;
   const int64_t tile_end = p.num_pair_tiles;
-  // D2 (output features 256 ..) is double buffered when two copies fit beside the 256 columns of D1, so
-  // the tensor core restarts as soon as D1 has been drained
+  // TMEM map: D1 [0, 256) | D2 buffer(s) at 256 (+ d2_stride) | W hi image at tm_w_col (kp / 2 columns)
   constexpr uint32_t kD2Col = 256;
-  const uint32_t d2_stride = (p.n2 > 0 && 256 + 2 * p.n2 <= 512) ? uint32_t(p.n2) : 0u;
+  const uint32_t d2_stride = p.d2_stride;
+  const int nst = p.nstages;
 
   // ---- prologue ------------------------------------------------------------------------------
   for (int i = threadIdx.x; i < 3 * p.kp; i += kSegThreads) sm.w1x[i] = p.w1x[i];
   if (threadIdx.x == 0) {
-    for (int i = 0; i < kSegStages; ++i) {
+    for (int i = 0; i < nst; ++i) {
       mbar_init(&sm.bar_full[i], 2 * 4);          // the four warps of one producer group, both CTAs
       mbar_init(&sm.bar_empty[i], 1);
     }
@@ -1199,14 +1137,14 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kSegThreads, 1) seg_
   if (warp == kSegMmaWarp) {
     // =================================== MMA warp =============================================
     if (lane == 0) {
-      mbar_arrive_expect_tx(sm.bar_wres, 2 * p.part_bytes);
-      const uint8_t* gsrc = p.wimg + size_t(rank) * 2 * p.part_bytes;
-      bulk_g2s(sm.bres, gsrc, p.part_bytes, sm.bar_wres);
-      bulk_g2s(sm.bres + p.part_bytes, gsrc + p.part_bytes, p.part_bytes, sm.bar_wres);
+      const uint32_t bytes = p.part_bytes + p.hi2_bytes;
+      mbar_arrive_expect_tx(sm.bar_wres, bytes);
+      bulk_g2s(sm.bres, p.wimg + size_t(rank) * bytes, bytes, sm.bar_wres);
       mbar_wait(sm.bar_wres, 0);
     }
     __syncwarp();
-    cluster_sync();   // [sync A]
+    cluster_sync();   // [sync A] both CTAs' smem weights are resident and both W hi images sit in tensor memory
+    tc_fence_after();
     if (rank == 0) {
       // The whole warp runs this loop converged; elect_one() predicates the tcgen05 instructions only.
       const uint32_t tmem_u = __shfl_sync(0xffffffffu, tmem, 0);
@@ -1214,11 +1152,15 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kSegThreads, 1) seg_
       const uint32_t idesc2 = make_idesc_bf16(256, p.n2 > 0 ? p.n2 : 16);      // M = edges, N = features
       const uint32_t sbo_b = uint32_t(p.kp / 8) * 128u;
       const uint64_t h_hi0 = make_smem_desc(smem_u32(sm.a), 128, 256);
-      const uint64_t w_hi0 = make_smem_desc(smem_u32(sm.bres), 128, sbo_b);
-      const uint64_t w_lo0 = make_smem_desc(smem_u32(sm.bres) + p.part_bytes, 128, sbo_b);
-      const uint64_t w2_off = uint64_t((16u * sbo_b) >> 4);   // rows 128.. of this rank's image = features 256..
+      const uint64_t w_lo0 = make_smem_desc(smem_u32(sm.bres), 128, sbo_b);
+      const uint64_t w_hi2 = make_smem_desc(smem_u32(sm.bres) + p.part_bytes, 128, sbo_b);   // instruction 2's rows, hi
+      const uint64_t w2_off = uint64_t((16u * sbo_b) >> 4);   // rows 128.. of the lo part = features 256.. (lo)
+      const uint32_t w_tm0 = tmem_u + p.tm_w_col;
       const bool has2 = p.n2 > 0;
-      uint32_t tile_iter = 0, it = 0;
+      uint32_t tile_iter = 0, stage = 0, phase = 0;
+#ifdef PG_LAB
+      uint32_t it = 0;
+#endif
       for (int64_t tile = tile0; tile < tile_end; tile += tstride, ++tile_iter) {
         const uint32_t buf = d2_stride ? (tile_iter & 1u) : 0u;
         const uint32_t d1 = tmem_u, d2 = tmem_u + kD2Col + buf * d2_stride;
@@ -1230,28 +1172,34 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kSegThreads, 1) seg_
         }
         tc_fence_after();
         uint64_t kb = 0;
-        for (int s = 0; s < p.ks; ++s, kb += 16, ++it) {
-          const uint32_t stage = it & (kSegStages - 1);
+        uint32_t w_tm = w_tm0;          // 8 TMEM columns (16 BF16 values per lane) per k-step
+        for (int s = 0; s < p.ks; ++s, kb += 16, w_tm += 8) {
           if (lane == 0) PG_TRACE(0, it, 0);
-          mbar_wait(&sm.bar_full[stage], (it / kSegStages) & 1u);
+          mbar_wait(&sm.bar_full[stage], phase);
           if (lane == 0) PG_TRACE(0, it, 1);
           tc_fence_after();
           const uint64_t h_hi = h_hi0 + uint64_t(stage * (kStageBytes >> 4));
           const uint64_t h_lo = h_hi + uint64_t((kStageBytes / 2) >> 4);
-          const uint64_t w_hi = w_hi0 + kb, w_lo = w_lo0 + kb;
+          const uint64_t w_lo = w_lo0 + kb;
           if (elect_one()) {
-            mma_bf16<2>(d1, w_hi, h_hi, idesc1, s > 0);
-            mma_bf16<2>(d1, w_hi, h_lo, idesc1, true);
+            // D1[feature, edge] += W^T x h^T as  W_hi h_hi + W_hi h_lo + W_lo h_hi;  W_hi is read from tensor
+            // memory (no shared-memory operand fetch, and its 90 KB of shared memory became ring stages)
+            mma_bf16_ts<2>(d1, w_tm, h_hi, idesc1, s > 0);
+            mma_bf16_ts<2>(d1, w_tm, h_lo, idesc1, true);
             mma_bf16<2>(d1, w_lo, h_hi, idesc1, true);
             if (has2) {
-              mma_bf16<2>(d2, h_hi, w_hi + w2_off, idesc2, s > 0);
-              mma_bf16<2>(d2, h_lo, w_hi + w2_off, idesc2, true);
+              mma_bf16<2>(d2, h_hi, w_hi2 + kb, idesc2, s > 0);
+              mma_bf16<2>(d2, h_lo, w_hi2 + kb, idesc2, true);
               mma_bf16<2>(d2, h_hi, w_lo + w2_off, idesc2, true);
             }
             mma_commit_2cta(&sm.bar_empty[stage], 0x3);
           }
           __syncwarp();
           if (lane == 0) PG_TRACE(0, it, 2);
+#ifdef PG_LAB
+          ++it;
+#endif
+          if (++stage == uint32_t(nst)) { stage = 0; phase ^= 1u; }
         }
         if (elect_one()) mma_commit_2cta(sm.bar_tmem_full, 0x3);
         __syncwarp();
@@ -1260,8 +1208,22 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kSegThreads, 1) seg_
     __syncwarp();
   } else if (warp >= kSegEpiWarp0) {
     // =================================== epilogue warps =======================================
-    cluster_sync();   // [sync A]
     const int quarter = warp & 3;
+    {
+      // W hi -> tensor memory, once: lane (quarter, lane) = feature row rank * 128 + 32 quarter + lane of the
+      // transposed GEMM's A operand, 8 columns (one k-step) per store
+      const uint32_t* img = p.wtm + size_t(rank) * size_t(p.kp / 2) * 128u + uint32_t(quarter * 32 + lane);
+      const uint32_t taddr = tmem + (uint32_t(quarter * 32) << 16) + p.tm_w_col;
+      for (int c0 = 0; c0 < p.kp / 2; c0 += 8) {
+        uint32_t v[8];
+#pragma unroll
+        for (int jj = 0; jj < 8; ++jj) v[jj] = __ldg(img + size_t(c0 + jj) * 128u);
+        tmem_st8(taddr + uint32_t(c0), v);
+      }
+      tmem_st_wait();
+      tc_fence_before();
+    }
+    cluster_sync();   // [sync A]
     uint32_t tile_iter = 0;
     for (int64_t tile = tile0; tile < tile_end; tile += tstride, ++tile_iter) {
       const uint32_t buf = d2_stride ? (tile_iter & 1u) : 0u;
@@ -1673,29 +1635,67 @@ TcShape tc_shape(int k, int n) {
   return t;
 }
 
+// =================================================================================================
+// Prepared layers.  Everything that depends only on the WEIGHTS is done once, when a layer is prepared:
+// the BF16 hi / lo operand images in the UMMA core-matrix layout (and, for the fused GNN edge kernel, the
+// tensor-memory image of W hi), padded biases, the hoisted first-layer matrices.  A forward pass then
+// launches compute kernels only.  The per-call entry points (pg_fully_connected, pg_edge_mlp_max) prepare
+// into stream-ordered temporaries and apply once; pg_layer_* keeps the prepared state in a handle.
+// =================================================================================================
+
+// ---- one fully-connected layer -----------------------------------------------------------------
+struct PreparedFc {
+  int k = 0, n = 0;            // logical GEMM shape [k, n]
+  int n_src = 0, ld_src = 0;   // the caller's matrix holds n_src <= n columns (the rest are zero), row stride ld_src
+  const float* w = nullptr;    // caller's fp32 tensors (FFMA path; must outlive the handle)
+  const float* bias = nullptr;
+  bool tc = false;
+  TcShape t{};
+  Temp img, bias_pad;
+};
+
+int prepare_fc(PreparedFc& f, const float* w, int ld_src, const float* bias, int k, int n_src, int n, bool want_tc,
+               cudaStream_t s) {
+  f.k = k;
+  f.n = n;
+  f.n_src = n_src;
+  f.ld_src = ld_src;
+  f.w = w;
+  f.bias = bias;
+  f.t = tc_shape(k, n);
+  // narrow / shallow layers (N < 8, K < 64: the 64->3, 64->4, 64->7 heads) stay on the fp32 FFMA kernel
+  f.tc = want_tc && f.t.ok && (k & 3) == 0;
+  if (!f.tc) return PG_OK;
+  PG_CUDA_OK(f.bias_pad.alloc(sizeof(float) * f.t.np, s));
+  pad_rows_kernel<<<2, 256, 0, s>>>(bias, 1, n_src, f.t.np, f.bias_pad.as<float>());
+  PG_LAUNCH_CHECK();
+  PG_CUDA_OK(f.img.alloc(size_t(4) * f.t.part, s));
+  pack_w2_kernel<<<std::min(num_sms(), 64), 256, 0, s>>>(w, k, n_src, ld_src, f.t.kp, f.t.n1, f.t.n2, f.img.as<uint8_t>(),
+                                                         f.t.part, 2 * f.t.part);
+  PG_LAUNCH_CHECK();
+  return PG_OK;
+}
+
 template <int kProd, int kEpi>
-int launch_row_gemm(TcParams& p, const TcShape& t, const float* w, int k, int n, const float* bias, Temp& t_img,
-                    Temp& t_bias, cudaStream_t s) {
-  PG_CUDA_OK(t_bias.alloc(sizeof(float) * t.np, s));
-  pad_rows_kernel<<<2, 256, 0, s>>>(bias, 1, n, t.np, t_bias.as<float>());
-  PG_LAUNCH_CHECK();
-  PG_CUDA_OK(t_img.alloc(size_t(4) * t.part, s));
-  pack_w2_kernel<<<std::min(num_sms(), 64), 256, 0, s>>>(w, k, n, t.kp, t.n1, t.n2, t_img.as<uint8_t>(), t.part, 2 * t.part);
-  PG_LAUNCH_CHECK();
-  p.bias = t_bias.as<float>();
+int launch_row_gemm(TcParams& p, const TcShape& t, int n, const uint8_t* img, const float* bias_pad, cudaStream_t s) {
+  p.bias = bias_pad;
   p.kp = t.kp;
   p.ks = t.kp / 16;
   p.n = n;
   p.np = t.np;
   p.n1 = t.n1;
   p.n2 = t.n2;
-  p.wimg = t_img.as<uint8_t>();
+  p.wimg = img;
   p.part_bytes = t.part;
   p.tmem_cols = t.tmem_cols;
   p.num_pair_tiles = ceil_div(p.num_rows, 2 * kTileRows);
   const size_t smem = tc_smem_bytes(t.kp, t.np, kProd);
   PG_REQUIRE(smem <= 227 * 1024, "tcgen05 kernel needs %zu B of shared memory", smem);
-  PG_CUDA_OK(cudaFuncSetAttribute(row_gemm_tc_kernel<kProd, kEpi>, cudaFuncAttributeMaxDynamicSharedMemorySize, int(smem)));
+  static bool attr_done = false;
+  if (!attr_done) {
+    PG_CUDA_OK(cudaFuncSetAttribute(row_gemm_tc_kernel<kProd, kEpi>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
+    attr_done = true;
+  }
   const int clusters = int(std::min<int64_t>(p.num_pair_tiles, num_sms() / 2));
   row_gemm_tc_kernel<kProd, kEpi><<<2 * clusters, kThreads, smem, s>>>(p);
   PG_LAUNCH_CHECK();
@@ -1703,83 +1703,146 @@ int launch_row_gemm(TcParams& p, const TcShape& t, const float* w, int k, int n,
   return PG_OK;
 }
 
-// Launch seg_gemm_tc_kernel (transposed GNN edge GEMM + in-register segment max).  `p` carries the
-// producer fields; W is [k, n] row-major.  Requires k >= 64 (more k-steps than stages) and n <= 512.
-bool seg_gemm_fits(int k, int n) {
-  const int kp = (k + 15) / 16 * 16, np = (n + 15) / 16 * 16;
-  const int n2 = std::max(0, np - 256);
-  const uint32_t part = uint32_t((256 + n2) / 16) * uint32_t(kp / 8) * 128u;
-  // ks >= 12: the producers publish next-tile source indices half a tile ahead of their first use
-  return pg_tc_available() && n >= 8 && n2 <= 256 && kp / 16 >= 12 && seg_smem_layout(nullptr, kp, part, nullptr) <= 227 * 1024;
+// out [m, ldo]: columns [0, n) = act(x @ W + b) (+ residual [m, n]); ldo >= n
+int apply_fc(const PreparedFc& f, const float* x, int64_t m, int act, const float* residual, float* out, int ldo,
+             cudaStream_t s) {
+  if (m == 0) return PG_OK;
+  if (!f.tc) {
+    PG_REQUIRE(f.ld_src == f.n_src, "FFMA dense layer needs a contiguous weight matrix");
+    PG_REQUIRE(f.n == f.n_src || ldo == f.n, "FFMA dense layer: padded width %d needs ldo == n", f.n);
+    return fc_fp32_launch(x, m, f.k, f.w, f.bias, f.n_src, act, residual, out, ldo, s);
+  }
+  TcParams p{};
+  p.P = x;
+  p.ldp = f.k;
+  p.k_real = f.k;
+  p.num_rows = m;
+  p.out = out;
+  p.ldo = ldo;
+  p.act = act;
+  p.residual = residual;
+  return launch_row_gemm<PROD_ROWS, EPI_STORE>(p, f.t, f.n, f.img.as<uint8_t>(), f.bias_pad.as<float>(), s);
 }
 
-int launch_seg_gemm(TcParams& p, const float* w, int k, int n, const float* bias, Temp& t_img, Temp& t_bias,
-                    cudaStream_t s) {
-  const int kp = (k + 15) / 16 * 16, np = (n + 15) / 16 * 16;
-  const int n2 = std::max(0, np - 256);
-  const uint32_t part = uint32_t((256 + n2) / 16) * uint32_t(kp / 8) * 128u;
-  PG_CUDA_OK(t_bias.alloc(sizeof(float) * (256 + n2), s));
-  pad_rows_kernel<<<2, 256, 0, s>>>(bias, 1, n, 256 + n2, t_bias.as<float>());
-  PG_LAUNCH_CHECK();
-  PG_CUDA_OK(t_img.alloc(size_t(4) * part, s));
-  pack_w2_kernel<<<std::min(num_sms(), 64), 256, 0, s>>>(w, k, n, kp, 256, n2, t_img.as<uint8_t>(), part, 2 * part);
-  PG_LAUNCH_CHECK();
-  p.bias = t_bias.as<float>();
-  p.kp = kp;
-  p.ks = kp / 16;
-  p.n = n;
-  p.np = 256 + n2;
-  p.n1 = 256;
-  p.n2 = n2;
-  p.wimg = t_img.as<uint8_t>();
-  p.part_bytes = part;
-  p.tmem_cols = n2 > 0 ? 512 : 256;
-  p.num_pair_tiles = ceil_div(p.num_rows, 2 * kTileRows);
-  PG_REQUIRE(p.num_src * int64_t(p.ldp) < (int64_t(1) << 31), "vertex table too large for 32-bit element offsets");
-  const size_t smem = seg_smem_layout(nullptr, kp, part, nullptr);
-  PG_REQUIRE(smem <= 227 * 1024, "tcgen05 kernel needs %zu B of shared memory", smem);
-  PG_CUDA_OK(cudaFuncSetAttribute(seg_gemm_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, int(smem)));
-  const int clusters = int(std::min<int64_t>(p.num_pair_tiles, num_sms() / 2));
-#ifdef PG_LAB
-  const char* trace_path = getenv("PG_TC_TRACE");           // lab build only: dump the in-kernel trace
-#else
-  const char* trace_path = nullptr;
-#endif
-  Temp t_trace;
-  const size_t trace_words = size_t(8) * 128 * 3;
-  if (trace_path != nullptr) {
-    PG_CUDA_OK(t_trace.alloc(trace_words * 8, s));
-    PG_CUDA_OK(cudaMemsetAsync(t_trace.ptr, 0, trace_words * 8, s));
-    p.trace = t_trace.as<unsigned long long>();
+// ---- fused edge layers ------------------------------------------------------------------------
+enum { EDGE_FP32 = 0, EDGE_SEG = 1, EDGE_ROWS = 2, EDGE_CHAIN = 3 };
+
+struct SegShape {
+  int kp, np, n2, nstages;
+  uint32_t part, hi2, tm_w_col, d2_stride;
+  size_t smem;
+  bool ok;
+};
+
+// seg_gemm_tc_kernel: k-steps >= 12 (the producers publish next-tile source indices half a tile ahead of their
+// first use), N <= 512, and D1 (256) + D2 (n2, twice if it fits) + the W hi image (kp / 2) within 512 TMEM columns
+SegShape seg_shape(int k, int n) {
+  SegShape g{};
+  g.kp = (k + 15) / 16 * 16;
+  g.np = (n + 15) / 16 * 16;
+  g.n2 = std::max(0, g.np - 256);
+  g.part = uint32_t((256 + g.n2) / 16) * uint32_t(g.kp / 8) * 128u;   // lo part: all rows of one rank
+  g.hi2 = uint32_t(g.n2 / 16) * uint32_t(g.kp / 8) * 128u;            // hi part: instruction-2 rows only
+  const int w_cols = g.kp / 2;
+  if (g.n2 > 0 && 256 + 2 * g.n2 + w_cols <= 512) g.d2_stride = uint32_t(g.n2);
+  g.tm_w_col = 256u + (g.d2_stride ? 2u : 1u) * uint32_t(g.n2);
+  const bool tmem_ok = g.tm_w_col + uint32_t(w_cols) <= 512u;
+  g.nstages = 0;
+  for (int st = kSegMaxStages; st >= 4; --st)
+    if (seg_smem_layout(nullptr, g.kp, g.part, g.hi2, st, nullptr) <= 227 * 1024) { g.nstages = st; break; }
+  g.smem = g.nstages ? seg_smem_layout(nullptr, g.kp, g.part, g.hi2, g.nstages, nullptr) : 0;
+  g.ok = pg_tc_available() && n >= 8 && g.n2 <= 256 && g.kp / 16 >= 12 && tmem_ok && g.nstages >= 4;
+  return g;
+}
+
+struct PreparedEdge {
+  int mode = 0, c_in = 0, num_layers = 0, path = EDGE_FP32;
+  std::vector<int32_t> dims;
+  std::vector<const float*> w, b;     // caller's tensors (must outlive the handle)
+  // GNN (EDGE_SEG / EDGE_ROWS)
+  PreparedFc p_fc;                    // hoisted first layer: P = F @ W1[:C] + b1, zero padded to kp columns
+  Temp w1x;                           // [3, kp] = W1[C:], zero padded
+  SegShape g{};
+  TcShape t{};
+  Temp img, tm_img, bias_pad;
+  // POOL (EDGE_CHAIN)
+  ChainParams cp{};
+  size_t chain_smem = 0;
+  Temp c_first, c_img, c_mid, c_bias;
+};
+
+int prepare_chain(PreparedEdge& e, cudaStream_t s, bool* ok);
+
+int prepare_edge(PreparedEdge& e, int mode, int c_in, const float* const* weights, const float* const* biases,
+                 const int32_t* dims, int num_layers, bool want_tc, cudaStream_t s) {
+  PG_REQUIRE(num_layers >= 1 && num_layers <= 8, "edge MLP depth %d not in [1, 8]", num_layers);
+  PG_REQUIRE(dims[0] == c_in + 3, "dims[0]=%d must equal feature channels + 3 = %d", dims[0], c_in + 3);
+  e.mode = mode;
+  e.c_in = c_in;
+  e.num_layers = num_layers;
+  e.dims.assign(dims, dims + num_layers + 1);
+  e.w.assign(weights, weights + num_layers);
+  e.b.assign(biases, biases + num_layers);
+  for (int l = 0; l < num_layers; ++l) PG_REQUIRE(weights[l] && biases[l], "null weight/bias for layer %d", l);
+  e.path = EDGE_FP32;
+  if (!want_tc || !pg_tc_available()) return PG_OK;
+  if (mode == PG_EDGE_POOL) {
+    bool ok = false;
+    if (c_in == 1)
+      if (int rc = prepare_chain(e, s, &ok)) return rc;
+    if (ok) e.path = EDGE_CHAIN;
+    return PG_OK;
   }
-  seg_gemm_tc_kernel<<<2 * clusters, kSegThreads, smem, s>>>(p);
-  PG_LAUNCH_CHECK();
-  if (trace_path != nullptr) {
-    std::vector<unsigned long long> h(trace_words);
-    PG_CUDA_OK(cudaMemcpyAsync(h.data(), t_trace.ptr, trace_words * 8, cudaMemcpyDeviceToHost, s));
-    PG_CUDA_OK(cudaStreamSynchronize(s));
-    if (FILE* f = fopen(trace_path, "w")) {
-      for (size_t i = 0; i < trace_words; i += 3)
-        fprintf(f, "%zu %zu %llu %llu %llu\n", i / 3 / 128, (i / 3) % 128, h[i], h[i + 1], h[i + 2]);
-      fclose(f);
-    }
+  if (num_layers != 2) return PG_OK;
+  const int d1 = dims[1], n = dims[2];
+  e.g = seg_shape(d1, n);
+  e.t = tc_shape(d1, n);
+  if (!e.g.ok && !e.t.ok) return PG_OK;
+  const int kp = e.g.ok ? e.g.kp : e.t.kp;
+  // hoisted first layer on the tensor cores too: logical N = kp, the pad columns get zero weights and bias
+  if (int rc = prepare_fc(e.p_fc, weights[0], d1, biases[0], c_in, d1, kp, true, s)) return rc;
+  if (!e.p_fc.tc) {   // FFMA fallback writes the zero padding itself (ldo = kp)
+    e.p_fc.n = d1;
+    PG_REQUIRE(kp <= (d1 + 63) / 64 * 64, "hoisted layer: padded width %d too far from %d", kp, d1);
   }
-  g_tc_launches[0].fetch_add(1, std::memory_order_relaxed);
+  PG_CUDA_OK(e.w1x.alloc(sizeof(float) * 3 * kp, s));
+  pad_rows_kernel<<<4, 256, 0, s>>>(weights[0] + int64_t(c_in) * d1, 3, d1, kp, e.w1x.as<float>());
+  PG_LAUNCH_CHECK();
+  if (e.g.ok) {
+    const SegShape& g = e.g;
+    PG_CUDA_OK(e.bias_pad.alloc(sizeof(float) * (256 + g.n2), s));
+    pad_rows_kernel<<<2, 256, 0, s>>>(biases[1], 1, n, 256 + g.n2, e.bias_pad.as<float>());
+    PG_LAUNCH_CHECK();
+    PG_CUDA_OK(e.img.alloc(size_t(2) * (g.part + g.hi2), s));
+    PG_CUDA_OK(e.tm_img.alloc(size_t(2) * (g.kp / 2) * 128 * sizeof(uint32_t), s));
+    pack_seg_kernel<<<std::min(num_sms(), 64), 256, 0, s>>>(weights[1], d1, n, g.kp, g.n2, e.img.as<uint8_t>(), g.part,
+                                                            g.part + g.hi2, e.tm_img.as<__nv_bfloat16>());
+    PG_LAUNCH_CHECK();
+    e.path = EDGE_SEG;
+  } else {
+    PG_CUDA_OK(e.bias_pad.alloc(sizeof(float) * e.t.np, s));
+    pad_rows_kernel<<<2, 256, 0, s>>>(biases[1], 1, n, e.t.np, e.bias_pad.as<float>());
+    PG_LAUNCH_CHECK();
+    PG_CUDA_OK(e.img.alloc(size_t(4) * e.t.part, s));
+    pack_w2_kernel<<<std::min(num_sms(), 64), 256, 0, s>>>(weights[1], d1, n, n, e.t.kp, e.t.n1, e.t.n2, e.img.as<uint8_t>(),
+                                                           e.t.part, 2 * e.t.part);
+    PG_LAUNCH_CHECK();
+    e.path = EDGE_ROWS;
+  }
   return PG_OK;
 }
 
-// PointSetPooling's per-edge MLP + segment max on the chain kernel.  Returns PG_OK with *handled = false
-// when the layer shapes do not fit it (the caller then falls back to the other paths).
-int pool_chain_launch(const float* features, const float* xyz_src, const float* xyz_dst, const int32_t* dst_index,
-                      const int32_t* src, const int32_t* dst, int64_t num_edges, int64_t num_src, int64_t num_dst,
-                      const float* const* weights, const float* const* biases, const int32_t* dims, int num_layers,
-                      float* out, cudaStream_t s, bool* handled) {
-  *handled = false;
+// PointSetPooling's per-edge MLP + segment max on the chain kernel: shapes, images, parameter block.
+int prepare_chain(PreparedEdge& e, cudaStream_t s, bool* ok) {
+  *ok = false;
+  const int num_layers = e.num_layers;
+  const int32_t* dims = e.dims.data();
   const int P = num_layers - 1;
-  if (!pg_tc_available() || P < 1 || P > kChainMaxPhases || dims[0] != 4 || num_edges < 1) return PG_OK;
+  if (P < 1 || P > kChainMaxPhases || dims[0] != 4) return PG_OK;
   const int k0 = dims[1];
   if (k0 % 16 != 0 || k0 > kChainMaxK0) return PG_OK;
-  ChainParams cp{};
+  ChainParams& cp = e.cp;
+  cp = ChainParams{};
   uint32_t d_col = 0, b_off = 0, it_off = 0, bias_off = 0;
   for (int ph = 0; ph < P; ++ph) {
     const int k = dims[ph + 1], n = dims[ph + 2];
@@ -1809,130 +1872,68 @@ int pool_chain_launch(const float* features, const float* xyz_src, const float* 
   cp.wimg_rank_bytes = b_off;
   cp.mid_bias_floats = int(bias_off);
   cp.k0 = k0;
-  const size_t smem = chain_smem_layout(nullptr, cp.wimg_rank_bytes, k0, cp.mid_bias_floats, nullptr);
-  if (smem > 227 * 1024) return PG_OK;
-  *handled = true;
+  e.chain_smem = chain_smem_layout(nullptr, cp.wimg_rank_bytes, k0, cp.mid_bias_floats, nullptr);
+  if (e.chain_smem > 227 * 1024) return PG_OK;
+  *ok = true;
 
   const int n = dims[num_layers], np_last = cp.ph[P - 1].n1 + cp.ph[P - 1].n2;
-  Temp t_first, t_img, t_mid, t_bias, t_err;
-  PG_CUDA_OK(t_first.alloc(sizeof(float) * 5 * k0, s));
-  PG_CUDA_OK(cudaMemcpyAsync(t_first.ptr, weights[0], sizeof(float) * 4 * k0, cudaMemcpyDeviceToDevice, s));
-  PG_CUDA_OK(cudaMemcpyAsync(t_first.as<float>() + 4 * k0, biases[0], sizeof(float) * k0, cudaMemcpyDeviceToDevice, s));
-  PG_CUDA_OK(t_img.alloc(size_t(2) * cp.wimg_rank_bytes, s));
-  PG_CUDA_OK(t_mid.alloc(sizeof(float) * std::max(cp.mid_bias_floats, 4), s));
+  PG_CUDA_OK(e.c_first.alloc(sizeof(float) * 5 * k0, s));
+  PG_CUDA_OK(cudaMemcpyAsync(e.c_first.ptr, e.w[0], sizeof(float) * 4 * k0, cudaMemcpyDeviceToDevice, s));
+  PG_CUDA_OK(cudaMemcpyAsync(e.c_first.as<float>() + 4 * k0, e.b[0], sizeof(float) * k0, cudaMemcpyDeviceToDevice, s));
+  PG_CUDA_OK(e.c_img.alloc(size_t(2) * cp.wimg_rank_bytes, s));
+  PG_CUDA_OK(e.c_mid.alloc(sizeof(float) * std::max(cp.mid_bias_floats, 4), s));
   for (int ph = 0; ph < P; ++ph) {
     const ChainPhase& c = cp.ph[ph];
-    pack_w2_kernel<<<std::min(num_sms(), 64), 256, 0, s>>>(weights[ph + 1], dims[ph + 1], dims[ph + 2], dims[ph + 1], c.n1,
-                                                           c.n2, t_img.as<uint8_t>() + c.b_off, c.part_bytes,
+    pack_w2_kernel<<<std::min(num_sms(), 64), 256, 0, s>>>(e.w[ph + 1], dims[ph + 1], dims[ph + 2], dims[ph + 2], dims[ph + 1],
+                                                           c.n1, c.n2, e.c_img.as<uint8_t>() + c.b_off, c.part_bytes,
                                                            cp.wimg_rank_bytes);
     PG_LAUNCH_CHECK();
     if (ph + 1 < P) {
-      pad_rows_kernel<<<2, 256, 0, s>>>(biases[ph + 1], 1, dims[ph + 2], c.n1 + c.n2, t_mid.as<float>() + c.bias_off);
+      pad_rows_kernel<<<2, 256, 0, s>>>(e.b[ph + 1], 1, dims[ph + 2], c.n1 + c.n2, e.c_mid.as<float>() + c.bias_off);
       PG_LAUNCH_CHECK();
     }
   }
-  PG_CUDA_OK(t_bias.alloc(sizeof(float) * np_last, s));
-  pad_rows_kernel<<<2, 256, 0, s>>>(biases[num_layers - 1], 1, n, np_last, t_bias.as<float>());
+  PG_CUDA_OK(e.c_bias.alloc(sizeof(float) * np_last, s));
+  pad_rows_kernel<<<2, 256, 0, s>>>(e.b[num_layers - 1], 1, n, np_last, e.c_bias.as<float>());
   PG_LAUNCH_CHECK();
-  PG_CUDA_OK(t_err.alloc(sizeof(int), s));
-  PG_CUDA_OK(cudaMemsetAsync(t_err.ptr, 0, sizeof(int), s));
-  if (int rc = fill_async(out, num_dst * n, -FLT_MAX, s)) return rc;
+  cp.first = e.c_first.as<float>();
+  cp.mid_bias = e.c_mid.as<float>();
+  cp.wimg = e.c_img.as<uint8_t>();
+  cp.seg.bias = e.c_bias.as<float>();
+  cp.seg.n = n;
+  cp.seg.np = np_last;
+  cp.seg.n1 = cp.ph[P - 1].n1;
+  cp.seg.n2 = cp.ph[P - 1].n2;
+  return PG_OK;
+}
 
-  cp.feat = features;
-  cp.first = t_first.as<float>();
-  cp.mid_bias = t_mid.as<float>();
-  cp.wimg = t_img.as<uint8_t>();
-  TcParams& p = cp.seg;
-  p.xyz_src = xyz_src;
-  p.xyz_dst = xyz_dst;
-  p.dst_index = dst_index;
-  p.src = src;
-  p.dst = dst;
-  p.num_rows = num_edges;
-  p.num_src = num_src;
-  p.num_dst = num_dst;
-  p.bias = t_bias.as<float>();
-  p.n = n;
-  p.np = np_last;
-  p.n1 = cp.ph[P - 1].n1;
-  p.n2 = cp.ph[P - 1].n2;
-  p.out = out;
-  p.err = t_err.as<int>();
-  p.num_pair_tiles = ceil_div(num_edges, 2 * kTileRows);
-  PG_CUDA_OK(cudaFuncSetAttribute(mlp_chain_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, int(smem)));
-  const int clusters = int(std::min<int64_t>(p.num_pair_tiles, num_sms() / 2));
-  mlp_chain_tc_kernel<<<2 * clusters, kChainThreads, smem, s>>>(cp);
-  PG_LAUNCH_CHECK();
-  g_tc_launches[0].fetch_add(1, std::memory_order_relaxed);
+// read the range-error word back unless the caller vouched for the indices (PG_FLAG_TRUSTED_INDICES)
+int finish_index_check(const Temp& t_err, int64_t num_src, int64_t num_dst, cudaStream_t s) {
   int h = 0;
-  if (!trusted_indices()) {   // PG_FLAG_TRUSTED_INDICES: no read-back, no synchronisation
+  if (!trusted_indices()) {
     PG_CUDA_OK(cudaMemcpyAsync(&h, t_err.ptr, sizeof(int), cudaMemcpyDeviceToHost, s));
     PG_CUDA_OK(cudaStreamSynchronize(s));
   }
-  PG_REQUIRE(h == 0, "set index out of range (point in [0,%lld), keypoint in [0,%lld))", (long long)num_src,
+  PG_REQUIRE(h == 0, "edge index out of range (src in [0,%lld), dst in [0,%lld))", (long long)num_src,
              (long long)num_dst);
   return PG_OK;
 }
 
-}  // namespace
-
-int fc_tc_bf16x3(const float* x, int64_t m, int k, const float* w, const float* bias, int n, int act,
-                 const float* residual, float* out, cudaStream_t s) {
-  const TcShape t = tc_shape(k, n);
-  // narrow / shallow layers (N < 8, K < 64: the 64->3, 64->4, 64->7 heads) stay on the fp32 FFMA kernel
-  if (!t.ok || (k & 3) != 0 || m < 1) return fc_fp32_launch(x, m, k, w, bias, n, act, residual, out, n, s);
-  TcParams p{};
-  p.P = x;
-  p.ldp = k;
-  p.k_real = k;
-  p.num_rows = m;
-  p.out = out;
-  p.ldo = n;
-  p.act = act;
-  p.residual = residual;
-  Temp t_img, t_bias;
-  return launch_row_gemm<PROD_ROWS, EPI_STORE>(p, t, w, k, n, bias, t_img, t_bias, s);
-}
-
-int edge_mlp_max_tc(int mode, const float* features, int c_in, const float* xyz_src, const float* xyz_dst,
-                    const int32_t* dst_index, const int32_t* src, const int32_t* dst, int64_t num_edges,
-                    int64_t num_src, int64_t num_dst, const float* const* weights, const float* const* biases,
-                    const int32_t* dims, int num_layers, float* out, cudaStream_t s) {
-  if (mode == PG_EDGE_POOL && c_in == 1) {
-    bool handled = false;
-    if (int rc = pool_chain_launch(features, xyz_src, xyz_dst, dst_index, src, dst, num_edges, num_src, num_dst, weights,
-                                   biases, dims, num_layers, out, s, &handled))
-      return rc;
-    if (handled) return PG_OK;
-  }
-  TcShape t{};
-  const bool pool_tc = mode == PG_EDGE_POOL && num_layers == 4 && c_in == 1 && dims[1] == kPoolC1 &&
-                       dims[2] == kPoolC2 && dims[3] == kPoolC3;
-  if (mode == PG_EDGE_GNN && num_layers == 2) t = tc_shape(dims[1], dims[2]);
-  if (pool_tc) {
-    t = tc_shape(dims[3], dims[4]);
-    t.ok = t.ok && tc_smem_bytes(t.kp, t.np, PROD_POOL) <= 227 * 1024;
-  }
-  if (t.ok && pool_tc && num_edges > 0) {
-    // PointSetPooling (gnn.py:256-277): layers 1-3 of the point MLP run in the producer warps (FFMA),
-    // the 128 -> 300 layer (79% of the FLOPs) on the tensor cores, max / bias / relu in the epilogue.
-    Temp t_w, t_img, t_bias, t_err;
-    PG_CUDA_OK(t_w.alloc(sizeof(float) * kPoolWFloats, s));
-    float* pw = t_w.as<float>();
-    const int sizes[6] = {4 * kPoolC1, kPoolC1, kPoolC1 * kPoolC2, kPoolC2, kPoolC2 * kPoolC3, kPoolC3};
-    const float* srcs[6] = {weights[0], biases[0], weights[1], biases[1], weights[2], biases[2]};
-    size_t off = 0;
-    for (int i = 0; i < 6; ++i) {
-      PG_CUDA_OK(cudaMemcpyAsync(pw + off, srcs[i], sizeof(float) * sizes[i], cudaMemcpyDeviceToDevice, s));
-      off += sizes[i];
-    }
-    PG_CUDA_OK(t_err.alloc(sizeof(int), s));
-    PG_CUDA_OK(cudaMemsetAsync(t_err.ptr, 0, sizeof(int), s));
-    const int n = dims[4];
-    if (int rc = fill_async(out, num_dst * n, -FLT_MAX, s)) return rc;
-    TcParams p{};
-    p.pool_w = pw;
-    p.pool_feat = features;
+int apply_edge(const PreparedEdge& e, const float* features, const float* xyz_src, const float* xyz_dst,
+               const int32_t* dst_index, const int32_t* src, const int32_t* dst, int64_t num_edges, int64_t num_src,
+               int64_t num_dst, float* out, cudaStream_t s) {
+  const int n = e.dims[e.num_layers];
+  if (e.path == EDGE_FP32 || num_edges == 0)
+    return edge_mlp_max_fp32(e.mode, features, e.c_in, xyz_src, xyz_dst, dst_index, src, dst, num_edges, num_src, num_dst,
+                             e.w.data(), e.b.data(), e.dims.data(), e.num_layers, out, s);
+  Temp t_err;
+  PG_CUDA_OK(t_err.alloc(sizeof(int), s));
+  PG_CUDA_OK(cudaMemsetAsync(t_err.ptr, 0, sizeof(int), s));
+  if (int rc = fill_async(out, num_dst * n, -FLT_MAX, s)) return rc;
+  if (e.path == EDGE_CHAIN) {
+    ChainParams cp = e.cp;
+    cp.feat = features;
+    TcParams& p = cp.seg;
     p.xyz_src = xyz_src;
     p.xyz_dst = xyz_dst;
     p.dst_index = dst_index;
@@ -1943,63 +1944,26 @@ int edge_mlp_max_tc(int mode, const float* features, int c_in, const float* xyz_
     p.num_dst = num_dst;
     p.out = out;
     p.err = t_err.as<int>();
-    if (int rc = launch_row_gemm<PROD_POOL, EPI_SEGMAX>(p, t, weights[3], dims[3], n, biases[3], t_img, t_bias, s)) return rc;
-    int h = 0;
-    if (!trusted_indices()) {   // PG_FLAG_TRUSTED_INDICES: no read-back, no synchronisation
-      PG_CUDA_OK(cudaMemcpyAsync(&h, t_err.ptr, sizeof(int), cudaMemcpyDeviceToHost, s));
-      PG_CUDA_OK(cudaStreamSynchronize(s));
+    p.num_pair_tiles = ceil_div(num_edges, 2 * kTileRows);
+    static bool attr_done = false;
+    if (!attr_done) {
+      PG_CUDA_OK(cudaFuncSetAttribute(mlp_chain_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
+      attr_done = true;
     }
-    PG_REQUIRE(h == 0, "set index out of range (point in [0,%lld), keypoint in [0,%lld))", (long long)num_src,
-               (long long)num_dst);
-    return PG_OK;
+    const int clusters = int(std::min<int64_t>(p.num_pair_tiles, num_sms() / 2));
+    mlp_chain_tc_kernel<<<2 * clusters, kChainThreads, e.chain_smem, s>>>(cp);
+    PG_LAUNCH_CHECK();
+    g_tc_launches[0].fetch_add(1, std::memory_order_relaxed);
+    return finish_index_check(t_err, num_src, num_dst, s);
   }
-  if (!t.ok || pool_tc || num_edges == 0)
-    return edge_mlp_max_fp32(mode, features, c_in, xyz_src, xyz_dst, dst_index, src, dst, num_edges, num_src,
-                             num_dst, weights, biases, dims, num_layers, out, s);
-  PG_REQUIRE(dims[0] == c_in + 3, "dims[0]=%d must equal feature channels + 3 = %d", dims[0], c_in + 3);
-  const int d1 = dims[1], n = dims[2];
-  Temp t_p, t_w1x, t_img, t_bias, t_err;
-  // hoisted first layer: P = F @ W1[:C] + b1 (row stride kp, pad columns zero) on the tensor cores too
-  PG_CUDA_OK(t_p.alloc(sizeof(float) * num_src * t.kp, s));
-  {
-    const TcShape tp = tc_shape(c_in, d1);
-    if (tp.ok && (c_in & 3) == 0 && t.kp == tp.np) {
-      TcParams q{};
-      q.P = features;
-      q.ldp = c_in;
-      q.k_real = c_in;
-      q.num_rows = num_src;
-      q.out = t_p.as<float>();
-      q.ldo = t.kp;
-      q.act = 0;
-      q.residual = nullptr;
-      Temp q_img, q_bias;
-      // n = kp here: the pad columns [d1, kp) get bias 0 and zero weights -> written as exact zeros
-      Temp w_pad, b_pad;
-      PG_CUDA_OK(w_pad.alloc(sizeof(float) * size_t(c_in) * t.kp, s));
-      pad_rows_kernel<<<64, 256, 0, s>>>(weights[0], c_in, d1, t.kp, w_pad.as<float>());
-      PG_LAUNCH_CHECK();
-      PG_CUDA_OK(b_pad.alloc(sizeof(float) * t.kp, s));
-      pad_rows_kernel<<<2, 256, 0, s>>>(biases[0], 1, d1, t.kp, b_pad.as<float>());
-      PG_LAUNCH_CHECK();
-      const TcShape tq = tc_shape(c_in, t.kp);
-      if (int rc = launch_row_gemm<PROD_ROWS, EPI_STORE>(q, tq, w_pad.as<float>(), c_in, t.kp, b_pad.as<float>(), q_img,
-                                                         q_bias, s))
-        return rc;
-    } else if (int rc = fc_fp32_launch(features, num_src, c_in, weights[0], biases[0], d1, 0, nullptr, t_p.as<float>(),
-                                       t.kp, s)) {
-      return rc;
-    }
-  }
-  PG_CUDA_OK(t_w1x.alloc(sizeof(float) * 3 * t.kp, s));
-  pad_rows_kernel<<<4, 256, 0, s>>>(weights[0] + int64_t(c_in) * d1, 3, d1, t.kp, t_w1x.as<float>());
-  PG_LAUNCH_CHECK();
-  PG_CUDA_OK(t_err.alloc(sizeof(int), s));
-  PG_CUDA_OK(cudaMemsetAsync(t_err.ptr, 0, sizeof(int), s));
-  if (int rc = fill_async(out, num_dst * n, -FLT_MAX, s)) return rc;
+  // GNN edge layer: hoisted per-vertex GEMM, then the fused gather / second layer / segment max kernel
+  const int kp = e.path == EDGE_SEG ? e.g.kp : e.t.kp;
+  Temp t_p;
+  PG_CUDA_OK(t_p.alloc(sizeof(float) * num_src * kp, s));
+  if (int rc = apply_fc(e.p_fc, features, num_src, 0, nullptr, t_p.as<float>(), kp, s)) return rc;
   TcParams p{};
   p.P = t_p.as<float>();
-  p.ldp = t.kp;
+  p.ldp = kp;
   p.xyz_src = xyz_src;
   p.xyz_dst = xyz_dst;
   p.dst_index = dst_index;
@@ -2008,22 +1972,416 @@ int edge_mlp_max_tc(int mode, const float* features, int c_in, const float* xyz_
   p.num_rows = num_edges;
   p.num_src = num_src;
   p.num_dst = num_dst;
-  p.w1x = t_w1x.as<float>();
+  p.w1x = e.w1x.as<float>();
   p.out = out;
   p.err = t_err.as<int>();
-  if (seg_gemm_fits(d1, n)) {
-    if (int rc = launch_seg_gemm(p, weights[1], d1, n, biases[1], t_img, t_bias, s)) return rc;
-  } else if (int rc = launch_row_gemm<PROD_GNN, EPI_SEGMAX>(p, t, weights[1], d1, n, biases[1], t_img, t_bias, s)) {
-    return rc;
+  if (e.path == EDGE_SEG) {
+    const SegShape& g = e.g;
+    p.bias = e.bias_pad.as<float>();
+    p.kp = g.kp;
+    p.ks = g.kp / 16;
+    p.n = n;
+    p.np = 256 + g.n2;
+    p.n1 = 256;
+    p.n2 = g.n2;
+    p.wimg = e.img.as<uint8_t>();
+    p.wtm = e.tm_img.as<uint32_t>();
+    p.part_bytes = g.part;
+    p.hi2_bytes = g.hi2;
+    p.tm_w_col = g.tm_w_col;
+    p.d2_stride = g.d2_stride;
+    p.nstages = g.nstages;
+    p.tmem_cols = 512;
+    p.num_pair_tiles = ceil_div(p.num_rows, 2 * kTileRows);
+    PG_REQUIRE(p.num_src * int64_t(p.ldp) < (int64_t(1) << 31), "vertex table too large for 32-bit element offsets");
+    static bool attr_done = false;
+    if (!attr_done) {
+      PG_CUDA_OK(cudaFuncSetAttribute(seg_gemm_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
+      attr_done = true;
+    }
+    const int clusters = int(std::min<int64_t>(p.num_pair_tiles, num_sms() / 2));
+#ifdef PG_LAB
+    const char* trace_path = getenv("PG_TC_TRACE");           // lab build only: dump the in-kernel trace
+    Temp t_trace;
+    const size_t trace_words = size_t(8) * 128 * 3;
+    if (trace_path != nullptr) {
+      PG_CUDA_OK(t_trace.alloc(trace_words * 8, s));
+      PG_CUDA_OK(cudaMemsetAsync(t_trace.ptr, 0, trace_words * 8, s));
+      p.trace = t_trace.as<unsigned long long>();
+    }
+#endif
+    seg_gemm_tc_kernel<<<2 * clusters, kSegThreads, g.smem, s>>>(p);
+    PG_LAUNCH_CHECK();
+#ifdef PG_LAB
+    if (trace_path != nullptr) {
+      std::vector<unsigned long long> h(trace_words);
+      PG_CUDA_OK(cudaMemcpyAsync(h.data(), t_trace.ptr, trace_words * 8, cudaMemcpyDeviceToHost, s));
+      PG_CUDA_OK(cudaStreamSynchronize(s));
+      if (FILE* f = fopen(trace_path, "w")) {
+        for (size_t i = 0; i < trace_words; i += 3)
+          fprintf(f, "%zu %zu %llu %llu %llu\n", i / 3 / 128, (i / 3) % 128, h[i], h[i + 1], h[i + 2]);
+        fclose(f);
+      }
+    }
+#endif
+    g_tc_launches[0].fetch_add(1, std::memory_order_relaxed);
+  } else {
+    if (int rc = launch_row_gemm<PROD_GNN, EPI_SEGMAX>(p, e.t, n, e.img.as<uint8_t>(), e.bias_pad.as<float>(), s)) return rc;
   }
-  int h = 0;
-  if (!trusted_indices()) {   // PG_FLAG_TRUSTED_INDICES: no read-back, no synchronisation
-    PG_CUDA_OK(cudaMemcpyAsync(&h, t_err.ptr, sizeof(int), cudaMemcpyDeviceToHost, s));
-    PG_CUDA_OK(cudaStreamSynchronize(s));
+  return finish_index_check(t_err, num_src, num_dst, s);
+}
+
+// ---- the class-aware predictor heads (gnn.py:133-163) ---------------------------------------------
+// After the concatenated first layers (one GEMM: [D] -> H * (C + 1), ReLU) everything left is tiny per vertex:
+// cls H -> C (linear), and per class H -> H (ReLU) -> box_len (linear).  One SIMT kernel does all of it for a
+// tile of 32 vertices with every head weight resident in shared memory, and writes logits, class
+// probabilities (softmax, models.py:165-168) and the stacked box encodings [K, C, box_len].
+constexpr int kHeadRows = 32;
+constexpr int kHeadThreads = 256;
+constexpr int kHeadMaxQ = 16;   // rows per thread in the second layer: kHeadRows / (kHeadThreads / H)
+
+struct HeadsParams {
+  const float* hid;      // [m, htot] = relu(first layers), columns: cls hidden [H] then class c hidden [H] ...
+  int64_t m;
+  int htot, H, C, box;
+  const float* wpack;    // [Wcls H*C | bcls C | per class: W2 H*H | b2 H | W3 H*box | b3 box]
+  int wfloats;
+  float* logits;         // [m, C]
+  float* probs;          // [m, C] or null
+  float* boxes;          // [m, C, box]
+};
+
+__global__ void __launch_bounds__(kHeadThreads) predictor_heads_kernel(HeadsParams p) {
+  extern __shared__ __align__(16) float hsm[];
+  float* w = hsm;                                  // all head weights
+  float* hid = w + ((p.wfloats + 3) & ~3);         // [kHeadRows][htot + 1]
+  const int hs = p.htot + 1;
+  float* h2 = hid + kHeadRows * hs;                // [kHeadRows][H + 1]
+  const int H = p.H, C = p.C, box = p.box;
+  for (int i = threadIdx.x; i < p.wfloats; i += kHeadThreads) w[i] = p.wpack[i];
+  const float* wcls = w;
+  const float* bcls = w + H * C;
+  const int per_class = H * H + H + H * box + box;
+  const int64_t tiles = (p.m + kHeadRows - 1) / kHeadRows;
+  for (int64_t tile = blockIdx.x; tile < tiles; tile += gridDim.x) {
+    const int64_t row0 = tile * kHeadRows;
+    const int rows = int(min(int64_t(kHeadRows), p.m - row0));
+    __syncthreads();
+    for (int i = threadIdx.x; i < rows * p.htot; i += kHeadThreads) {
+      const int r = i / p.htot, c = i - r * p.htot;
+      hid[r * hs + c] = p.hid[(row0 + r) * p.htot + c];
+    }
+    __syncthreads();
+    // class logits + softmax: one thread per row (H * C MACs)
+    if (threadIdx.x < rows) {
+      const int r = threadIdx.x;
+      float lg[16];
+      float mx = -FLT_MAX;
+      for (int c = 0; c < C; ++c) {
+        float a = bcls[c];
+        for (int i = 0; i < H; ++i) a = fmaf(hid[r * hs + i], wcls[i * C + c], a);
+        lg[c] = a;
+        mx = fmaxf(mx, a);
+        p.logits[(row0 + r) * C + c] = a;
+      }
+      if (p.probs != nullptr) {
+        float sum = 0.0f;
+        for (int c = 0; c < C; ++c) sum += expf(lg[c] - mx);
+        for (int c = 0; c < C; ++c) p.probs[(row0 + r) * C + c] = expf(lg[c] - mx) / sum;
+      }
+    }
+    for (int c = 0; c < C; ++c) {
+      const float* w2 = w + H * C + C + c * per_class;
+      const float* b2 = w2 + H * H;
+      const float* w3 = b2 + H;
+      const float* b3 = w3 + H * box;
+      const float* hc = hid + H * (c + 1);
+      // second layer: thread (j, row group) -> rows rg, rg + G, ...   (G = threads / H row groups)
+      const int j = threadIdx.x % H, rg = threadIdx.x / H, G = kHeadThreads / H;
+      const int nq = kHeadRows / G;          // rows per thread (<= kHeadMaxQ, checked on the host)
+      float acc[kHeadMaxQ];
+#pragma unroll
+      for (int q = 0; q < kHeadMaxQ; ++q) acc[q] = b2[j];
+      for (int i = 0; i < H; ++i) {
+        const float wv = w2[i * H + j];
+#pragma unroll
+        for (int q = 0; q < kHeadMaxQ; ++q)
+          if (q < nq) acc[q] = fmaf(hc[(q * G + rg) * hs + i], wv, acc[q]);
+      }
+#pragma unroll
+      for (int q = 0; q < kHeadMaxQ; ++q)
+        if (q < nq) h2[(q * G + rg) * (H + 1) + j] = fmaxf(acc[q], 0.0f);
+      __syncthreads();
+      for (int o = threadIdx.x; o < rows * box; o += kHeadThreads) {
+        const int r = o / box, ob = o - r * box;
+        float a = b3[ob];
+        for (int i = 0; i < H; ++i) a = fmaf(h2[r * (H + 1) + i], w3[i * box + ob], a);
+        p.boxes[((row0 + r) * C + c) * box + ob] = a;
+      }
+      __syncthreads();
+    }
   }
-  PG_REQUIRE(h == 0, "edge index out of range (src in [0,%lld), dst in [0,%lld))", (long long)num_src,
-             (long long)num_dst);
-  return PG_OK;
+}
+
+__global__ void copy_block_kernel(const float* __restrict__ src, int64_t rows, int cols, int ld_dst, float* __restrict__ dst) {
+  for (int64_t i = int64_t(blockIdx.x) * blockDim.x + threadIdx.x; i < rows * cols; i += int64_t(gridDim.x) * blockDim.x) {
+    const int64_t r = i / cols;
+    const int c = int(i - r * cols);
+    dst[r * ld_dst + c] = src[i];
+  }
+}
+
+struct PreparedPredictor {
+  int D = 0, H = 0, C = 0, box = 0, htot = 0;
+  bool fused = false;
+  Temp wcat, bcat, wpack;                  // [D, htot] concatenated first layers, [htot], head weights
+  std::vector<PreparedFc> first;           // column groups of the concatenated first layer (<= 256 wide each)
+  std::vector<int> col0;
+  int wfloats = 0;
+  size_t smem = 0;
+};
+
+}  // namespace
+
+// ---------------------------------------------------------------------------------------------------
+// per-call entry points (prepare into temporaries, apply once)
+// ---------------------------------------------------------------------------------------------------
+int fc_tc_bf16x3(const float* x, int64_t m, int k, const float* w, const float* bias, int n, int act,
+                 const float* residual, float* out, cudaStream_t s) {
+  PreparedFc f;
+  if (int rc = prepare_fc(f, w, n, bias, k, n, n, m >= 1, s)) return rc;
+  return apply_fc(f, x, m, act, residual, out, n, s);
+}
+
+int edge_mlp_max_tc(int mode, const float* features, int c_in, const float* xyz_src, const float* xyz_dst,
+                    const int32_t* dst_index, const int32_t* src, const int32_t* dst, int64_t num_edges,
+                    int64_t num_src, int64_t num_dst, const float* const* weights, const float* const* biases,
+                    const int32_t* dims, int num_layers, float* out, cudaStream_t s) {
+  PreparedEdge e;
+  if (int rc = prepare_edge(e, mode, c_in, weights, biases, dims, num_layers, num_edges > 0, s)) return rc;
+  return apply_edge(e, features, xyz_src, xyz_dst, dst_index, src, dst, num_edges, num_src, num_dst, out, s);
 }
 
 }  // namespace pg
+
+// ---------------------------------------------------------------------------------------------------
+// pg_layer: prepared layers behind the C ABI
+// ---------------------------------------------------------------------------------------------------
+struct pg_layer {
+  int kind = 0, precision = 0, num_layers = 0;
+  std::vector<int32_t> dims;
+  std::vector<pg::PreparedFc> fcs;      // PG_LAYER_MLP
+  pg::PreparedEdge edge;                // PG_LAYER_EDGE_POOL / PG_LAYER_EDGE_GNN
+  pg::PreparedPredictor pred;           // PG_LAYER_PREDICTOR
+  std::vector<const float*> w, b;
+};
+
+using namespace pg;
+
+extern "C" int pg_layer_create(int32_t kind, const float* const* weights_host, const float* const* biases_host,
+                               const int32_t* dims_host, int32_t num_layers, int32_t precision, void* stream,
+                               pg_layer** out_layer) {
+  cudaStream_t s = static_cast<cudaStream_t>(stream);
+  PG_REQUIRE(out_layer != nullptr, "pg_layer_create: out_layer is null");
+  *out_layer = nullptr;
+  PG_REQUIRE(weights_host && biases_host && dims_host && num_layers >= 1 && num_layers <= 64, "pg_layer_create: bad layer tables");
+  PG_REQUIRE(precision == 0 || precision == 1, "pg_layer_create: unknown precision %d", precision);
+  PG_REQUIRE(kind == PG_LAYER_MLP || kind == PG_LAYER_EDGE_POOL || kind == PG_LAYER_EDGE_GNN || kind == PG_LAYER_PREDICTOR,
+             "pg_layer_create: unknown kind %d", kind);
+  for (int l = 0; l < num_layers; ++l) PG_REQUIRE(weights_host[l] && biases_host[l], "pg_layer_create: null weight/bias %d", l);
+  pg_layer* L = new pg_layer();
+  L->kind = kind;
+  L->precision = precision;
+  L->num_layers = num_layers;
+  L->w.assign(weights_host, weights_host + num_layers);
+  L->b.assign(biases_host, biases_host + num_layers);
+  int rc = PG_OK;
+  const bool tc = precision == 1 && pg_tc_available();
+  if (kind == PG_LAYER_MLP) {
+    L->dims.assign(dims_host, dims_host + num_layers + 1);
+    L->fcs.resize(num_layers);
+    for (int l = 0; l < num_layers && rc == PG_OK; ++l)
+      rc = prepare_fc(L->fcs[l], weights_host[l], dims_host[l + 1], biases_host[l], dims_host[l], dims_host[l + 1],
+                      dims_host[l + 1], tc, s);
+  } else if (kind == PG_LAYER_EDGE_POOL || kind == PG_LAYER_EDGE_GNN) {
+    L->dims.assign(dims_host, dims_host + num_layers + 1);
+    rc = prepare_edge(L->edge, kind == PG_LAYER_EDGE_POOL ? PG_EDGE_POOL : PG_EDGE_GNN, dims_host[0] - 3, weights_host,
+                      biases_host, dims_host, num_layers, tc, s);
+  } else {
+    // predictor: dims = {D, H, C, box_len}; layers = cls fc0, cls fc1, then per class c: fc0, fc1, fc2
+    L->dims.assign(dims_host, dims_host + 4);
+    PreparedPredictor& P = L->pred;
+    P.D = dims_host[0];
+    P.H = dims_host[1];
+    P.C = dims_host[2];
+    P.box = dims_host[3];
+    if (num_layers != 2 + 3 * P.C || P.C < 1 || P.C > 16 || P.H < 1 || P.box < 1) {
+      delete L;
+      PG_REQUIRE(false, "pg_layer_create: predictor needs 2 + 3 C layers, 1 <= C <= 16");
+    }
+    P.htot = P.H * (P.C + 1);
+    P.wfloats = P.H * P.C + P.C + P.C * (P.H * P.H + P.H + P.H * P.box + P.box);
+    P.smem = (size_t((P.wfloats + 3) & ~3) + size_t(kHeadRows) * (P.htot + 1) + size_t(kHeadRows) * (P.H + 1)) * sizeof(float);
+    P.fused = P.H <= kHeadThreads && kHeadThreads % P.H == 0 && kHeadRows % (kHeadThreads / P.H) == 0 &&
+              kHeadRows / (kHeadThreads / P.H) <= kHeadMaxQ && P.smem <= 227 * 1024 && (P.H % 4) == 0;
+    if (P.fused) {
+      auto cuda_ok = [&](cudaError_t e) { if (e != cudaSuccess && rc == PG_OK) { pg::set_error("predictor prepare: %s", cudaGetErrorString(e)); rc = PG_ERR_CUDA; } };
+      cuda_ok(P.wcat.alloc(sizeof(float) * size_t(P.D) * P.htot, s));
+      cuda_ok(P.bcat.alloc(sizeof(float) * P.htot, s));
+      cuda_ok(P.wpack.alloc(sizeof(float) * P.wfloats, s));
+      if (rc == PG_OK) {
+        // concatenated first layers: column block h = 0 is the cls head, h = 1 + c the loc head of class c
+        for (int h = 0; h <= P.C; ++h) {
+          const int l = h == 0 ? 0 : 2 + 3 * (h - 1);
+          copy_block_kernel<<<32, 256, 0, s>>>(weights_host[l], P.D, P.H, P.htot, P.wcat.as<float>() + h * P.H);
+          count_launch();
+          cuda_ok(cudaMemcpyAsync(P.bcat.as<float>() + h * P.H, biases_host[l], sizeof(float) * P.H, cudaMemcpyDeviceToDevice, s));
+        }
+        float* wp = P.wpack.as<float>();
+        size_t off = 0;
+        auto put = [&](const float* src, size_t count) {
+          cuda_ok(cudaMemcpyAsync(wp + off, src, sizeof(float) * count, cudaMemcpyDeviceToDevice, s));
+          off += count;
+        };
+        put(weights_host[1], size_t(P.H) * P.C);
+        put(biases_host[1], P.C);
+        for (int c = 0; c < P.C; ++c) {
+          put(weights_host[2 + 3 * c + 1], size_t(P.H) * P.H);
+          put(biases_host[2 + 3 * c + 1], P.H);
+          put(weights_host[2 + 3 * c + 2], size_t(P.H) * P.box);
+          put(biases_host[2 + 3 * c + 2], P.box);
+        }
+        // column groups of at most 256 (whole heads) -> one tensor-core GEMM each
+        const int heads_per_group = std::max(1, 256 / P.H);
+        for (int h0 = 0; h0 <= P.C && rc == PG_OK; h0 += heads_per_group) {
+          const int nh = std::min(heads_per_group, P.C + 1 - h0);
+          P.first.emplace_back();
+          P.col0.push_back(h0 * P.H);
+          rc = prepare_fc(P.first.back(), P.wcat.as<float>() + h0 * P.H, P.htot, P.bcat.as<float>() + h0 * P.H, P.D,
+                          nh * P.H, nh * P.H, tc, s);
+          if (rc == PG_OK && !P.first.back().tc) P.fused = false;   // FFMA kernel needs contiguous weights: per-layer path
+        }
+      }
+    }
+    if (!P.fused && rc == PG_OK) {
+      // generic route: every layer prepared on its own (used for shapes the heads kernel is not built for)
+      P.first.clear();
+      L->fcs.resize(num_layers);
+      for (int l = 0; l < num_layers && rc == PG_OK; ++l) {
+        const int pos = l < 2 ? l : (l - 2) % 3;
+        const int k = pos == 0 ? P.D : P.H;
+        const int n = l == 1 ? P.C : (l >= 2 && pos == 2 ? P.box : P.H);
+        rc = prepare_fc(L->fcs[l], weights_host[l], n, biases_host[l], k, n, n, tc, s);
+      }
+    }
+  }
+  if (rc != PG_OK) {
+    delete L;
+    return rc;
+  }
+  *out_layer = L;
+  return PG_OK;
+}
+
+extern "C" int pg_layer_destroy(pg_layer* layer) {
+  delete layer;      // prepared buffers are returned to the stream-ordered pool on the stream they were made on
+  return PG_OK;
+}
+
+extern "C" int pg_layer_mlp(const pg_layer* layer, const float* x, int64_t m, int32_t last_linear, const float* residual,
+                            float* out, void* stream) {
+  cudaStream_t s = static_cast<cudaStream_t>(stream);
+  PG_REQUIRE(layer && layer->kind == PG_LAYER_MLP, "pg_layer_mlp: not an MLP layer");
+  if (m == 0) return PG_OK;
+  PG_REQUIRE(x && out && m > 0, "pg_layer_mlp: bad argument");
+  const int L = layer->num_layers;
+  Temp bufs[2];
+  int widest = 0;
+  for (int l = 1; l < L; ++l) widest = std::max(widest, int(layer->dims[l]));
+  if (L > 1) {
+    PG_CUDA_OK(bufs[0].alloc(sizeof(float) * m * widest, s));
+    if (L > 2) PG_CUDA_OK(bufs[1].alloc(sizeof(float) * m * widest, s));
+  }
+  const float* cur = x;
+  for (int l = 0; l < L; ++l) {
+    const bool last = l + 1 == L;
+    float* dst = last ? out : bufs[l & 1].as<float>();
+    const int act = (last && last_linear) ? 0 : 1;
+    if (int rc = apply_fc(layer->fcs[l], cur, m, act, last ? residual : nullptr, dst, layer->dims[l + 1], s)) return rc;
+    cur = dst;
+  }
+  return PG_OK;
+}
+
+extern "C" int pg_layer_edge_mlp_max(const pg_layer* layer, const float* features, const float* xyz_src,
+                                     const float* xyz_dst, const int32_t* dst_index, const int32_t* src,
+                                     const int32_t* dst, int64_t num_edges, int64_t num_src, int64_t num_dst, float* out,
+                                     int32_t flags, void* stream) {
+  cudaStream_t s = static_cast<cudaStream_t>(stream);
+  PG_REQUIRE(layer && (layer->kind == PG_LAYER_EDGE_POOL || layer->kind == PG_LAYER_EDGE_GNN),
+             "pg_layer_edge_mlp_max: not an edge layer");
+  PG_REQUIRE(num_edges >= 0 && num_src >= 1 && num_dst >= 0, "pg_layer_edge_mlp_max: bad sizes");
+  PG_REQUIRE(out != nullptr || num_dst == 0, "pg_layer_edge_mlp_max: out is null");
+  PG_REQUIRE((features && xyz_src && xyz_dst && src && dst) || num_edges == 0, "pg_layer_edge_mlp_max: null input");
+  PG_REQUIRE(layer->kind == PG_LAYER_EDGE_GNN || dst_index != nullptr || num_edges == 0,
+             "pg_layer_edge_mlp_max: POOL mode needs keypoint indices");
+  struct TrustedScope {
+    explicit TrustedScope(bool v) { pg::set_trusted_indices(v); }
+    ~TrustedScope() { pg::set_trusted_indices(false); }
+  } scope((flags & PG_FLAG_TRUSTED_INDICES) != 0);
+  return apply_edge(layer->edge, features, xyz_src, xyz_dst, dst_index, src, dst, num_edges, num_src, num_dst, out, s);
+}
+
+extern "C" int pg_layer_predictor(const pg_layer* layer, const float* x, int64_t m, float* logits, float* boxes,
+                                  float* probs, void* stream) {
+  cudaStream_t s = static_cast<cudaStream_t>(stream);
+  PG_REQUIRE(layer && layer->kind == PG_LAYER_PREDICTOR, "pg_layer_predictor: not a predictor layer");
+  if (m == 0) return PG_OK;
+  PG_REQUIRE(x && logits && boxes && m > 0, "pg_layer_predictor: bad argument");
+  const PreparedPredictor& P = layer->pred;
+  if (P.fused) {
+    Temp hid;
+    PG_CUDA_OK(hid.alloc(sizeof(float) * m * P.htot, s));
+    for (size_t g = 0; g < P.first.size(); ++g)
+      if (int rc = apply_fc(P.first[g], x, m, 1, nullptr, hid.as<float>() + P.col0[g], P.htot, s)) return rc;
+    HeadsParams hp{};
+    hp.hid = hid.as<float>();
+    hp.m = m;
+    hp.htot = P.htot;
+    hp.H = P.H;
+    hp.C = P.C;
+    hp.box = P.box;
+    hp.wpack = P.wpack.as<float>();
+    hp.wfloats = P.wfloats;
+    hp.logits = logits;
+    hp.probs = probs;
+    hp.boxes = boxes;
+    static bool attr_done = false;
+    if (!attr_done) {
+      PG_CUDA_OK(cudaFuncSetAttribute(predictor_heads_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
+      attr_done = true;
+    }
+    const int blocks = int(std::min<int64_t>(ceil_div(m, kHeadRows), num_sms()));
+    predictor_heads_kernel<<<blocks, kHeadThreads, P.smem, s>>>(hp);
+    PG_LAUNCH_CHECK();
+    return PG_OK;
+  }
+  // generic route: layer by layer
+  Temp h1, h2, tmp;
+  PG_CUDA_OK(h1.alloc(sizeof(float) * m * P.H, s));
+  PG_CUDA_OK(h2.alloc(sizeof(float) * m * P.H, s));
+  PG_CUDA_OK(tmp.alloc(sizeof(float) * m * P.box, s));
+  if (int rc = apply_fc(layer->fcs[0], x, m, 1, nullptr, h1.as<float>(), P.H, s)) return rc;
+  if (int rc = apply_fc(layer->fcs[1], h1.as<float>(), m, 0, nullptr, logits, P.C, s)) return rc;
+  if (probs != nullptr)
+    if (int rc = pg_softmax_rows(logits, m, P.C, probs, stream)) return rc;
+  for (int c = 0; c < P.C; ++c) {
+    const int l = 2 + 3 * c;
+    if (int rc = apply_fc(layer->fcs[l], x, m, 1, nullptr, h1.as<float>(), P.H, s)) return rc;
+    if (int rc = apply_fc(layer->fcs[l + 1], h1.as<float>(), m, 1, nullptr, h2.as<float>(), P.H, s)) return rc;
+    if (int rc = apply_fc(layer->fcs[l + 2], h2.as<float>(), m, 0, nullptr, tmp.as<float>(), P.box, s)) return rc;
+    copy_block_kernel<<<64, 256, 0, s>>>(tmp.as<float>(), m, P.box, P.C * P.box, boxes + c * P.box);
+    PG_LAUNCH_CHECK();
+  }
+  return PG_OK;
+}

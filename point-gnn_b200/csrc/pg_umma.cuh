@@ -169,6 +169,27 @@ __device__ __forceinline__ void mma_bf16(uint32_t tmem_d, uint64_t desc_a, uint6
         : "memory");
 }
 
+// Same with the A operand in TENSOR MEMORY: lane i of the issuing CTA's (and, for cta_group::2, of the peer's)
+// TMEM holds row i of its M-half, K-major, two 16-bit elements per 32-bit column (element k in column
+// k / 2, low half first) - i.e. a K = 16 MMA reads 8 columns starting at `tmem_a`.
+template <int kCtaGroup>
+__device__ __forceinline__ void mma_bf16_ts(uint32_t tmem_d, uint32_t tmem_a, uint64_t desc_b, uint32_t idesc,
+                                            bool accumulate) {
+  const uint32_t acc = accumulate ? 1u : 0u;
+  if constexpr (kCtaGroup == 1)
+    asm volatile(
+        "{\n\t.reg .pred p;\n\tsetp.ne.b32 p, %4, 0;\n\t"
+        "tcgen05.mma.cta_group::1.kind::f16 [%0], [%1], %2, %3, p;\n\t}" ::"r"(tmem_d),
+        "r"(tmem_a), "l"(desc_b), "r"(idesc), "r"(acc)
+        : "memory");
+  else
+    asm volatile(
+        "{\n\t.reg .pred p;\n\tsetp.ne.b32 p, %4, 0;\n\t"
+        "tcgen05.mma.cta_group::2.kind::f16 [%0], [%1], %2, %3, p;\n\t}" ::"r"(tmem_d),
+        "r"(tmem_a), "l"(desc_b), "r"(idesc), "r"(acc)
+        : "memory");
+}
+
 // All previously issued MMAs of this thread complete -> one arrival on `bar` (1-CTA form), or on the
 // barrier at the same offset in every CTA of `cta_mask` (2-CTA form).  Implies fence::before_thread_sync.
 __device__ __forceinline__ void mma_commit_1cta(uint64_t* bar) {
@@ -205,6 +226,13 @@ __device__ __forceinline__ void tmem_ld32(uint32_t tmem_addr, uint32_t (&v)[32])
       : "r"(tmem_addr)
       : "memory");
 }
+// registers -> TMEM: thread t of the warp writes v[0..7] to columns [c, c+8) of TMEM lane (base + t)
+__device__ __forceinline__ void tmem_st8(uint32_t tmem_addr, const uint32_t (&v)[8]) {
+  asm volatile("tcgen05.st.sync.aligned.32x32b.x8.b32 [%0], {%1, %2, %3, %4, %5, %6, %7, %8};" ::"r"(tmem_addr),
+               "r"(v[0]), "r"(v[1]), "r"(v[2]), "r"(v[3]), "r"(v[4]), "r"(v[5]), "r"(v[6]), "r"(v[7])
+               : "memory");
+}
+__device__ __forceinline__ void tmem_st_wait() { asm volatile("tcgen05.wait::st.sync.aligned;" ::: "memory"); }
 __device__ __forceinline__ void tmem_ld_wait() { asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory"); }
 
 // ---- BF16 three-way split ------------------------------------------------------------------

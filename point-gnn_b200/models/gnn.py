@@ -33,10 +33,12 @@ class VariableStore(object):
 
     def __init__(self, variables=None, device=None):
         self.vars = {}
+        self.prepared = {}      # (kind, first variable, depth, precision) -> _lib.PreparedLayer (weights packed once)
         if variables:
             self.load(variables, device)
 
     def load(self, variables, device=None):
+        self.prepared.clear()
         device = device or torch.device('cuda', torch.cuda.current_device())
         for name, value in variables.items():
             if not (name.endswith('/weights') or name.endswith('/biases')):
@@ -83,14 +85,49 @@ def variable_scope(name):
         _ctx.scope.pop()
 
 
-def _next_fully_connected():
+def _next_fully_connected_named():
     if _ctx.store is None:
         raise RuntimeError('no VariableStore bound: call inside model.predict / variable_session')
     scope = '/'.join(_ctx.scope)
     i = _ctx.counters.get(scope, 0)
     _ctx.counters[scope] = i + 1
     base = (scope + '/' if scope else '') + ('fully_connected' if i == 0 else 'fully_connected_%d' % i)
-    return _ctx.store.get(base + '/weights'), _ctx.store.get(base + '/biases')
+    return base, _ctx.store.get(base + '/weights'), _ctx.store.get(base + '/biases')
+
+
+def _next_fully_connected():
+    return _next_fully_connected_named()[1:]
+
+
+def _take_mlp(num_layers):
+    """The next ``num_layers`` slim.fully_connected variables of the current scope -> (names, weights, biases)."""
+    names, ws, bs = [], [], []
+    for _ in range(num_layers):
+        n, w, b = _next_fully_connected_named()
+        names.append(n)
+        ws.append(w)
+        bs.append(b)
+    return names, ws, bs
+
+
+def _prepared(kind, names, weights, biases, dims):
+    """The prepared (weights packed once) layer for these variables, cached on the bound VariableStore - the
+    stand-in for TF creating / restoring its variables once and only computing at sess.run."""
+    store = _ctx.store
+    key = (kind, names[0], len(names), get_precision())
+    layer = store.prepared.get(key)
+    if layer is None:
+        layer = _lib.PreparedLayer(kind, weights, biases, dims, get_precision())
+        store.prepared[key] = layer
+    return layer
+
+
+def _mlp_dims(ws, bs, widths):
+    dims = [ws[0].shape[0]] + [w.shape[1] for w in ws]
+    for i, (w, b) in enumerate(zip(ws, bs)):
+        assert w.shape[0] == dims[i] and b.numel() == dims[i + 1], 'inconsistent layer shapes in the checkpoint'
+    assert dims[1:] == [int(k) for k in widths], 'checkpoint layer widths %s != configured %s' % (dims[1:], list(widths))
+    return dims
 
 
 # the reference's tables (gnn.py:17-32); only the entries its shipped configs use are executable
@@ -119,12 +156,9 @@ def multi_layer_fc_fn(sv, mask=None, Ks=(64, 32, 64), num_classes=4, is_logits=F
     assert len(sv.shape) == 2
     assert len(Ks) == num_layer - 1
     _check_types(normalization_type, activation_type)
-    features = sv
-    for i in range(num_layer - 1):
-        features = _fully_connected(features, relu=True)
-        assert features.shape[1] == Ks[i]
-    features = _fully_connected(features, relu=not is_logits)
-    assert features.shape[1] == num_classes
+    names, ws, bs = _take_mlp(num_layer)
+    layer = _prepared(_lib.PG_LAYER_MLP, names, ws, bs, _mlp_dims(ws, bs, list(Ks) + [num_classes]))
+    features = layer.mlp(sv.contiguous(), last_linear=is_logits)
     if mask is not None:
         features = features * mask
     return features
@@ -136,21 +170,13 @@ def multi_layer_neural_network_fn(features, Ks=(64, 32, 64), is_logits=False,
     """gnn.py:86-104.  ``residual`` (extension): added to the last layer's output in-kernel."""
     assert len(features.shape) == 2
     _check_types(normalization_type, activation_type)
-    for i in range(len(Ks)):
-        last = i == len(Ks) - 1
-        features = _fully_connected(features, relu=not (is_logits and last),
-                                    residual=residual if last else None)
-        assert features.shape[1] == Ks[i]
-    return features
+    names, ws, bs = _take_mlp(len(Ks))
+    layer = _prepared(_lib.PG_LAYER_MLP, names, ws, bs, _mlp_dims(ws, bs, Ks))
+    return layer.mlp(features.contiguous(), last_linear=is_logits, residual=residual)
 
 
 def _take_mlp_weights(num_layers):
-    ws, bs = [], []
-    for _ in range(num_layers):
-        w, b = _next_fully_connected()
-        ws.append(w)
-        bs.append(b)
-    return ws, bs
+    return _take_mlp(num_layers)[1:]
 
 
 def graph_scatter_max_fn(point_features, point_centers, num_centers):
@@ -180,8 +206,46 @@ class ClassAwarePredictor(object):
         self._cls_fn = cls_fn
         self._loc_fn = loc_fn
 
+    def _head_width(self):
+        """H when cls_fn / loc_fn are the registry's ``partial(multi_layer_fc_fn, Ks=(H,), num_layer=2)`` /
+        ``partial(multi_layer_fc_fn, Ks=(H, H), num_layer=3)`` (models.py:60-64), else None."""
+        c, l = self._cls_fn, self._loc_fn
+        if not (isinstance(c, partial) and isinstance(l, partial) and c.func is multi_layer_fc_fn
+                and l.func is multi_layer_fc_fn and not c.args and not l.args):
+            return None
+        ck, lk = c.keywords, l.keywords
+        if set(ck) != {'Ks', 'num_layer'} or set(lk) != {'Ks', 'num_layer'}:
+            return None
+        if ck['num_layer'] != 2 or lk['num_layer'] != 3 or len(ck['Ks']) != 1 or len(lk['Ks']) != 2:
+            return None
+        h = int(ck['Ks'][0])
+        return h if (int(lk['Ks'][0]) == h and int(lk['Ks'][1]) == h) else None
+
     def apply_regular(self, features, num_classes, box_encoding_len,
                       normalization_type='fused_BN_center', activation_type='ReLU'):
+        h = self._head_width()
+        if h is not None and normalization_type == 'NONE' and activation_type == 'ReLU':
+            # all heads in two launches per column group: the C + 1 first layers as ONE concatenated GEMM, then
+            # one kernel for every remaining (tiny) layer, the softmax and the [K, C, box] stacking
+            names, ws, bs = [], [], []
+            with variable_scope('predictor'):
+                with variable_scope('cls'):
+                    n, w, b = _take_mlp(2)
+                    names, ws, bs = names + n, ws + w, bs + b
+                with variable_scope('loc'):
+                    for class_idx in range(num_classes):
+                        with variable_scope('cls_%d' % class_idx):
+                            n, w, b = _take_mlp(3)
+                            names, ws, bs = names + n, ws + w, bs + b
+            d = ws[0].shape[0]
+            assert tuple(ws[1].shape) == (h, num_classes) and tuple(ws[0].shape) == (d, h)
+            for class_idx in range(num_classes):
+                w0, w1, w2 = ws[2 + 3 * class_idx:5 + 3 * class_idx]
+                assert tuple(w0.shape) == (d, h) and tuple(w1.shape) == (h, h) and tuple(w2.shape) == (h, box_encoding_len)
+            layer = _prepared(_lib.PG_LAYER_PREDICTOR, names, ws, bs, [d, h, num_classes, box_encoding_len])
+            logits, box_encodings, probs = layer.predictor(features.contiguous())
+            logits._pg_probs = (probs, logits._version)      # models.postprocess returns these (softmax fused)
+            return logits, box_encodings
         box_encodings_list = []
         with variable_scope('predictor'):
             with variable_scope('cls'):
@@ -221,11 +285,14 @@ class PointSetPooling(object):
         src, dst = set_indices[:, 0], set_indices[:, 1]
         with variable_scope('extract_vertex_features'):
             if self._fusable(point_MLP_normalization_type, point_MLP_activation_type):
-                ws, bs = _take_mlp_weights(len(point_MLP_depth_list))
-                set_features = _lib.edge_mlp_max(
-                    _PG_EDGE_POOL, point_features.contiguous(), point_coordinates.contiguous(),
-                    point_coordinates.contiguous(), _i32(keypoint_indices.reshape(-1)), _i32(src), _i32(dst),
-                    num_keypoints, ws, bs, precision=get_precision(), trusted=_ctx.trusted_edges)
+                names, ws, bs = _take_mlp(len(point_MLP_depth_list))
+                dims = [point_features.shape[1] + 3] + [int(k) for k in point_MLP_depth_list]
+                assert _mlp_dims(ws, bs, point_MLP_depth_list) == dims, 'point MLP input width mismatch'
+                layer = _prepared(_lib.PG_LAYER_EDGE_POOL, names, ws, bs, dims)
+                set_features = layer.edge_mlp_max(
+                    point_features.contiguous(), point_coordinates.contiguous(), point_coordinates.contiguous(),
+                    _i32(keypoint_indices.reshape(-1)), _i32(src), _i32(dst), num_keypoints,
+                    trusted=_ctx.trusted_edges)
             else:
                 # op-by-op composition, gnn.py:256-277
                 psf = _lib.gather_rows(point_features.contiguous(), _i32(src))
@@ -285,11 +352,13 @@ class GraphNetAutoCenter(object):
                 dest_coordinates = (source_coordinates + offset).contiguous()
         with variable_scope('extract_vertex_features'):
             if self._fusable(edge_MLP_normalization_type, edge_MLP_activation_type):
-                ws, bs = _take_mlp_weights(len(edge_MLP_depth_list))
-                aggregated_edge_features = _lib.edge_mlp_max(
-                    _PG_EDGE_GNN, input_vertex_features.contiguous(), source_coordinates, dest_coordinates,
-                    None, _i32(src), _i32(dst), num_vertices, ws, bs, precision=get_precision(),
-                    trusted=_ctx.trusted_edges)
+                names, ws, bs = _take_mlp(len(edge_MLP_depth_list))
+                dims = [input_vertex_features.shape[1] + 3] + [int(k) for k in edge_MLP_depth_list]
+                assert _mlp_dims(ws, bs, edge_MLP_depth_list) == dims, 'edge MLP input width mismatch'
+                layer = _prepared(_lib.PG_LAYER_EDGE_GNN, names, ws, bs, dims)
+                aggregated_edge_features = layer.edge_mlp_max(
+                    input_vertex_features.contiguous(), source_coordinates, dest_coordinates, None, _i32(src),
+                    _i32(dst), num_vertices, trusted=_ctx.trusted_edges)
             else:
                 # op-by-op composition, gnn.py:338-365
                 s_feat = _lib.gather_rows(input_vertex_features.contiguous(), _i32(src))

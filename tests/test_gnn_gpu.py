@@ -78,7 +78,9 @@ def test_fully_connected_vs_oracle(precision):
                                            precision=pointgnn_b200.get_precision()).cpu().numpy()
                 assert got.shape == want.shape and np.abs(got - want).max() < tol, (m, k, n, relu)
     if precision == 'bf16x3':
-        assert _lib.tc_launch_count(1) - dense0 >= 6 * 4      # the wide shapes went through tcgen05
+        # (257,300,300), (255,256,256), (256,300,64), (33,128,300) x 4 bias/residual combinations; the others are
+        # K % 4 != 0, K < 64, N < 8 or too wide for resident weights and take the FFMA kernel
+        assert _lib.tc_launch_count(1) - dense0 >= 4 * 4
     pointgnn_b200.set_precision('fp32')
 
 

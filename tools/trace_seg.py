@@ -16,6 +16,3 @@ for t in range(1, 6):
 print('epilogue warp 0 of rank 0 (ns): waited for tmem_full | D1 | D2')
 for t in range(1, 6):
     print('  tile %d: waited %5d | D1 %5d | D2 %5d' % (t, e0[t, 1] - e0[t, 0], e0[t, 2] - e0[t, 1], f0[t, 0] - e0[t, 2]))
-print('producer pt0 rank 0, own iterations (ns): compute | wait empty | publish')
-for i in range(12, 24):
-    print('  %3d: compute %5d wait %5d publish %5d' % (i, pr[i, 0] - pr[i - 1, 2], pr[i, 1] - pr[i, 0], pr[i, 2] - pr[i, 1]))
