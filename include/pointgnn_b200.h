@@ -117,6 +117,24 @@ PG_API int pg_radius_graph(const float* points, const int32_t* point_frame_ptr, 
                     int64_t num_centers, double radius, int32_t* out_row_ptr, int32_t* out_src,
                     int32_t* out_dst, int64_t capacity, int64_t* out_num_edges_host, void* stream);
 
+/*
+ * gen_multi_level_local_graph_v3 (graph_gen.py:155-195) for the two-level structure of every shipped
+ * config - level 0: original cloud -> keypoints of ONE voxel scale (radius0), level 1: those keypoints
+ * -> themselves (radius1; equal consecutive scales, graph_gen.py:76-81) - as ONE call with ONE host
+ * round trip.  Keypoint and edge counts stay on the device between the stages; the caller passes
+ * over-sized buffers (kp_capacity <= num_points rows, capacity0 / capacity1 edges) and gets
+ * out_sizes_host = {K, E0, E1}.  PG_ERR_CAPACITY (sizes filled in) means a buffer was too small and the
+ * call must be repeated with larger ones.  Outputs as pg_voxel_keypoints / pg_radius_graph:
+ *   out_keypoint_idx [K], out_kp_frame_ptr [num_frames+1], out_kp_xyz [K,3] = xyz[out_keypoint_idx],
+ *   out_row_ptr{0,1} [kp_capacity+1] (entries beyond K repeat E), out_src / out_dst [E] per level.
+ */
+PG_API int pg_multi_level_graph(const float* xyz, const int32_t* frame_ptr, int32_t num_frames,
+                         int64_t num_points, const double* voxel_size_host, double radius0, double radius1,
+                         int32_t* out_keypoint_idx, int64_t kp_capacity, int32_t* out_kp_frame_ptr,
+                         float* out_kp_xyz, int32_t* out_row_ptr0, int32_t* out_src0, int32_t* out_dst0,
+                         int64_t capacity0, int32_t* out_row_ptr1, int32_t* out_src1, int32_t* out_dst1,
+                         int64_t capacity1, int64_t* out_sizes_host, void* stream);
+
 /* ------------------------------------------------------------------------ *
  * GNN ops  (reference models/gnn.py)
  * ------------------------------------------------------------------------ */

@@ -85,8 +85,8 @@ def _segment_max(x, dst, num):
 
 
 def predict(weights, layer_configs, num_classes, box_encoding_len, features, coords, keypoints, edges,
-            chunk=1 << 19):
-    torch.set_num_threads(os.cpu_count() or 1)
+            chunk=1 << 19, num_threads=None):
+    torch.set_num_threads(num_threads or os.cpu_count() or 1)
     w = _W(weights)
     f = torch.from_numpy(np.ascontiguousarray(features, dtype=np.float32))
     coords = [torch.from_numpy(np.ascontiguousarray(c, dtype=np.float32)) for c in coords]

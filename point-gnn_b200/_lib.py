@@ -36,6 +36,10 @@ SIGNATURES = {
                                             ctypes.c_double, c_i32p, c_i64, c_i32p, c_i32p, ctypes.c_void_p]),
     'pg_radius_graph': (ctypes.c_int, [c_f32p, c_i32p, c_f32p, c_i32p, c_i32, c_i64, c_i64, ctypes.c_double,
                                        c_i32p, c_i32p, c_i32p, c_i64, ctypes.POINTER(c_i64), ctypes.c_void_p]),
+    'pg_multi_level_graph': (ctypes.c_int, [c_f32p, c_i32p, c_i32, c_i64, ctypes.POINTER(ctypes.c_double),
+                                            ctypes.c_double, ctypes.c_double, c_i32p, c_i64, c_i32p, c_f32p,
+                                            c_i32p, c_i32p, c_i32p, c_i64, c_i32p, c_i32p, c_i32p, c_i64,
+                                            ctypes.POINTER(c_i64), ctypes.c_void_p]),
     'pg_scatter_max': (ctypes.c_int, [c_f32p, c_i32p, c_i64, c_i32, c_i64, c_f32p, ctypes.c_void_p]),
     'pg_gather_rows': (ctypes.c_int, [c_f32p, c_i64, c_i32, c_i32p, c_i64, c_f32p, ctypes.c_void_p]),
     'pg_fully_connected': (ctypes.c_int, [c_f32p, c_i64, c_i32, c_f32p, c_f32p, c_i32, c_i32, c_f32p, c_f32p,
@@ -174,6 +178,53 @@ def radius_graph(points, point_frame_ptr, centers, center_frame_ptr, radius):
     _edge_capacity[key] = max(_edge_capacity.get(key, 0), int(e.value * 1.25) + 1024)
     # rows of buf are src / dst; the [E,2] transpose view of this slice has contiguous columns
     return row_ptr, buf[:, :e.value]
+
+
+_graph_capacity = {}
+
+
+def multi_level_graph(xyz, frame_ptr, voxel_size, radius0, radius1):
+    """pg_multi_level_graph: keypoints + both radius graphs in one call with one host round trip.
+    -> (kp_idx [K] int32, kp_frame_ptr [F+1] int32, kp_xyz [K,3], edges0 [2,E0], edges1 [2,E1])."""
+    lib = load()
+    n = xyz.shape[0]
+    num_frames = frame_ptr.numel() - 1
+    dev = xyz.device
+    key = (dev.index, int(n), tuple(float(v) for v in voxel_size), float(radius0), float(radius1))
+    # buffer sizes: 1.25 x the largest result seen for this problem shape (first call: generous guesses)
+    kcap, cap0, cap1 = _graph_capacity.get(key, (min(n, max(4096, n // 4)), 32 * n, 48 * n))
+    vs = (ctypes.c_double * 3)(*[float(v) for v in voxel_size])
+    sizes = (c_i64 * 3)()
+    while True:
+        kcap = min(int(kcap), n)
+        kp_idx = torch.empty(kcap, dtype=torch.int32, device=dev)
+        kp_fp = torch.empty(num_frames + 1, dtype=torch.int32, device=dev)
+        kp_xyz = torch.empty((kcap, 3), dtype=torch.float32, device=dev)
+        rp0 = torch.empty(kcap + 1, dtype=torch.int32, device=dev)
+        rp1 = torch.empty(kcap + 1, dtype=torch.int32, device=dev)
+        e0 = torch.empty((2, int(cap0)), dtype=torch.int32, device=dev)
+        e1 = torch.empty((2, int(cap1)), dtype=torch.int32, device=dev)
+        code = lib.pg_multi_level_graph(
+            _ptr(xyz, torch.float32, 'xyz'), _ptr(frame_ptr, torch.int32, 'frame_ptr'), num_frames, n, vs,
+            float(radius0), float(radius1), _ptr(kp_idx, torch.int32, 'kp_idx'), kcap,
+            _ptr(kp_fp, torch.int32, 'kp_fp'), _ptr(kp_xyz, torch.float32, 'kp_xyz'),
+            _ptr(rp0, torch.int32, 'rp0'), ctypes.c_void_p(e0[0].data_ptr()), ctypes.c_void_p(e0[1].data_ptr()), int(cap0),
+            _ptr(rp1, torch.int32, 'rp1'), ctypes.c_void_p(e1[0].data_ptr()), ctypes.c_void_p(e1[1].data_ptr()), int(cap1),
+            sizes, _stream())
+        k, n0, n1 = int(sizes[0]), int(sizes[1]), int(sizes[2])
+        if code == PG_ERR_CAPACITY:
+            if k > kcap:      # the edge counts were computed on a truncated keypoint set: scale them up too
+                cap0, cap1 = max(cap0, int(n0 * 1.3 * k / kcap) + 1024), max(cap1, int(n1 * 1.7 * k / kcap) + 1024)
+                kcap = int(k * 1.25) + 64
+            else:
+                cap0, cap1 = max(cap0, int(n0 * 1.25) + 1024), max(cap1, int(n1 * 1.25) + 1024)
+            continue
+        _check(code)
+        break
+    old = _graph_capacity.get(key, (0, 0, 0))
+    _graph_capacity[key] = (max(old[0], int(k * 1.25) + 64), max(old[1], int(n0 * 1.25) + 1024),
+                            max(old[2], int(n1 * 1.25) + 1024))
+    return kp_idx[:k], kp_fp, kp_xyz[:k], e0[:, :n0], e1[:, :n1]
 
 
 def radius_graph_two_pass(points, point_frame_ptr, centers, center_frame_ptr, radius):

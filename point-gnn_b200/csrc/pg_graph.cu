@@ -98,14 +98,23 @@ __device__ inline void cell_of(const GridSpec& g, const uint32_t* __restrict__ b
   *iz = (long long)floor(__ddiv_rn(__dsub_rn(double(z), oz), g.cell[2]));
 }
 
+// `n_valid` (optional, device): only rows [0, *n_valid) of the n-row buffer hold points (a point set whose size is
+// still on the device, e.g. the keypoints of the same call); the others get the key of frame `num_frames`, which
+// sorts behind every real cell and is never looked up.
 __global__ void point_keys_kernel(const float* __restrict__ xyz, const int32_t* __restrict__ frame_ptr,
-                                  int num_frames, int64_t n, GridSpec g,
+                                  int num_frames, int64_t n, const int32_t* __restrict__ n_valid, GridSpec g,
                                   const uint32_t* __restrict__ bounds, uint64_t* __restrict__ keys,
                                   int32_t* __restrict__ vals, int* __restrict__ range_error) {
   int64_t i = int64_t(blockIdx.x) * blockDim.x + threadIdx.x;
   if (i >= n) return;
+  const int64_t nv = n_valid ? int64_t(*n_valid) : n;
   // the caller's frame partition must run from 0 to n (checked here instead of with a host round trip)
-  if (i == 0 && (frame_ptr[0] != 0 || int64_t(frame_ptr[num_frames]) != n)) atomicOr(range_error, kErrFramePtr);
+  if (i == 0 && (frame_ptr[0] != 0 || int64_t(frame_ptr[num_frames]) != nv)) atomicOr(range_error, kErrFramePtr);
+  if (i >= nv) {
+    keys[i] = make_key(uint32_t(num_frames), 0, 0, 0);
+    vals[i] = int32_t(i);
+    return;
+  }
   const int f = find_frame(frame_ptr, num_frames, i);
   long long ix, iy, iz;
   cell_of(g, bounds, f, xyz[3 * i], xyz[3 * i + 1], xyz[3 * i + 2], &ix, &iy, &iz);
@@ -246,12 +255,16 @@ struct CenterCell {
 template <bool kFill>
 __global__ void __launch_bounds__(256) radius_query_kernel(
     SortedGrid g, GridSpec spec, const uint32_t* __restrict__ bounds, const float* __restrict__ centers,
-    const int32_t* __restrict__ center_frame_ptr, int num_frames, int64_t num_centers, double r2,
-    int32_t* __restrict__ counts, const int32_t* __restrict__ row_ptr, int32_t* __restrict__ out_src,
-    int* __restrict__ err) {
+    const int32_t* __restrict__ center_frame_ptr, int num_frames, int64_t num_centers_cap,
+    const int32_t* __restrict__ num_centers_dev, double r2, int32_t* __restrict__ counts,
+    const int32_t* __restrict__ row_ptr, int32_t* __restrict__ out_src, int64_t capacity, int* __restrict__ err,
+    unsigned long long* __restrict__ total64) {
   const int lane = threadIdx.x & 31;
   const int64_t c = (int64_t(blockIdx.x) * blockDim.x + threadIdx.x) >> 5;
-  if (c >= num_centers) return;
+  // the number of centres may still be on the device (keypoints of the same call): launch for the capacity
+  const int64_t num_centers = num_centers_dev ? int64_t(*num_centers_dev) : num_centers_cap;
+  if (c >= num_centers || c >= num_centers_cap) return;
+  if (kFill && int64_t(row_ptr[min(num_centers, num_centers_cap)]) > capacity) return;   // edge buffer too small: reported by the host
   if (!kFill && c == 0 && lane == 0 &&
       (center_frame_ptr[0] != 0 || int64_t(center_frame_ptr[num_frames]) != num_centers))
     atomicOr(err, kErrCenterPtr);
@@ -286,7 +299,10 @@ __global__ void __launch_bounds__(256) radius_query_kernel(
       }
     }
   }
-  if (!kFill && lane == 0) counts[c] = total;
+  if (!kFill && lane == 0) {
+    counts[c] = total;
+    atomicAdd(total64, (unsigned long long)total);   // 64-bit edge total: the int32 row_ptr scan may wrap
+  }
 }
 
 // Sort every CSR row ascending (canonical order) and expand the destination index.
@@ -301,9 +317,10 @@ constexpr int kWarpRowMax = 1024;   // rows up to this length are sorted by one 
 // entries, and the block-per-row version spent its time in 36+ __syncthreads per row).  Also expands dst.
 __global__ void __launch_bounds__(256) sort_rows_warp_kernel(const int32_t* __restrict__ row_ptr, int64_t num_rows,
                                                               int32_t* __restrict__ src, int32_t* __restrict__ dst,
-                                                              int* __restrict__ has_long_rows) {
+                                                              int* __restrict__ has_long_rows, int64_t capacity) {
   __shared__ int32_t srows[8][kWarpRowMax];
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  if (int64_t(row_ptr[num_rows]) > capacity) return;      // the edge buffer was too small: nothing was filled
   int32_t* a = srows[warp];
   for (int64_t r = int64_t(blockIdx.x) * 8 + warp; r < num_rows; r += int64_t(gridDim.x) * 8) {
     const int b = row_ptr[r], e = row_ptr[r + 1];
@@ -334,9 +351,9 @@ __global__ void __launch_bounds__(256) sort_rows_warp_kernel(const int32_t* __re
 
 __global__ void __launch_bounds__(256) sort_rows_kernel(const int32_t* __restrict__ row_ptr, int64_t num_rows,
                                                          int32_t* __restrict__ src, int32_t* __restrict__ dst,
-                                                         const int* __restrict__ has_long_rows) {
+                                                         const int* __restrict__ has_long_rows, int64_t capacity) {
   extern __shared__ int32_t srow[];
-  if (*has_long_rows == 0) return;                      // the usual case: every row was sorted by a warp
+  if (*has_long_rows == 0 || int64_t(row_ptr[num_rows]) > capacity) return;                      // the usual case: every row was sorted by a warp
   for (int64_t r = blockIdx.x; r < num_rows; r += gridDim.x) {
     const int b = row_ptr[r], e = row_ptr[r + 1];
     const int len = e - b;
@@ -370,6 +387,17 @@ __global__ void __launch_bounds__(256) sort_rows_kernel(const int32_t* __restric
   }
 }
 
+// coordinates of the selected keypoints (count still on the device)
+__global__ void gather_keypoints_kernel(const float* __restrict__ xyz, const int32_t* __restrict__ kp_idx,
+                                        const int32_t* __restrict__ num_kp, int64_t capacity, float* __restrict__ out) {
+  const int64_t v = int64_t(blockIdx.x) * blockDim.x + threadIdx.x;
+  if (v >= capacity || v >= *num_kp) return;
+  const int64_t j = kp_idx[v];
+  out[3 * v + 0] = xyz[3 * j + 0];
+  out[3 * v + 1] = xyz[3 * j + 1];
+  out[3 * v + 2] = xyz[3 * j + 2];
+}
+
 // ---- host-side building blocks ----------------------------------------------------------------
 struct BuiltGrid {
   Temp bounds, keys_a, keys_b, vals_a, vals_b, sorted_pts, head, head_scan, cell_key, cell_start, cub_tmp, err;
@@ -377,8 +405,8 @@ struct BuiltGrid {
 };
 
 int build_grid(const float* xyz, const int32_t* frame_ptr, int num_frames, int64_t n, const GridSpec& spec,
-               cudaStream_t s, BuiltGrid* out) {
-  PG_REQUIRE(num_frames >= 1 && num_frames <= 65535, "num_frames=%d out of range [1,65535]", num_frames);
+               cudaStream_t s, BuiltGrid* out, const int32_t* n_valid = nullptr) {
+  PG_REQUIRE(num_frames >= 1 && num_frames <= 65534, "num_frames=%d out of range [1,65534]", num_frames);
   PG_REQUIRE(n >= 1 && n < (int64_t(1) << 31), "num_points=%lld out of range", (long long)n);
   PG_CUDA_OK(out->bounds.alloc(sizeof(uint32_t) * 3 * num_frames, s));
   PG_CUDA_OK(out->keys_a.alloc(sizeof(uint64_t) * n, s));
@@ -399,13 +427,13 @@ int build_grid(const float* xyz, const int32_t* frame_ptr, int num_frames, int64
   const int blocks_per_frame = int(std::min<int64_t>(std::max<int64_t>(1, ceil_div(n / num_frames, 1024)), 64));
   frame_min_kernel<<<dim3(blocks_per_frame, num_frames), 256, 0, s>>>(xyz, frame_ptr, n, bounds);
   PG_LAUNCH_CHECK();
-  point_keys_kernel<<<ceil_div(n, 256), 256, 0, s>>>(xyz, frame_ptr, num_frames, n, spec, bounds,
+  point_keys_kernel<<<ceil_div(n, 256), 256, 0, s>>>(xyz, frame_ptr, num_frames, n, n_valid, spec, bounds,
                                                       out->keys_a.as<uint64_t>(), out->vals_a.as<int32_t>(),
                                                       out->err.as<int>());
   PG_LAUNCH_CHECK();
   // radix sort (key, original index); stable, so equal keys keep ascending point index
   int frame_bits = 1;
-  while ((1 << frame_bits) < num_frames) ++frame_bits;
+  while ((1 << frame_bits) < num_frames + 1) ++frame_bits;     // + 1: the key of rows beyond n_valid
   const int end_bit = 48 + frame_bits;
   size_t tmp_bytes = 0;
   PG_CUDA_OK(cub::DeviceRadixSort::SortPairs(nullptr, tmp_bytes, out->keys_a.as<uint64_t>(), out->keys_b.as<uint64_t>(),
@@ -507,24 +535,32 @@ extern "C" int pg_voxel_keypoints(const float* xyz, const int32_t* frame_ptr, in
 
 static int radius_count_impl(RadiusPlan& plan, const float* centers, const int32_t* center_frame_ptr, int num_frames,
                              int64_t num_centers, int32_t* out_row_ptr, int64_t* out_num_edges_host, cudaStream_t s) {
-  Temp counts, tmp;
+  Temp counts, tmp, total;
   PG_CUDA_OK(counts.alloc(sizeof(int32_t) * (num_centers + 1), s));
   PG_CUDA_OK(cudaMemsetAsync(counts.ptr, 0, sizeof(int32_t) * (num_centers + 1), s));
+  PG_CUDA_OK(total.alloc(sizeof(unsigned long long), s));
+  PG_CUDA_OK(cudaMemsetAsync(total.ptr, 0, sizeof(unsigned long long), s));
   radius_query_kernel<false><<<ceil_div(num_centers * 32, 256), 256, 0, s>>>(
       plan.grid.view, plan.spec, plan.grid.bounds.as<uint32_t>(), centers, center_frame_ptr, num_frames, num_centers,
-      plan.r2, counts.as<int32_t>(), nullptr, nullptr, plan.grid.err.as<int>());
+      nullptr, plan.r2, counts.as<int32_t>(), nullptr, nullptr, 0, plan.grid.err.as<int>(),
+      total.as<unsigned long long>());
   PG_LAUNCH_CHECK();
   size_t bytes = 0;
   PG_CUDA_OK(cub::DeviceScan::ExclusiveSum(nullptr, bytes, counts.as<int32_t>(), out_row_ptr, int(num_centers + 1), s));
   PG_CUDA_OK(tmp.alloc(bytes, s));
   PG_CUDA_OK(cub::DeviceScan::ExclusiveSum(tmp.ptr, bytes, counts.as<int32_t>(), out_row_ptr, int(num_centers + 1), s));
   count_launch(2);
-  int32_t h[2] = {0, 0};   // the one host round trip of the graph build: E and the error word
-  PG_CUDA_OK(cudaMemcpyAsync(&h[0], out_row_ptr + num_centers, sizeof(int32_t), cudaMemcpyDeviceToHost, s));
-  PG_CUDA_OK(cudaMemcpyAsync(&h[1], plan.grid.err.ptr, sizeof(int32_t), cudaMemcpyDeviceToHost, s));
+  unsigned long long h_total = 0;   // the one host round trip of the graph build: E (64 bit) and the error word
+  int32_t h_err = 0;
+  PG_CUDA_OK(cudaMemcpyAsync(&h_total, total.ptr, sizeof(h_total), cudaMemcpyDeviceToHost, s));
+  PG_CUDA_OK(cudaMemcpyAsync(&h_err, plan.grid.err.ptr, sizeof(int32_t), cudaMemcpyDeviceToHost, s));
   PG_CUDA_OK(cudaStreamSynchronize(s));
-  if (int rc = graph_error(h[1])) return rc;
-  *out_num_edges_host = h[0];
+  if (int rc = graph_error(h_err)) return rc;
+  *out_num_edges_host = int64_t(h_total);
+  if (h_total > 0x7fffffffull) {    // row_ptr is int32 (the reference's int32 edge arrays, train.py:131)
+    set_error("radius graph has %llu edges: more than int32 row_ptr can index; split the batch", h_total);
+    return PG_ERR_RANGE;
+  }
   return PG_OK;
 }
 
@@ -533,18 +569,19 @@ static int radius_fill_impl(RadiusPlan& plan, const float* centers, const int32_
                             cudaStream_t s) {
   radius_query_kernel<true><<<ceil_div(num_centers * 32, 256), 256, 0, s>>>(
       plan.grid.view, plan.spec, plan.grid.bounds.as<uint32_t>(), centers, center_frame_ptr, num_frames, num_centers,
-      plan.r2, nullptr, row_ptr, out_src, nullptr);
+      nullptr, plan.r2, nullptr, row_ptr, out_src, int64_t(1) << 40, nullptr, nullptr);
   PG_LAUNCH_CHECK();
   const int wblocks = int(std::min<int64_t>(ceil_div(num_centers, 8), int64_t(num_sms()) * 6));
   Temp has_long;
   PG_CUDA_OK(has_long.alloc(sizeof(int), s));
   PG_CUDA_OK(cudaMemsetAsync(has_long.ptr, 0, sizeof(int), s));
-  sort_rows_warp_kernel<<<wblocks, 256, 0, s>>>(row_ptr, num_centers, out_src, out_dst, has_long.as<int>());
+  sort_rows_warp_kernel<<<wblocks, 256, 0, s>>>(row_ptr, num_centers, out_src, out_dst, has_long.as<int>(),
+                                                int64_t(1) << 40);
   PG_LAUNCH_CHECK();
   // rows longer than kWarpRowMax (dense full-360 clouds): one block per row
   const int blocks = int(std::min<int64_t>(num_centers, int64_t(num_sms()) * 4));
   sort_rows_kernel<<<blocks, 256, kRowSortMax * sizeof(int32_t), s>>>(row_ptr, num_centers, out_src, out_dst,
-                                                                      has_long.as<int>());
+                                                                      has_long.as<int>(), int64_t(1) << 40);
   PG_LAUNCH_CHECK();
   return PG_OK;
 }
@@ -595,4 +632,123 @@ extern "C" int pg_radius_graph(const float* points, const int32_t* point_frame_p
   if (*out_num_edges_host == 0) return PG_OK;
   PG_REQUIRE(out_src != nullptr, "pg_radius_graph: out_src is null");
   return radius_fill_impl(plan, centers, center_frame_ptr, num_frames, num_centers, out_row_ptr, out_src, out_dst, s);
+}
+
+
+// One radius level of pg_multi_level_graph: count -> scan -> fill -> row sort, the number of centres and the number
+// of edges staying on the device (`num_centers_dev`; E = out_row_ptr[kp_capacity]).
+static int radius_level_device(RadiusPlan& plan, const float* centers, const int32_t* center_frame_ptr, int num_frames,
+                               int64_t kp_capacity, const int32_t* num_centers_dev, int32_t* out_row_ptr,
+                               int32_t* out_src, int32_t* out_dst, int64_t capacity, unsigned long long* total64,
+                               cudaStream_t s) {
+  Temp counts, tmp, has_long;
+  PG_CUDA_OK(counts.alloc(sizeof(int32_t) * (kp_capacity + 1), s));
+  PG_CUDA_OK(cudaMemsetAsync(counts.ptr, 0, sizeof(int32_t) * (kp_capacity + 1), s));
+  const int qblocks = int(ceil_div(kp_capacity * 32, 256));
+  radius_query_kernel<false><<<qblocks, 256, 0, s>>>(plan.grid.view, plan.spec, plan.grid.bounds.as<uint32_t>(), centers,
+                                                     center_frame_ptr, num_frames, kp_capacity, num_centers_dev, plan.r2,
+                                                     counts.as<int32_t>(), nullptr, nullptr, 0, plan.grid.err.as<int>(),
+                                                     total64);
+  PG_LAUNCH_CHECK();
+  size_t bytes = 0;
+  PG_CUDA_OK(cub::DeviceScan::ExclusiveSum(nullptr, bytes, counts.as<int32_t>(), out_row_ptr, int(kp_capacity + 1), s));
+  PG_CUDA_OK(tmp.alloc(bytes, s));
+  PG_CUDA_OK(cub::DeviceScan::ExclusiveSum(tmp.ptr, bytes, counts.as<int32_t>(), out_row_ptr, int(kp_capacity + 1), s));
+  count_launch(2);
+  // rows beyond the real number of centres are empty, so row_ptr[c] == E for every c >= K
+  radius_query_kernel<true><<<qblocks, 256, 0, s>>>(plan.grid.view, plan.spec, plan.grid.bounds.as<uint32_t>(), centers,
+                                                    center_frame_ptr, num_frames, kp_capacity, num_centers_dev, plan.r2,
+                                                    nullptr, out_row_ptr, out_src, capacity, nullptr, nullptr);
+  PG_LAUNCH_CHECK();
+  PG_CUDA_OK(has_long.alloc(sizeof(int), s));
+  PG_CUDA_OK(cudaMemsetAsync(has_long.ptr, 0, sizeof(int), s));
+  const int wblocks = int(std::min<int64_t>(ceil_div(kp_capacity, 8), int64_t(num_sms()) * 6));
+  sort_rows_warp_kernel<<<wblocks, 256, 0, s>>>(out_row_ptr, kp_capacity, out_src, out_dst, has_long.as<int>(), capacity);
+  PG_LAUNCH_CHECK();
+  const int blocks = int(std::min<int64_t>(kp_capacity, int64_t(num_sms()) * 4));
+  sort_rows_kernel<<<blocks, 256, kRowSortMax * sizeof(int32_t), s>>>(out_row_ptr, kp_capacity, out_src, out_dst,
+                                                                      has_long.as<int>(), capacity);
+  PG_LAUNCH_CHECK();
+  return PG_OK;
+}
+
+extern "C" int pg_multi_level_graph(const float* xyz, const int32_t* frame_ptr, int32_t num_frames, int64_t num_points,
+                                    const double* voxel_size_host, double radius0, double radius1,
+                                    int32_t* out_keypoint_idx, int64_t kp_capacity, int32_t* out_kp_frame_ptr,
+                                    float* out_kp_xyz, int32_t* out_row_ptr0, int32_t* out_src0, int32_t* out_dst0,
+                                    int64_t capacity0, int32_t* out_row_ptr1, int32_t* out_src1, int32_t* out_dst1,
+                                    int64_t capacity1, int64_t* out_sizes_host, void* stream) {
+  cudaStream_t s = static_cast<cudaStream_t>(stream);
+  PG_REQUIRE(xyz && frame_ptr && voxel_size_host && out_keypoint_idx && out_kp_frame_ptr && out_kp_xyz && out_row_ptr0 &&
+                 out_row_ptr1 && out_sizes_host,
+             "pg_multi_level_graph: null argument");
+  PG_REQUIRE(out_src0 && out_dst0 && out_src1 && out_dst1 && capacity0 >= 1 && capacity1 >= 1,
+             "pg_multi_level_graph: edge buffers are required");
+  PG_REQUIRE(kp_capacity >= 1 && kp_capacity <= num_points, "pg_multi_level_graph: keypoint capacity out of range");
+  PG_REQUIRE(voxel_size_host[0] > 0 && voxel_size_host[1] > 0 && voxel_size_host[2] > 0, "voxel size must be positive");
+  // ---- keypoints (multi_layer_downsampling_select, graph_gen.py:49-90) ---------------------------
+  GridSpec vspec;
+  vspec.cell[0] = voxel_size_host[0];
+  vspec.cell[1] = voxel_size_host[1];
+  vspec.cell[2] = voxel_size_host[2];
+  vspec.origin_off = 0.5;
+  BuiltGrid vgrid;
+  if (int rc = build_grid(xyz, frame_ptr, num_frames, num_points, vspec, s, &vgrid)) return rc;
+  voxel_keypoint_kernel<<<ceil_div(num_points, 128), 128, 0, s>>>(vgrid.view, vspec, vgrid.bounds.as<uint32_t>(),
+                                                                    out_keypoint_idx, kp_capacity);
+  PG_LAUNCH_CHECK();
+  frame_ranges_kernel<<<ceil_div(num_frames + 1, 128), 128, 0, s>>>(vgrid.view.cell_key, vgrid.view.num_cells, num_frames,
+                                                                     out_kp_frame_ptr);
+  PG_LAUNCH_CHECK();
+  const int32_t* k_dev = vgrid.view.num_cells;      // K = number of occupied voxels, on the device
+  gather_keypoints_kernel<<<ceil_div(kp_capacity, 256), 256, 0, s>>>(xyz, out_keypoint_idx, k_dev, kp_capacity, out_kp_xyz);
+  PG_LAUNCH_CHECK();
+  Temp totals;
+  PG_CUDA_OK(totals.alloc(2 * sizeof(unsigned long long), s));
+  PG_CUDA_OK(cudaMemsetAsync(totals.ptr, 0, 2 * sizeof(unsigned long long), s));
+  // ---- level 0: original points -> keypoints (graph_gen.py:186-194, graph_level 0) -----------------
+  RadiusPlan plan0;
+  if (int rc = radius_prepare(xyz, frame_ptr, num_frames, num_points, radius0, s, &plan0)) return rc;
+  if (int rc = radius_level_device(plan0, out_kp_xyz, out_kp_frame_ptr, num_frames, kp_capacity, k_dev, out_row_ptr0,
+                                   out_src0, out_dst0, capacity0, totals.as<unsigned long long>(), s))
+    return rc;
+  // ---- level 1: keypoints -> keypoints (same scale: graph_gen.py:76-81 makes level 2 = level 1) ------
+  RadiusPlan plan1;
+  PG_REQUIRE(radius1 > 0.0, "radius must be positive");
+  plan1.spec.cell[0] = plan1.spec.cell[1] = plan1.spec.cell[2] = radius1 * kCellSlack;
+  plan1.spec.origin_off = 0.0;
+  plan1.r2 = radius1 * radius1;
+  if (int rc = build_grid(out_kp_xyz, out_kp_frame_ptr, num_frames, kp_capacity, plan1.spec, s, &plan1.grid, k_dev)) return rc;
+  if (int rc = radius_level_device(plan1, out_kp_xyz, out_kp_frame_ptr, num_frames, kp_capacity, k_dev, out_row_ptr1,
+                                   out_src1, out_dst1, capacity1, totals.as<unsigned long long>() + 1, s))
+    return rc;
+  // ---- the ONE host round trip: K, E0, E1 and the error words ---------------------------------------
+  int32_t h_k = 0, h_err[3] = {0, 0, 0};
+  unsigned long long h_tot[2] = {0, 0};
+  PG_CUDA_OK(cudaMemcpyAsync(&h_k, k_dev, sizeof(int32_t), cudaMemcpyDeviceToHost, s));
+  PG_CUDA_OK(cudaMemcpyAsync(h_tot, totals.ptr, sizeof(h_tot), cudaMemcpyDeviceToHost, s));
+  PG_CUDA_OK(cudaMemcpyAsync(&h_err[0], vgrid.err.ptr, sizeof(int32_t), cudaMemcpyDeviceToHost, s));
+  PG_CUDA_OK(cudaMemcpyAsync(&h_err[1], plan0.grid.err.ptr, sizeof(int32_t), cudaMemcpyDeviceToHost, s));
+  PG_CUDA_OK(cudaMemcpyAsync(&h_err[2], plan1.grid.err.ptr, sizeof(int32_t), cudaMemcpyDeviceToHost, s));
+  PG_CUDA_OK(cudaStreamSynchronize(s));
+  out_sizes_host[0] = h_k;
+  out_sizes_host[1] = int64_t(h_tot[0]);
+  out_sizes_host[2] = int64_t(h_tot[1]);
+  if (h_k > kp_capacity) {
+    // the downstream levels only saw the first kp_capacity keypoints: everything must be redone with a larger buffer
+    set_error("keypoint buffer too small: need %d, capacity %lld", h_k, (long long)kp_capacity);
+    return PG_ERR_CAPACITY;
+  }
+  for (int i = 0; i < 3; ++i)
+    if (int rc = graph_error(h_err[i])) return rc;
+  if (h_tot[0] > 0x7fffffffull || h_tot[1] > 0x7fffffffull) {
+    set_error("radius graph has more edges than int32 row_ptr can index; split the batch");
+    return PG_ERR_RANGE;
+  }
+  if (int64_t(h_tot[0]) > capacity0 || int64_t(h_tot[1]) > capacity1) {
+    set_error("edge buffer too small: need %llu / %llu, capacity %lld / %lld", h_tot[0], h_tot[1], (long long)capacity0,
+              (long long)capacity1);
+    return PG_ERR_CAPACITY;
+  }
+  return PG_OK;
 }

@@ -105,15 +105,46 @@ def _radius_edges(points, point_fp, centers, center_fp, radius, num_neighbors,
     if num_neighbors > 0:
         raise NotImplementedError('num_neighbors > 0 is the training-time random neighbour cap '
                                   '(graph_gen.py:210-214); inference configs use -1')
-    if scale is not None:
-        s = torch.as_tensor(np.asarray(scale, dtype=np.float32), device=points.device)
-        points = (points / s).contiguous()          # graph_gen.py:203-206
-        centers = (centers / s).contiguous()
+    if scale is not None and not np.all(np.asarray(scale, dtype=np.float64) == 1.0):
+        # graph_gen.py:203-206 divides in float64 and builds the tree on float64 coordinates; dividing in
+        # float32 here would move boundary edges.  No shipped config passes `scale`.
+        raise NotImplementedError('per-axis `scale` of gen_disjointed_rnn_local_graph_v3 is not built '
+                                  '(unused by every shipped config)')
     _, edges = _lib.radius_graph(points, point_fp, centers, center_fp, radius)
     edges = edges.t()     # [E,2] view whose columns (src, dst) are contiguous
     # index ranges are guaranteed by construction: lets model.predict skip the per-layer range check
     edges._pg_trusted = (int(points.shape[0]), int(centers.shape[0]), edges._version)
     return edges
+
+
+def _is_two_level(level_configs, add_rnd3d):
+    """level 0: cloud -> keypoints of one scale, level 1: the same keypoints -> themselves (configs/*_config)."""
+    if add_rnd3d or len(level_configs) != 2:
+        return False
+    a, b = level_configs
+    if a['graph_level'] != 0 or b['graph_level'] != 1 or not np.isclose(a['graph_scale'], b['graph_scale']):
+        return False
+    for c in (a, b):
+        kw = c['graph_gen_kwargs']
+        if kw.get('num_neighbors', -1) > 0 or kw.get('scale') is not None:
+            return False
+    return True
+
+
+def _two_level_graph(cloud, base_voxel_size, level_configs):
+    a, b = level_configs
+    idx, kp_fp, kp_xyz, e0, e1 = _lib.multi_level_graph(
+        cloud.xyz, cloud.frame_ptr, _voxel_vector(base_voxel_size, a['graph_scale']),
+        a['graph_gen_kwargs']['radius'], b['graph_gen_kwargs']['radius'])
+    n, k = int(cloud.xyz.shape[0]), int(kp_xyz.shape[0])
+    kidx0 = idx[:, None]
+    kidx0._pg_trusted = (n, kidx0._version)
+    kidx1 = torch.arange(k, dtype=torch.int32, device=kp_xyz.device)[:, None]
+    kidx1._pg_trusted = (k, kidx1._version)
+    edges0, edges1 = e0.t(), e1.t()
+    edges0._pg_trusted = (n, k, edges0._version)
+    edges1._pg_trusted = (k, k, edges1._version)
+    return ([cloud.xyz, kp_xyz, kp_xyz], [kidx0, kidx1], [edges0, edges1], [cloud.frame_ptr, kp_fp, kp_fp])
 
 
 def gen_disjointed_rnn_local_graph_v3(points_xyz, center_xyz, radius, num_neighbors,
@@ -137,16 +168,22 @@ def gen_multi_level_local_graph_v3(points_xyz, base_voxel_size, level_configs, a
         raise NotImplementedError("downsample_method='random' is training-only (graph_gen.py:92-153)")
     cloud = _Cloud(points_xyz, frame_ptr)
     scales = [config['graph_scale'] for config in level_configs]
-    vertex_coord_list, keypoint_indices_list, frame_ptr_list = _downsampling_select(
-        cloud, base_voxel_size, scales, add_rnd3d)
-    edges_list = []
     for config in level_configs:
-        graph_level = config['graph_level']
         if config['graph_gen_method'] != 'disjointed_rnn_local_graph_v3':
             raise KeyError(config['graph_gen_method'])
-        edges_list.append(_radius_edges(vertex_coord_list[graph_level], frame_ptr_list[graph_level],
-                                        vertex_coord_list[graph_level + 1], frame_ptr_list[graph_level + 1],
-                                        **config['graph_gen_kwargs']))
+    if _is_two_level(level_configs, add_rnd3d) and cloud.xyz.shape[0] > 0:
+        # the structure of every shipped config: ONE library call, one host round trip
+        vertex_coord_list, keypoint_indices_list, edges_list, frame_ptr_list = _two_level_graph(
+            cloud, base_voxel_size, level_configs)
+    else:
+        vertex_coord_list, keypoint_indices_list, frame_ptr_list = _downsampling_select(
+            cloud, base_voxel_size, scales, add_rnd3d)
+        edges_list = []
+        for config in level_configs:
+            graph_level = config['graph_level']
+            edges_list.append(_radius_edges(vertex_coord_list[graph_level], frame_ptr_list[graph_level],
+                                            vertex_coord_list[graph_level + 1], frame_ptr_list[graph_level + 1],
+                                            **config['graph_gen_kwargs']))
     if cloud.numpy_io:
         vertex_coord_list = [v.cpu().numpy() for v in vertex_coord_list]
         keypoint_indices_list = [k.cpu().numpy().astype(np.int64) for k in keypoint_indices_list]

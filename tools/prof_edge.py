@@ -12,6 +12,8 @@ from oracle import synth  # noqa: E402
 from pointgnn_b200 import _lib  # noqa: E402
 if os.environ.get('PG_USE_LAB_LIB'):      # lab build (make -C point-gnn_b200/csrc lab): in-kernel tracing via PG_TC_TRACE
     _lib.LIB_PATH = os.path.join(os.path.dirname(_lib.LIB_PATH), 'libpointgnn_b200_lab.so')
+if os.environ.get('PG_LIB_VARIANT'):      # experiment builds (tools/build_variant.sh NAME -DFLAG...): lab/<NAME>.so
+    _lib.LIB_PATH = os.path.join(ROOT, 'lab', os.environ['PG_LIB_VARIANT'] + '.so')
 from pointgnn_b200.models import graph_gen  # noqa: E402
 
 frames = int(sys.argv[1]) if len(sys.argv) > 1 else 8
@@ -30,15 +32,17 @@ ws = [torch.from_numpy(w[s + '/weights']).cuda(), torch.from_numpy(w[s + '_1/wei
 bs = [torch.from_numpy(w[s + '/biases']).cuda(), torch.from_numpy(w[s + '_1/biases']).cuda()]
 src, dst = edges[1][:, 0].contiguous(), edges[1][:, 1].contiguous()
 print('K', k, 'E1', src.numel())
+layer = _lib.PreparedLayer(_lib.PG_LAYER_EDGE_GNN, ws, bs, [303, 300, 300], prec)
 for _ in range(2):
-    _lib.edge_mlp_max(1, feats, coords[1], coords[1], None, src, dst, k, ws, bs, precision=prec)
+    layer.edge_mlp_max(feats, coords[1], coords[1], None, src, dst, k, trusted=True)
 torch.cuda.synchronize()
 a = torch.cuda.Event(enable_timing=True)
 b = torch.cuda.Event(enable_timing=True)
 a.record()
 for _ in range(reps):
-    _lib.edge_mlp_max(1, feats, coords[1], coords[1], None, src, dst, k, ws, bs, precision=prec)
+    layer.edge_mlp_max(feats, coords[1], coords[1], None, src, dst, k, trusted=True)
 b.record()
 b.synchronize()
 ms = a.elapsed_time(b) / reps
-print('edge_mlp_max precision %d: %.3f ms per call, %.1f algorithmic TFLOP/s' % (prec, ms, src.numel() * 361800 / ms / 1e9))
+print('prepared edge layer (P GEMM + fill + fused edge kernel) precision %d: %.3f ms per call, %.1f algorithmic TFLOP/s'
+      % (prec, ms, src.numel() * 361800 / ms / 1e9))
