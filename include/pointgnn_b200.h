@@ -260,6 +260,60 @@ PG_API int pg_layer_predictor(const pg_layer* layer, const float* x, int64_t m, 
 PG_API int pg_softmax_rows(const float* logits, int64_t num_rows, int32_t num_classes, float* out,
                     void* stream);
 
+/* ------------------------------------------------------------------------ *
+ * Post-processing: the step after the path (reference run.py:265-325)
+ * ------------------------------------------------------------------------ */
+
+/*
+ * classaware_all_class_box_decoding (models/box_encoding.py:265-299) for every (vertex, class) pair.
+ *   class_table_host  (host) [C][4] floats per class label: median l, h, w (box_encoding.py:211-229) and the
+ *                     yaw offset (0 for the "horizontal" label, pi/2 for the "vertical" one); l <= 0 marks
+ *                     labels that are not decoded (Background, DontCare).
+ *   out_boxes [K, C, 7] = (x, y, z, l, h, w, yaw), float32 arithmetic as the reference's NumPy code.
+ */
+PG_API int pg_decode_boxes(const float* box_encodings, const float* xyz, int64_t num_vertices,
+                    int32_t num_classes, const float* class_table_host, float* out_boxes, void* stream);
+
+/*
+ * Candidate selection + decoding + NMS for a batch of frames (run.py:265-325):
+ *   candidates      class c of vertex v iff 0 < c < C-1 and probs[v,c] > 1/C (run.py:281-284), labels 2/4/6
+ *                   folded onto 1/3/5 (run.py:291-293), decoded with pg_decode_boxes' rule;
+ *   NMS             nms.nms_boxes_3d_uncertainty (models/nms.py:133-170, 256-270) with
+ *                   overlapped_boxes_3d_fast_poly (nms.py:64-88) and top_k = -1: score-sorted greedy
+ *                   suppression inside a class; flags bit 0 (PG_NMS_MERGE): the kept box becomes the
+ *                   coordinate-wise median of itself and the boxes it suppresses; bit 1 (PG_NMS_RESCORE): its
+ *                   score grows by sum_j score_j * IoU(merged box, box_j).  flags 0 / 1 / 2 are nms_boxes_3d's
+ *                   siblings (nms.py:172-240).
+ *   frame_ptr [num_frames+1] partitions the K vertices; frames are processed independently.
+ * Outputs (caller buffers of `capacity` detections, frame by frame, in score order of the candidates):
+ *   out_label / out_box [.,7] / out_score / out_index (= flat v*C + c of the kept candidate, i.e.
+ *   box_indices[nms_indices] of run.py), out_det_frame_ptr [num_frames+1];
+ *   out_cand_index [K*(C-2)] + out_cand_frame_ptr [num_frames+1] (optional): all candidates in ascending
+ *   (v, c) order = run.py's box_indices (the KITTI writer's occlusion rescoring needs them, run.py:395-404);
+ *   out_sizes_host = {detections, candidates}.
+ * max_candidates_per_frame bounds the pairwise bit matrix; PG_ERR_CAPACITY when a frame exceeds it or the
+ * detection buffer is too small.  Two host round trips (matrix width, result size).
+ */
+#define PG_NMS_MERGE 1
+#define PG_NMS_RESCORE 2
+#define PG_NMS_INT_CORNERS 4   /* pg_nms_boxes_3d only: np.int32(corners * appr_factor), nms.py:114 */
+PG_API int pg_postprocess(const float* probs, const float* box_encodings, const float* xyz,
+                   const int32_t* frame_ptr, int32_t num_frames, int64_t num_vertices, int32_t num_classes,
+                   const float* class_table_host, double overlapped_thres, int32_t flags,
+                   int64_t max_candidates_per_frame, int32_t* out_label, float* out_box, float* out_score,
+                   int32_t* out_index, int64_t capacity, int32_t* out_det_frame_ptr,
+                   int32_t* out_cand_index, int32_t* out_cand_frame_ptr, int64_t* out_sizes_host,
+                   void* stream);
+
+/* The NMS stage alone on caller-provided boxes (models/nms.py:243-301's four entry points):
+ * class_labels / boxes [B,7] / scores, frame_ptr [num_frames+1] over the B boxes; out_index = position of the
+ * kept box in the input (the reference's `attributes=np.arange(B)` convention, run.py:305). */
+PG_API int pg_nms_boxes_3d(const int32_t* class_labels, const float* boxes, const float* scores,
+                    const int32_t* frame_ptr, int32_t num_frames, int64_t num_boxes, double overlapped_thres,
+                    double appr_factor, int32_t flags, int64_t max_candidates_per_frame, int32_t* out_label,
+                    float* out_box, float* out_score, int32_t* out_index, int64_t capacity,
+                    int32_t* out_det_frame_ptr, int64_t* out_sizes_host, void* stream);
+
 /* tcgen05 kernel launches so far (which: 0 = fused edge MLP + segment max, 1 = dense layer);
  * lets callers and tests verify that the tensor-core path, not the FFMA path, actually ran. */
 PG_API int64_t pg_tc_launch_count(int32_t which);

@@ -252,3 +252,43 @@ def postprocess_frame(probs, box_encodings, points_xyz, label_method, nms_overla
         return labels, boxes, scores
     lab, bx, sc, _ = nms_boxes_3d_uncertainty(labels, boxes, scores, nms_overlapped_thres, merge, rescore)
     return lab, bx, sc
+
+
+# ---------------------------------------------------------------------------------------------
+# seeded synthetic network outputs (clusters of proposals around a few objects)
+# ---------------------------------------------------------------------------------------------
+def synthetic_outputs(seed, num_objects=12, per_object=25, num_classes=4, spread=0.6):
+    """-> (points_xyz [K,3] f32, box_encodings [K,C,7] f32, probs [K,C] f32): K = num_objects * per_object
+    vertices scattered around object centres, each proposing a noisy box per class."""
+    rng = np.random.default_rng(seed)
+    centers = np.c_[rng.uniform(-20, 20, num_objects), rng.uniform(0.5, 2, num_objects), rng.uniform(5, 60, num_objects)]
+    k = num_objects * per_object
+    pts = (np.repeat(centers, per_object, axis=0) + rng.normal(0, spread, (k, 3))).astype(np.float32)
+    enc = rng.normal(0, 0.15, (k, num_classes, 7)).astype(np.float32)
+    probs = rng.dirichlet(np.ones(num_classes) * 0.6, k).astype(np.float32)
+    return pts, enc, probs
+
+
+def reference_postprocess_frame(be, nms, probs, box_encodings, points_xyz, label_method, thres, variant='uncertainty'):
+    """run.py:265-325 executed with the reference's OWN modules (be, nms = reference_modules())."""
+    num_classes = probs.shape[1]
+    label_map = LABEL_MAPS[label_method]
+    box_probs = probs
+    box_labels = np.tile(np.expand_dims(np.arange(num_classes), axis=0), (box_probs.shape[0], 1)).reshape((-1))
+    box_probs = box_probs.reshape((-1))
+    pred_boxes = box_encodings.reshape((-1, 1, 7))
+    xyz = np.tile(np.expand_dims(points_xyz, axis=1), (1, num_classes, 1)).reshape((-1, 3))
+    decoded = be.classaware_all_class_box_decoding(np.expand_dims(box_labels, axis=1), xyz, pred_boxes, label_map)
+    mask = (box_labels > 0) * (box_labels < num_classes - 1) * (box_probs > 1. / num_classes)
+    idx = np.nonzero(mask)[0]
+    lab = box_labels[idx]
+    sc = box_probs[idx]
+    dec = decoded[idx, 0]
+    lab[lab == 2] = 1
+    lab[lab == 4] = 3
+    lab[lab == 6] = 5
+    fn = {'uncertainty': nms.nms_boxes_3d_uncertainty, 'merge_only': nms.nms_boxes_3d_merge_only,
+          'score_only': nms.nms_boxes_3d_score_only, 'plain': nms.nms_boxes_3d}[variant]
+    out = fn(lab, dec, sc, overlapped_fn=nms.overlapped_boxes_3d_fast_poly, overlapped_thres=thres, appr_factor=100.0,
+             top_k=-1, attributes=np.arange(len(idx)))
+    return dict(label=out[0], box=out[1], score=out[2], nms_index=out[3], cand_index=idx, decoded=decoded[:, 0])

@@ -49,6 +49,15 @@ SIGNATURES = {
                                        ctypes.POINTER(c_i32), c_i32, c_f32p, c_i32, ctypes.c_void_p]),
     'pg_softmax_rows': (ctypes.c_int, [c_f32p, c_i64, c_i32, c_f32p, ctypes.c_void_p]),
     'pg_check_edges': (ctypes.c_int, [c_i32p, c_i32p, c_i64, c_i64, c_i64, ctypes.c_void_p]),
+    'pg_decode_boxes': (ctypes.c_int, [c_f32p, c_f32p, c_i64, c_i32, ctypes.POINTER(ctypes.c_float), c_f32p,
+                                       ctypes.c_void_p]),
+    'pg_postprocess': (ctypes.c_int, [c_f32p, c_f32p, c_f32p, c_i32p, c_i32, c_i64, c_i32,
+                                      ctypes.POINTER(ctypes.c_float), ctypes.c_double, c_i32, c_i64, c_i32p, c_f32p,
+                                      c_f32p, c_i32p, c_i64, c_i32p, c_i32p, c_i32p, ctypes.POINTER(c_i64),
+                                      ctypes.c_void_p]),
+    'pg_nms_boxes_3d': (ctypes.c_int, [c_i32p, c_f32p, c_f32p, c_i32p, c_i32, c_i64, ctypes.c_double,
+                                       ctypes.c_double, c_i32, c_i64, c_i32p, c_f32p, c_f32p, c_i32p, c_i64, c_i32p,
+                                       ctypes.POINTER(c_i64), ctypes.c_void_p]),
     'pg_layer_create': (ctypes.c_int, [c_i32, ctypes.POINTER(ctypes.c_void_p), ctypes.POINTER(ctypes.c_void_p),
                                        ctypes.POINTER(c_i32), c_i32, c_i32, ctypes.c_void_p,
                                        ctypes.POINTER(ctypes.c_void_p)]),
@@ -388,3 +397,89 @@ class PreparedLayer(object):
                                          _ptr(logits, torch.float32, 'logits'), _ptr(boxes, torch.float32, 'boxes'),
                                          _ptr(probs, torch.float32, 'probs'), _stream()))
         return logits, boxes, probs
+
+
+# ---------------------------------------------------------------------------------------------
+# post-processing (box decoding + NMS)
+# ---------------------------------------------------------------------------------------------
+PG_NMS_MERGE, PG_NMS_RESCORE, PG_NMS_INT_CORNERS = 1, 2, 4
+MAX_CANDIDATES_PER_FRAME = 16384
+
+
+def _class_table(table):
+    flat = [float(v) for row in table for v in row]
+    return (ctypes.c_float * len(flat))(*flat)
+
+
+def decode_boxes(box_encodings, xyz, class_table):
+    """[K, C, 7] encodings at the K vertices -> [K, C, 7] boxes (box_encoding.py:265-299)."""
+    k, c, _ = box_encodings.shape
+    out = torch.empty_like(box_encodings)
+    _check(load().pg_decode_boxes(_ptr(box_encodings, torch.float32, 'box_encodings'), _ptr(xyz, torch.float32, 'xyz'),
+                                  k, c, _class_table(class_table), _ptr(out, torch.float32, 'out'), _stream()))
+    return out
+
+
+def postprocess(probs, box_encodings, xyz, frame_ptr, class_table, overlapped_thres, merge=True, rescore=True,
+                want_candidates=False):
+    """run.py:265-325 for a batch of frames on the device.
+    -> dict(label [D] int32, box [D,7], score [D], index [D] int32, frame_ptr [F+1] int32
+            [, cand_index [B] int32, cand_frame_ptr [F+1] int32])."""
+    lib = load()
+    k, c = probs.shape
+    num_frames = frame_ptr.numel() - 1
+    dev = probs.device
+    cap = max(1024, k)
+    flags = (PG_NMS_MERGE if merge else 0) | (PG_NMS_RESCORE if rescore else 0)
+    sizes = (c_i64 * 2)()
+    cand_index = torch.empty(k * max(c - 2, 1), dtype=torch.int32, device=dev) if want_candidates else None
+    cand_fp = torch.empty(num_frames + 1, dtype=torch.int32, device=dev) if want_candidates else None
+    while True:
+        label = torch.empty(cap, dtype=torch.int32, device=dev)
+        box = torch.empty((cap, 7), dtype=torch.float32, device=dev)
+        score = torch.empty(cap, dtype=torch.float32, device=dev)
+        index = torch.empty(cap, dtype=torch.int32, device=dev)
+        det_fp = torch.empty(num_frames + 1, dtype=torch.int32, device=dev)
+        code = lib.pg_postprocess(
+            _ptr(probs, torch.float32, 'probs'), _ptr(box_encodings, torch.float32, 'box_encodings'),
+            _ptr(xyz, torch.float32, 'xyz'), _ptr(frame_ptr, torch.int32, 'frame_ptr'), num_frames, k, c,
+            _class_table(class_table), float(overlapped_thres), flags, MAX_CANDIDATES_PER_FRAME,
+            _ptr(label, torch.int32, 'label'), _ptr(box, torch.float32, 'box'), _ptr(score, torch.float32, 'score'),
+            _ptr(index, torch.int32, 'index'), cap, _ptr(det_fp, torch.int32, 'det_fp'),
+            _ptr(cand_index, torch.int32, 'cand_index'), _ptr(cand_fp, torch.int32, 'cand_fp'), sizes, _stream())
+        if code == PG_ERR_CAPACITY and int(sizes[0]) > cap:
+            cap = int(sizes[0])
+            continue
+        _check(code)
+        break
+    d, b = int(sizes[0]), int(sizes[1])
+    out = dict(label=label[:d], box=box[:d], score=score[:d], index=index[:d], frame_ptr=det_fp)
+    if want_candidates:
+        out['cand_index'] = cand_index[:b]
+        out['cand_frame_ptr'] = cand_fp
+    return out
+
+
+def nms_boxes_3d(class_labels, boxes, scores, frame_ptr, overlapped_thres, merge, rescore, appr_factor=0.0,
+                 int_corners=False):
+    """models/nms.py's entry points on caller-provided boxes.  -> (label, box, score, index, det_frame_ptr)."""
+    lib = load()
+    n = boxes.shape[0]
+    num_frames = frame_ptr.numel() - 1
+    dev = boxes.device
+    flags = (PG_NMS_MERGE if merge else 0) | (PG_NMS_RESCORE if rescore else 0) | (PG_NMS_INT_CORNERS if int_corners else 0)
+    sizes = (c_i64 * 2)()
+    label = torch.empty(n, dtype=torch.int32, device=dev)
+    box = torch.empty((n, 7), dtype=torch.float32, device=dev)
+    score = torch.empty(n, dtype=torch.float32, device=dev)
+    index = torch.empty(n, dtype=torch.int32, device=dev)
+    det_fp = torch.empty(num_frames + 1, dtype=torch.int32, device=dev)
+    _check(lib.pg_nms_boxes_3d(_ptr(class_labels, torch.int32, 'class_labels'), _ptr(boxes, torch.float32, 'boxes'),
+                               _ptr(scores, torch.float32, 'scores'), _ptr(frame_ptr, torch.int32, 'frame_ptr'),
+                               num_frames, n, float(overlapped_thres), float(appr_factor), flags,
+                               MAX_CANDIDATES_PER_FRAME, _ptr(label, torch.int32, 'label'),
+                               _ptr(box, torch.float32, 'box'), _ptr(score, torch.float32, 'score'),
+                               _ptr(index, torch.int32, 'index'), n, _ptr(det_fp, torch.int32, 'det_fp'), sizes,
+                               _stream()))
+    d = int(sizes[0])
+    return label[:d], box[:d], score[:d], index[:d], det_fp

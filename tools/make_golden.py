@@ -91,5 +91,33 @@ def main():
               'logits', logits.shape, float(np.abs(logits).max()), 'restatement-vs-graphdef %g' % err)
 
 
+POST_CASES = [   # (name, label_method, num_classes, nms_overlapped_thres of the shipped config, seed)
+    ('car', 'Car', 4, 0.01, 11),
+    ('ped', 'Pedestrian_and_Cyclist', 6, 0.2, 12),
+]
+
+
+def post_goldens():
+    """tests/golden/post_<case>.npz: run.py:265-325 executed with the reference's own box_encoding.py and nms.py
+    (shapely replaced by the convex-polygon stand-in of oracle/postprocess.py) on seeded synthetic network outputs."""
+    from oracle import postprocess as pp
+    be, nms = pp.reference_modules()
+    for name, method, c, thres, seed in POST_CASES:
+        pts, enc, probs = pp.synthetic_outputs(seed, num_classes=c)
+        out = {'points_xyz': pts, 'box_encodings': enc, 'probs': probs, 'thres': np.float64(thres)}
+        for variant in ('uncertainty', 'merge_only', 'score_only', 'plain'):
+            r = pp.reference_postprocess_frame(be, nms, probs.copy(), enc.copy(), pts.copy(), method, thres, variant)
+            for k in ('label', 'box', 'score', 'nms_index'):
+                out['%s_%s' % (variant, k)] = r[k]
+            out['cand_index'] = r['cand_index']
+            out['decoded'] = r['decoded']
+        np.savez_compressed(os.path.join(GOLDEN, 'post_%s.npz' % name), **out)
+        print('post', name, 'candidates', len(out['cand_index']), 'kept', len(out['uncertainty_label']))
+
+
 if __name__ == '__main__':
-    main()
+    if len(sys.argv) > 1 and sys.argv[1] == 'post':
+        post_goldens()
+    else:
+        main()
+        post_goldens()
