@@ -52,6 +52,32 @@ PG_API int pg_device_is_sm100(void);
 PG_API int pg_tc_available(void);
 
 /* ------------------------------------------------------------------------ *
+ * Input stage: the step before the path (reference dataset/kitti_dataset.py)
+ * ------------------------------------------------------------------------ */
+
+/*
+ * KittiDataset.get_cam_points_in_image_with_rgb (kitti_dataset.py:666-689) for a batch of frames:
+ * velodyne points -> camera frame (velo_points_to_cam, :998-1006: float32 matmul + float32 offset) ->
+ * keep z > 0.1 and a projection strictly inside the image (cam_points_to_image, :1036-1052, float64) ->
+ * attributes [reflectance] or, with images, [reflectance, r, g, b] (rgb_to_cam_points, :990-996).
+ *   velo_points        [M,4] fp32 (x, y, z, reflectance) = the bytes of the .bin files, 16-byte aligned
+ *   frame_ptr          [num_frames+1] int32 over the M points
+ *   velo_to_cam_host   (host) [num_frames][4][4] fp32  calib['velo_to_cam'] (kitti_dataset.py:510-511)
+ *   cam_to_image_host  (host) [num_frames][3][4] fp64  calib['cam_to_image'] (:501)
+ *   image_size_host    (host) [num_frames][2] int32    (width, height) of the frame's image
+ *   images / image_offset_host  optional: concatenated [H,W,3] uint8 BGR images (cv2.imread layout) and the
+ *                      byte offset of each frame's image; required when attr_channels == 4
+ * Output order = input order.  out_xyz [N,3], out_attr [N,attr_channels], out_frame_ptr [num_frames+1];
+ * *out_num_points_host = N (one host round trip); PG_ERR_CAPACITY when capacity < N.
+ */
+PG_API int pg_cam_points_in_image(const float* velo_points, const int32_t* frame_ptr, int32_t num_frames,
+                           int64_t num_points, const float* velo_to_cam_host,
+                           const double* cam_to_image_host, const int32_t* image_size_host,
+                           const uint8_t* images, const int64_t* image_offset_host, float* out_xyz,
+                           float* out_attr, int32_t attr_channels, int64_t capacity,
+                           int32_t* out_frame_ptr, int64_t* out_num_points_host, void* stream);
+
+/* ------------------------------------------------------------------------ *
  * Graph construction  (reference models/graph_gen.py)
  * ------------------------------------------------------------------------ */
 

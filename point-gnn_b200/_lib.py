@@ -49,6 +49,10 @@ SIGNATURES = {
                                        ctypes.POINTER(c_i32), c_i32, c_f32p, c_i32, ctypes.c_void_p]),
     'pg_softmax_rows': (ctypes.c_int, [c_f32p, c_i64, c_i32, c_f32p, ctypes.c_void_p]),
     'pg_check_edges': (ctypes.c_int, [c_i32p, c_i32p, c_i64, c_i64, c_i64, ctypes.c_void_p]),
+    'pg_cam_points_in_image': (ctypes.c_int, [c_f32p, c_i32p, c_i32, c_i64, ctypes.POINTER(ctypes.c_float),
+                                              ctypes.POINTER(ctypes.c_double), ctypes.POINTER(c_i32), ctypes.c_void_p,
+                                              ctypes.POINTER(c_i64), c_f32p, c_f32p, c_i32, c_i64, c_i32p,
+                                              ctypes.POINTER(c_i64), ctypes.c_void_p]),
     'pg_decode_boxes': (ctypes.c_int, [c_f32p, c_f32p, c_i64, c_i32, ctypes.POINTER(ctypes.c_float), c_f32p,
                                        ctypes.c_void_p]),
     'pg_postprocess': (ctypes.c_int, [c_f32p, c_f32p, c_f32p, c_i32p, c_i32, c_i64, c_i32,
@@ -483,3 +487,37 @@ def nms_boxes_3d(class_labels, boxes, scores, frame_ptr, overlapped_thres, merge
                                _stream()))
     d = int(sizes[0])
     return label[:d], box[:d], score[:d], index[:d], det_fp
+
+
+# ---------------------------------------------------------------------------------------------
+# input stage
+# ---------------------------------------------------------------------------------------------
+def cam_points_in_image(velo, frame_ptr, velo_to_cam, cam_to_image, image_sizes, images=None, image_offsets=None):
+    """pg_cam_points_in_image.  velo [M,4] CUDA fp32, frame_ptr [F+1] CUDA int32, velo_to_cam [F,4,4] / cam_to_image
+    [F,3,4] / image_sizes [F,2] host arrays; images: optional CUDA uint8 buffer (+ byte offsets per frame).
+    -> (xyz [N,3], attr [N,1 or 4], out_frame_ptr [F+1])."""
+    import numpy as np
+    lib = load()
+    m = velo.shape[0]
+    num_frames = frame_ptr.numel() - 1
+    vtc = np.ascontiguousarray(velo_to_cam, dtype=np.float32).reshape(num_frames, 16)
+    cti = np.ascontiguousarray(cam_to_image, dtype=np.float64).reshape(num_frames, 12)
+    wh = np.ascontiguousarray(image_sizes, dtype=np.int32).reshape(num_frames, 2)
+    channels = 4 if images is not None else 1
+    out_xyz = torch.empty((m, 3), dtype=torch.float32, device=velo.device)
+    out_attr = torch.empty((m, channels), dtype=torch.float32, device=velo.device)
+    out_fp = torch.empty(num_frames + 1, dtype=torch.int32, device=velo.device)
+    n = c_i64(0)
+    offs = None
+    if images is not None:
+        offs = np.ascontiguousarray(image_offsets, dtype=np.int64)
+        if images.dtype != torch.uint8 or not images.is_cuda:
+            raise TypeError('images must be a CUDA uint8 tensor')
+    _check(lib.pg_cam_points_in_image(
+        _ptr(velo, torch.float32, 'velo'), _ptr(frame_ptr, torch.int32, 'frame_ptr'), num_frames, m,
+        vtc.ctypes.data_as(ctypes.POINTER(ctypes.c_float)), cti.ctypes.data_as(ctypes.POINTER(ctypes.c_double)),
+        wh.ctypes.data_as(ctypes.POINTER(c_i32)), None if images is None else ctypes.c_void_p(images.data_ptr()),
+        None if offs is None else offs.ctypes.data_as(ctypes.POINTER(c_i64)), _ptr(out_xyz, torch.float32, 'out_xyz'),
+        _ptr(out_attr, torch.float32, 'out_attr'), channels, m, _ptr(out_fp, torch.int32, 'out_fp'), ctypes.byref(n),
+        _stream()))
+    return out_xyz[:n.value], out_attr[:n.value], out_fp

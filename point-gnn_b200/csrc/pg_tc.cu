@@ -2049,15 +2049,15 @@ int apply_edge(const PreparedEdge& e, const float* features, const float* xyz_sr
 // cls H -> C (linear), and per class H -> H (ReLU) -> box_len (linear).  One SIMT kernel does all of it for a
 // tile of 32 vertices with every head weight resident in shared memory, and writes logits, class
 // probabilities (softmax, models.py:165-168) and the stacked box encodings [K, C, box_len].
-constexpr int kHeadRows = 32;
-constexpr int kHeadThreads = 256;
-constexpr int kHeadMaxQ = 16;   // rows per thread in the second layer: kHeadRows / (kHeadThreads / H)
+constexpr int kHeadRows = 64;     // vertices per tile
+constexpr int kHeadThreads = 256; // thread = (row = tid / 4, quarter = tid % 4): 16 of the 64 second-layer outputs of its row
+constexpr int kHeadH = 64;        // hidden width the kernel is built for (models.py:60-64 classaware_predictor)
 
 struct HeadsParams {
   const float* hid;      // [m, htot] = relu(first layers), columns: cls hidden [H] then class c hidden [H] ...
   int64_t m;
-  int htot, H, C, box;
-  const float* wpack;    // [Wcls H*C | bcls C | per class: W2 H*H | b2 H | W3 H*box | b3 box]
+  int htot, C, box;
+  const float* wpack;    // [Wcls H*C | bcls C | per class: W2 H*H | b2 H | W3 H*box | b3 box], sections padded to 4 floats
   int wfloats;
   float* logits;         // [m, C]
   float* probs;          // [m, C] or null
@@ -2065,73 +2065,90 @@ struct HeadsParams {
 };
 
 __global__ void __launch_bounds__(kHeadThreads) predictor_heads_kernel(HeadsParams p) {
+  constexpr int H = kHeadH, XS = H + 1;
   extern __shared__ __align__(16) float hsm[];
   float* w = hsm;                                  // all head weights
-  float* hid = w + ((p.wfloats + 3) & ~3);         // [kHeadRows][htot + 1]
-  const int hs = p.htot + 1;
-  float* h2 = hid + kHeadRows * hs;                // [kHeadRows][H + 1]
-  const int H = p.H, C = p.C, box = p.box;
-  for (int i = threadIdx.x; i < p.wfloats; i += kHeadThreads) w[i] = p.wpack[i];
+  float* x = w + ((p.wfloats + 3) & ~3);           // [kHeadRows][H + 1]: the hidden slice being consumed
+  float* h2 = x + kHeadRows * XS;                  // [kHeadRows][H + 1]: second-layer output of the class
+  float* lg = h2 + kHeadRows * XS;                 // [kHeadRows][16]: class logits
+  const int C = p.C, box = p.box;
+  const int tid = threadIdx.x, r = tid >> 2, qd = tid & 3;
+  for (int i = tid; i < p.wfloats; i += kHeadThreads) w[i] = p.wpack[i];
+  // every section of the pack starts on a 16-byte boundary (128-bit shared loads below)
+  const int cpad = (C + 3) & ~3, hb = (H * box + 3) & ~3, bpad = (box + 3) & ~3;
   const float* wcls = w;
-  const float* bcls = w + H * C;
-  const int per_class = H * H + H + H * box + box;
+  const float* bcls = w + ((H * C + 3) & ~3);
+  const int head0 = ((H * C + 3) & ~3) + cpad;
+  const int per_class = H * H + H + hb + bpad;
   const int64_t tiles = (p.m + kHeadRows - 1) / kHeadRows;
   for (int64_t tile = blockIdx.x; tile < tiles; tile += gridDim.x) {
     const int64_t row0 = tile * kHeadRows;
     const int rows = int(min(int64_t(kHeadRows), p.m - row0));
-    __syncthreads();
-    for (int i = threadIdx.x; i < rows * p.htot; i += kHeadThreads) {
-      const int r = i / p.htot, c = i - r * p.htot;
-      hid[r * hs + c] = p.hid[(row0 + r) * p.htot + c];
-    }
-    __syncthreads();
-    // class logits + softmax: one thread per row (H * C MACs)
-    if (threadIdx.x < rows) {
-      const int r = threadIdx.x;
-      float lg[16];
-      float mx = -FLT_MAX;
-      for (int c = 0; c < C; ++c) {
-        float a = bcls[c];
-        for (int i = 0; i < H; ++i) a = fmaf(hid[r * hs + i], wcls[i * C + c], a);
-        lg[c] = a;
-        mx = fmaxf(mx, a);
-        p.logits[(row0 + r) * C + c] = a;
+    for (int c = -1; c < C; ++c) {
+      // stage the hidden slice of this head (c = -1: the cls head), coalesced
+      __syncthreads();
+      for (int i = tid; i < kHeadRows * H; i += kHeadThreads) {
+        const int rr = i >> 6, cc = i & (H - 1);
+        x[rr * XS + cc] = rr < rows ? p.hid[(row0 + rr) * p.htot + (c + 1) * H + cc] : 0.0f;
       }
-      if (p.probs != nullptr) {
-        float sum = 0.0f;
-        for (int c = 0; c < C; ++c) sum += expf(lg[c] - mx);
-        for (int c = 0; c < C; ++c) p.probs[(row0 + r) * C + c] = expf(lg[c] - mx) / sum;
+      __syncthreads();
+      if (c < 0) {
+        // class logits: thread (row, qd) -> classes qd, qd + 4, ...; then softmax by the row's first thread
+        for (int cls = qd; cls < C; cls += 4) {
+          float a = bcls[cls];
+#pragma unroll 8
+          for (int i = 0; i < H; ++i) a = fmaf(x[r * XS + i], wcls[i * C + cls], a);
+          lg[r * 16 + cls] = a;
+        }
+        __syncthreads();
+        if (qd == 0 && r < rows) {
+          float mx = -FLT_MAX;
+          for (int cls = 0; cls < C; ++cls) {
+            const float a = lg[r * 16 + cls];
+            p.logits[(row0 + r) * C + cls] = a;
+            mx = fmaxf(mx, a);
+          }
+          if (p.probs != nullptr) {
+            float sum = 0.0f;
+            for (int cls = 0; cls < C; ++cls) sum += expf(lg[r * 16 + cls] - mx);
+            for (int cls = 0; cls < C; ++cls) p.probs[(row0 + r) * C + cls] = expf(lg[r * 16 + cls] - mx) / sum;
+          }
+        }
+        continue;
       }
-    }
-    for (int c = 0; c < C; ++c) {
-      const float* w2 = w + H * C + C + c * per_class;
+      const float* w2 = w + head0 + c * per_class;
       const float* b2 = w2 + H * H;
       const float* w3 = b2 + H;
-      const float* b3 = w3 + H * box;
-      const float* hc = hid + H * (c + 1);
-      // second layer: thread (j, row group) -> rows rg, rg + G, ...   (G = threads / H row groups)
-      const int j = threadIdx.x % H, rg = threadIdx.x / H, G = kHeadThreads / H;
-      const int nq = kHeadRows / G;          // rows per thread (<= kHeadMaxQ, checked on the host)
-      float acc[kHeadMaxQ];
+      const float* b3 = w3 + hb;
+      // second layer: 16 outputs of row r per thread, weights as broadcast 128-bit shared loads
+      float acc[16];
 #pragma unroll
-      for (int q = 0; q < kHeadMaxQ; ++q) acc[q] = b2[j];
+      for (int j = 0; j < 16; ++j) acc[j] = b2[qd * 16 + j];
+#pragma unroll 4
       for (int i = 0; i < H; ++i) {
-        const float wv = w2[i * H + j];
+        const float xv = x[r * XS + i];
+        const float4* wr = reinterpret_cast<const float4*>(w2 + i * H + qd * 16);
 #pragma unroll
-        for (int q = 0; q < kHeadMaxQ; ++q)
-          if (q < nq) acc[q] = fmaf(hc[(q * G + rg) * hs + i], wv, acc[q]);
+        for (int j4 = 0; j4 < 4; ++j4) {
+          const float4 q = wr[j4];
+          acc[4 * j4 + 0] = fmaf(xv, q.x, acc[4 * j4 + 0]);
+          acc[4 * j4 + 1] = fmaf(xv, q.y, acc[4 * j4 + 1]);
+          acc[4 * j4 + 2] = fmaf(xv, q.z, acc[4 * j4 + 2]);
+          acc[4 * j4 + 3] = fmaf(xv, q.w, acc[4 * j4 + 3]);
+        }
       }
 #pragma unroll
-      for (int q = 0; q < kHeadMaxQ; ++q)
-        if (q < nq) h2[(q * G + rg) * (H + 1) + j] = fmaxf(acc[q], 0.0f);
+      for (int j = 0; j < 16; ++j) h2[r * XS + qd * 16 + j] = fmaxf(acc[j], 0.0f);
       __syncthreads();
-      for (int o = threadIdx.x; o < rows * box; o += kHeadThreads) {
-        const int r = o / box, ob = o - r * box;
-        float a = b3[ob];
-        for (int i = 0; i < H; ++i) a = fmaf(h2[r * (H + 1) + i], w3[i * box + ob], a);
-        p.boxes[((row0 + r) * C + c) * box + ob] = a;
+      // third layer (H -> box, linear): outputs qd, qd + 4, ... of row r
+      if (r < rows) {
+        for (int o = qd; o < box; o += 4) {
+          float a = b3[o];
+#pragma unroll 8
+          for (int i = 0; i < H; ++i) a = fmaf(h2[r * XS + i], w3[i * box + o], a);
+          p.boxes[((row0 + r) * C + c) * box + o] = a;
+        }
       }
-      __syncthreads();
     }
   }
 }
@@ -2233,10 +2250,10 @@ extern "C" int pg_layer_create(int32_t kind, const float* const* weights_host, c
       PG_REQUIRE(false, "pg_layer_create: predictor needs 2 + 3 C layers, 1 <= C <= 16");
     }
     P.htot = P.H * (P.C + 1);
-    P.wfloats = P.H * P.C + P.C + P.C * (P.H * P.H + P.H + P.H * P.box + P.box);
-    P.smem = (size_t((P.wfloats + 3) & ~3) + size_t(kHeadRows) * (P.htot + 1) + size_t(kHeadRows) * (P.H + 1)) * sizeof(float);
-    P.fused = P.H <= kHeadThreads && kHeadThreads % P.H == 0 && kHeadRows % (kHeadThreads / P.H) == 0 &&
-              kHeadRows / (kHeadThreads / P.H) <= kHeadMaxQ && P.smem <= 227 * 1024 && (P.H % 4) == 0;
+    auto pad4 = [](int v) { return (v + 3) & ~3; };
+    P.wfloats = pad4(P.H * P.C) + pad4(P.C) + P.C * (pad4(P.H * P.H) + pad4(P.H) + pad4(P.H * P.box) + pad4(P.box));
+    P.smem = (size_t((P.wfloats + 3) & ~3) + 2 * size_t(kHeadRows) * (kHeadH + 1) + size_t(kHeadRows) * 16) * sizeof(float);
+    P.fused = P.H == kHeadH && P.smem <= 227 * 1024;
     if (P.fused) {
       auto cuda_ok = [&](cudaError_t e) { if (e != cudaSuccess && rc == PG_OK) { pg::set_error("predictor prepare: %s", cudaGetErrorString(e)); rc = PG_ERR_CUDA; } };
       cuda_ok(P.wcat.alloc(sizeof(float) * size_t(P.D) * P.htot, s));
@@ -2252,9 +2269,10 @@ extern "C" int pg_layer_create(int32_t kind, const float* const* weights_host, c
         }
         float* wp = P.wpack.as<float>();
         size_t off = 0;
-        auto put = [&](const float* src, size_t count) {
+        cuda_ok(cudaMemsetAsync(wp, 0, sizeof(float) * P.wfloats, s));
+        auto put = [&](const float* src, size_t count) {     // sections start on 16-byte boundaries
           cuda_ok(cudaMemcpyAsync(wp + off, src, sizeof(float) * count, cudaMemcpyDeviceToDevice, s));
-          off += count;
+          off += (count + 3) & ~size_t(3);
         };
         put(weights_host[1], size_t(P.H) * P.C);
         put(biases_host[1], P.C);
@@ -2361,7 +2379,6 @@ extern "C" int pg_layer_predictor(const pg_layer* layer, const float* x, int64_t
     hp.hid = hid.as<float>();
     hp.m = m;
     hp.htot = P.htot;
-    hp.H = P.H;
     hp.C = P.C;
     hp.box = P.box;
     hp.wpack = P.wpack.as<float>();

@@ -129,8 +129,13 @@ def latest_checkpoint(checkpoint_dir):
 
 
 def load_checkpoint(prefix):
-    """prefix = '<dir>/model-1400000' -> {variable_name: np.ndarray}."""
+    """prefix = '<dir>/model-1400000' (or the checkpoint directory) -> {variable_name: np.ndarray}.
+
+    A directory without TensorFlow files but with ``weights.npz`` (variable name -> array, e.g. the export that
+    tools/make_golden.py writes) is accepted too."""
     if os.path.isdir(prefix):
+        if not os.path.isfile(os.path.join(prefix, 'checkpoint')) and os.path.isfile(os.path.join(prefix, 'weights.npz')):
+            return dict(np.load(os.path.join(prefix, 'weights.npz')))
         prefix = latest_checkpoint(prefix)
     entries = read_index(prefix + '.index')
     with open(prefix + '.data-00000-of-00001', 'rb') as f:

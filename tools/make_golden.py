@@ -115,9 +115,70 @@ def post_goldens():
         print('post', name, 'candidates', len(out['cand_index']), 'kept', len(out['uncertainty_label']))
 
 
+def kitti_goldens():
+    """tests/golden/kitti_io.npz + kitti_result_car.txt: the reference's own dataset/kitti_dataset.py (Open3D stubbed)
+    on a synthetic KITTI-format frame - calibration matrices, camera points in image with colours - and run.py:361-429
+    (label conversion + file text) assembled from the reference's functions on the post_car detections."""
+    import tempfile
+    import cv2
+    from oracle import kitti as ok
+    from oracle import postprocess as pp
+    ref = ok.reference_dataset_module()
+    be, nms = pp.reference_modules()
+    root = tempfile.mkdtemp()
+    ok.write_synthetic_kitti(root, [5], 6000)
+    ds = ref.KittiDataset(os.path.join(root, 'image/testing/image_2'), os.path.join(root, 'velodyne/testing/velodyne/'),
+                          os.path.join(root, 'calib/testing/calib/'), '', num_classes=4, is_training=False)
+    calib = ds.get_calib(0)
+    pts = ds.get_cam_points_in_image_with_rgb(0, None)
+    velo = np.fromfile(os.path.join(root, 'velodyne/testing/velodyne/000000.bin'), dtype=np.float32).reshape(-1, 4)
+    image = cv2.imread(os.path.join(root, 'image/testing/image_2/000000.png'))
+    # run.py:361-429 with the reference's functions, on the car post-processing fixture
+    g = dict(np.load(os.path.join(GOLDEN, 'post_car.npz')))
+    labels, boxes, scores = g['uncertainty_label'], g['uncertainty_box'], g['uncertainty_score']
+    cand_xyz = g['points_xyz'][g['cand_index'] // 4]
+
+    def occlusion(label, xyz):            # run.py:88-100
+        if xyz.shape[0] == 0:
+            return 0
+        normals, lower, upper = ds.box3d_to_normals(label)
+        projected = np.matmul(xyz, np.transpose(normals))
+        rates = [(np.max(projected[:, i]) - np.min(projected[:, i])) / (upper[i] - lower[i]) for i in range(3)]
+        return rates[0] * rates[1] * rates[2]
+
+    corners_all = nms.boxes_3d_to_corners(boxes)
+    names = ['Background', 'Car', 'Car', 'DontCare']
+    text = ''
+    for i in range(len(corners_all)):
+        corners_xy = ds.cam_points_to_image(ref.Points(xyz=corners_all[i], attr=None), calib).xyz[:, :2]
+        xmin, ymin = np.amin(corners_xy, axis=0)
+        xmax, ymax = np.amax(corners_xy, axis=0)
+        clip_xmin, clip_ymin, clip_xmax, clip_ymax = max(xmin, 0.0), max(ymin, 0.0), min(xmax, 1242.0), min(ymax, 375.0)
+        truncation_rate = 1.0 - (clip_ymax - clip_ymin) * (clip_xmax - clip_xmin) / ((ymax - ymin) * (xmax - xmin))
+        if truncation_rate > 0.4:
+            continue
+        x3d, y3d, z3d, l, h, w, yaw = boxes[i]
+        tmp_label = {"x3d": x3d, "y3d": y3d, "z3d": z3d, "yaw": yaw, "height": h, "width": w, "length": l}
+        inside_mask = ds.sel_xyz_in_box3d(tmp_label, cand_xyz)
+        score = (1 + occlusion(tmp_label, cand_xyz[inside_mask])) * scores[i]
+        for field in (names[labels[i]], -1, -1, 0, clip_xmin, clip_ymin, clip_xmax, clip_ymax, h, w, l, x3d, y3d, z3d, yaw, score):
+            text += str(field) + ' '
+        text += '\n'
+    text += '\n'
+    with open(os.path.join(GOLDEN, 'kitti_result_car.txt'), 'w') as f:
+        f.write(text)
+    np.savez_compressed(os.path.join(GOLDEN, 'kitti_io.npz'), velo=velo, image=image, xyz=pts.xyz, attr=pts.attr,
+                        **{'calib_' + k: np.asarray(calib[k]) for k in ('velo_to_cam', 'cam_to_image', 'cam_to_velo', 'P2')})
+    with open(os.path.join(GOLDEN, 'kitti_calib.txt'), 'w') as f:
+        f.write(ok.CALIB_TEXT)
+    print('kitti: points in image', pts.xyz.shape, 'result lines', text.count('\n') - 1)
+
+
 if __name__ == '__main__':
-    if len(sys.argv) > 1 and sys.argv[1] == 'post':
-        post_goldens()
-    else:
+    which = sys.argv[1] if len(sys.argv) > 1 else 'all'
+    if which in ('all', 'gnn'):
         main()
+    if which in ('all', 'post'):
         post_goldens()
+    if which in ('all', 'kitti'):
+        kitti_goldens()
