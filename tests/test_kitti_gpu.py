@@ -65,7 +65,14 @@ def test_run_twin_end_to_end(tmp_path, cfg_name):
     ckpt = tmp_path / 'ckpt'
     ckpt.mkdir()
     shutil.copy(os.path.join(GOLDEN, 'config_%s.json' % cfg_name), str(ckpt / 'config'))
-    shutil.copy(os.path.join(GOLDEN, 'weights_%s.npz' % cfg_name), str(ckpt / 'weights.npz'))
+    # the trained car model does not fire on the synthetic boxes, so the test checkpoint = the real weights with the
+    # object-class logit biases raised by 7: a couple of hundred candidates per frame, clustered on the obstacles.
+    # Both pipelines read the same file; this is a pipeline-parity test, not a detection-quality test.
+    w = dict(np.load(os.path.join(GOLDEN, 'weights_%s.npz' % cfg_name)))
+    b = w['output/predictor/cls/fully_connected_1/biases'].copy()
+    b[1:-1] += 7.0
+    w['output/predictor/cls/fully_connected_1/biases'] = b
+    np.savez(str(ckpt / 'weights.npz'), **w)
     out_dir = str(tmp_path / 'out')
     times = twin.main([str(ckpt), '--test', '--dataset_root_dir', root, '--output_dir', out_dir])
     assert set(times) >= {'fetch input', 'gen graph', 'gnn inference', 'decode box', 'nms', 'total'}   # run.py's timers
