@@ -752,3 +752,285 @@ extern "C" int pg_multi_level_graph(const float* xyz, const int32_t* frame_ptr, 
   }
   return PG_OK;
 }
+
+// =================================================================================================
+// Training-time graph path: random voxel keypoints and the random neighbour cap.
+// The reference draws from Python's / NumPy's global generators (graph_gen.py:92-153, 210-214), so parity is
+// statistical; everything that is NOT random is reproduced exactly: the voxel index arithmetic (float32
+// floor-division without the random shift, float64 with it), the set of occupied voxels, the first-appearance
+// output order of the keypoints, "one point of its own voxel per keypoint", and for the cap "rows of at most
+// num_neighbors entries keep every neighbour, longer rows keep exactly num_neighbors distinct neighbours".
+// =================================================================================================
+namespace pg {
+namespace {
+
+// NumPy's floor_divide for floats (npy_floor_divide / npy_divmod): Python semantics
+template <typename T>
+__device__ inline T np_floor_divide(T a, T b) {
+  T mod = fmod(a, b);
+  T div = (a - mod) / b;
+  if (mod != T(0) && ((b < T(0)) != (mod < T(0)))) div -= T(1);
+  if (div != T(0)) {
+    T fl = floor(div);
+    if (div - fl > T(0.5)) fl += T(1);
+    return fl;
+  }
+  return copysign(T(0), a / b);
+}
+
+// graph_gen.py:124-131 voxel index of every point; shift == nullptr: float32 arithmetic (add_rnd3d False),
+// else float64 with the per-frame random shift fractions (add_rnd3d True)
+__global__ void random_voxel_keys_kernel(const float* __restrict__ xyz, const int32_t* __restrict__ frame_ptr, int num_frames,
+                                         int64_t n, double vx, double vy, double vz, const double* __restrict__ shift,
+                                         const uint32_t* __restrict__ bounds, uint64_t* __restrict__ keys,
+                                         int32_t* __restrict__ vals, int* __restrict__ err) {
+  const int64_t i = int64_t(blockIdx.x) * blockDim.x + threadIdx.x;
+  if (i >= n) return;
+  if (i == 0 && (frame_ptr[0] != 0 || int64_t(frame_ptr[num_frames]) != n)) atomicOr(err, kErrFramePtr);
+  const int f = find_frame(frame_ptr, num_frames, i);
+  const float mn[3] = {ordered_to_float(bounds[3 * f]), ordered_to_float(bounds[3 * f + 1]), ordered_to_float(bounds[3 * f + 2])};
+  const double v[3] = {vx, vy, vz};
+  long long idx[3];
+  for (int a = 0; a < 3; ++a) {
+    const float d = __fsub_rn(xyz[3 * i + a], mn[a]);
+    if (shift == nullptr) {
+      idx[a] = (long long)np_floor_divide<float>(d, float(v[a]));
+    } else {
+      const double t = __dadd_rn(double(d), __dmul_rn(v[a], shift[3 * f + a]));
+      idx[a] = (long long)np_floor_divide<double>(t, v[a]);
+    }
+    if (idx[a] < 0 || idx[a] > kAxisMax) {
+      atomicOr(err, kErrRange);
+      idx[a] = 0;
+    }
+  }
+  keys[i] = make_key(uint32_t(f), uint32_t(idx[2]), uint32_t(idx[1]), uint32_t(idx[0]));
+  vals[i] = int32_t(i);
+}
+
+__global__ void head_flags_kernel(const uint64_t* __restrict__ keys, int64_t n, int32_t* __restrict__ head) {
+  const int64_t i = int64_t(blockIdx.x) * blockDim.x + threadIdx.x;
+  if (i < n) head[i] = (i == 0 || keys[i] != keys[i - 1]) ? 1 : 0;
+}
+
+// second sort key of every voxel: (frame, smallest original point index) = dict insertion order of graph_gen.py:133-139
+__global__ void voxel_first_keys_kernel(const uint64_t* __restrict__ cell_key, const int32_t* __restrict__ cell_start,
+                                        const int32_t* __restrict__ sorted_idx, const int32_t* __restrict__ num_cells,
+                                        int64_t n, int num_frames, uint64_t* __restrict__ keys2, int32_t* __restrict__ vals2) {
+  const int64_t v = int64_t(blockIdx.x) * blockDim.x + threadIdx.x;
+  if (v >= n) return;
+  vals2[v] = int32_t(v);
+  if (v < *num_cells) keys2[v] = ((cell_key[v] >> 48) << 32) | uint64_t(uint32_t(sorted_idx[cell_start[v]]));
+  else keys2[v] = uint64_t(num_frames) << 32;     // behind every real voxel
+}
+
+__global__ void random_pick_kernel(const int32_t* __restrict__ order, const int32_t* __restrict__ cell_start,
+                                   const int32_t* __restrict__ sorted_idx, const int32_t* __restrict__ num_cells,
+                                   const float* __restrict__ uniform, int64_t capacity, int32_t* __restrict__ out_idx) {
+  const int64_t o = int64_t(blockIdx.x) * blockDim.x + threadIdx.x;
+  if (o >= *num_cells || o >= capacity) return;
+  const int c = order[o];
+  const int s = cell_start[c], cnt = cell_start[c + 1] - s;
+  int pick = int(uniform[o] * float(cnt));          // random.choice(seq) = seq[floor(u * len)], u in [0, 1)
+  pick = min(max(pick, 0), cnt - 1);
+  out_idx[o] = sorted_idx[s + pick];
+}
+
+__global__ void random_frame_ranges_kernel(const uint64_t* __restrict__ keys2_sorted, const int32_t* __restrict__ num_cells,
+                                           int num_frames, int32_t* __restrict__ out_frame_ptr) {
+  const int f = blockIdx.x * blockDim.x + threadIdx.x;
+  if (f > num_frames) return;
+  out_frame_ptr[f] = lower_bound_u64(keys2_sorted, *num_cells, uint64_t(f) << 32);
+}
+
+// ---- random neighbour cap ------------------------------------------------------------------------
+__device__ inline uint32_t mix32(uint32_t x) {     // integer hash (murmur3 finaliser)
+  x ^= x >> 16; x *= 0x85ebca6bu; x ^= x >> 13; x *= 0xc2b2ae35u; x ^= x >> 16;
+  return x;
+}
+__device__ inline uint32_t edge_priority(uint32_t seed, uint32_t row, uint32_t src) {
+  return mix32(mix32(seed ^ (row * 0x9e3779b9u)) ^ (src * 0x7f4a7c15u));
+}
+
+__global__ void capped_counts_kernel(const int32_t* __restrict__ row_ptr, int64_t num_rows, int cap, int32_t* __restrict__ counts) {
+  const int64_t r = int64_t(blockIdx.x) * blockDim.x + threadIdx.x;
+  if (r > num_rows) return;
+  counts[r] = r < num_rows ? min(row_ptr[r + 1] - row_ptr[r], cap) : 0;
+}
+
+// One warp per row.  Rows longer than `cap` keep the `cap` entries with the smallest hash priority (a uniformly random
+// subset for a random seed), found by a bitwise search for the cap-th smallest priority; ascending source order is kept.
+__global__ void __launch_bounds__(256) cap_rows_kernel(const int32_t* __restrict__ row_ptr, const int32_t* __restrict__ src,
+                                                       int64_t num_rows, int cap, uint32_t seed,
+                                                       const int32_t* __restrict__ new_row_ptr, int32_t* __restrict__ out_src,
+                                                       int32_t* __restrict__ out_dst) {
+  const int lane = threadIdx.x & 31;
+  const int64_t r = (int64_t(blockIdx.x) * blockDim.x + threadIdx.x) >> 5;
+  if (r >= num_rows) return;
+  const int b = row_ptr[r], len = row_ptr[r + 1] - b, ob = new_row_ptr[r];
+  if (len <= cap) {
+    for (int i = lane; i < len; i += 32) {
+      out_src[ob + i] = src[b + i];
+      out_dst[ob + i] = int32_t(r);
+    }
+    return;
+  }
+  // largest threshold t with count(priority < t) <= cap, built bit by bit
+  uint32_t t = 0;
+  for (int bit = 31; bit >= 0; --bit) {
+    const uint32_t cand = t | (1u << bit);
+    int cnt = 0;
+    for (int i = lane; i < len; i += 32) cnt += edge_priority(seed, uint32_t(r), uint32_t(src[b + i])) < cand ? 1 : 0;
+    for (int o = 16; o > 0; o >>= 1) cnt += __shfl_xor_sync(0xffffffffu, cnt, o);
+    if (cnt <= cap) t = cand;
+  }
+  // entries with priority < t are kept; ties at t fill the remaining slots in source order
+  int below = 0;
+  for (int i = lane; i < len; i += 32) below += edge_priority(seed, uint32_t(r), uint32_t(src[b + i])) < t ? 1 : 0;
+  for (int o = 16; o > 0; o >>= 1) below += __shfl_xor_sync(0xffffffffu, below, o);
+  int need_ties = cap - below, written = 0;
+  for (int i0 = 0; i0 < len; i0 += 32) {
+    const int i = i0 + lane;
+    bool keep = false, tie = false;
+    int s = 0;
+    if (i < len) {
+      s = src[b + i];
+      const uint32_t pr = edge_priority(seed, uint32_t(r), uint32_t(s));
+      keep = pr < t;
+      tie = pr == t;
+    }
+    const uint32_t tm = __ballot_sync(0xffffffffu, tie);
+    const int tie_rank = __popc(tm & ((1u << lane) - 1u));
+    if (tie && tie_rank < need_ties) keep = true;
+    need_ties -= min(need_ties, __popc(tm));
+    const uint32_t km = __ballot_sync(0xffffffffu, keep);
+    if (keep) {
+      const int o = ob + written + __popc(km & ((1u << lane) - 1u));
+      out_src[o] = s;
+      out_dst[o] = int32_t(r);
+    }
+    written += __popc(km);
+  }
+}
+
+}  // namespace
+}  // namespace pg
+
+extern "C" int pg_random_keypoints(const float* xyz, const int32_t* frame_ptr, int32_t num_frames, int64_t num_points,
+                                   const double* voxel_size_host, const double* shift_host, const float* uniform,
+                                   int32_t* out_keypoint_idx, int64_t capacity, int32_t* out_kp_frame_ptr,
+                                   int64_t* out_num_keypoints_host, void* stream) {
+  cudaStream_t s = static_cast<cudaStream_t>(stream);
+  PG_REQUIRE(xyz && frame_ptr && voxel_size_host && uniform && out_keypoint_idx && out_kp_frame_ptr && out_num_keypoints_host,
+             "pg_random_keypoints: null argument");
+  PG_REQUIRE(voxel_size_host[0] > 0 && voxel_size_host[1] > 0 && voxel_size_host[2] > 0, "voxel size must be positive");
+  PG_REQUIRE(num_frames >= 1 && num_frames <= 65534, "num_frames=%d out of range [1,65534]", num_frames);
+  const int64_t n = num_points;
+  PG_REQUIRE(n >= 1 && n < (int64_t(1) << 31), "num_points=%lld out of range", (long long)n);
+  Temp bounds, keys_a, keys_b, vals_a, vals_b, head, head_scan, cell_key, cell_start, keys2a, keys2b, vals2a, vals2b, tmp, err,
+      shift;
+  PG_CUDA_OK(bounds.alloc(sizeof(uint32_t) * 3 * num_frames, s));
+  PG_CUDA_OK(keys_a.alloc(sizeof(uint64_t) * n, s));
+  PG_CUDA_OK(keys_b.alloc(sizeof(uint64_t) * n, s));
+  PG_CUDA_OK(vals_a.alloc(sizeof(int32_t) * n, s));
+  PG_CUDA_OK(vals_b.alloc(sizeof(int32_t) * n, s));
+  PG_CUDA_OK(head.alloc(sizeof(int32_t) * n, s));
+  PG_CUDA_OK(head_scan.alloc(sizeof(int32_t) * n, s));
+  PG_CUDA_OK(cell_key.alloc(sizeof(uint64_t) * n, s));
+  PG_CUDA_OK(cell_start.alloc(sizeof(int32_t) * (n + 1), s));
+  PG_CUDA_OK(keys2a.alloc(sizeof(uint64_t) * n, s));
+  PG_CUDA_OK(keys2b.alloc(sizeof(uint64_t) * n, s));
+  PG_CUDA_OK(vals2a.alloc(sizeof(int32_t) * n, s));
+  PG_CUDA_OK(vals2b.alloc(sizeof(int32_t) * n, s));
+  PG_CUDA_OK(err.alloc(sizeof(int), s));
+  PG_CUDA_OK(cudaMemsetAsync(err.ptr, 0, sizeof(int), s));
+  const double* shift_dev = nullptr;
+  if (shift_host != nullptr) {
+    PG_CUDA_OK(shift.alloc(sizeof(double) * 3 * num_frames, s));
+    PG_CUDA_OK(cudaMemcpyAsync(shift.ptr, shift_host, sizeof(double) * 3 * num_frames, cudaMemcpyHostToDevice, s));
+    shift_dev = shift.as<double>();
+  }
+  init_bounds_kernel<<<ceil_div(3 * num_frames, 256), 256, 0, s>>>(bounds.as<uint32_t>(), 3 * num_frames);
+  PG_LAUNCH_CHECK();
+  const int blocks_per_frame = int(std::min<int64_t>(std::max<int64_t>(1, ceil_div(n / num_frames, 1024)), 64));
+  frame_min_kernel<<<dim3(blocks_per_frame, num_frames), 256, 0, s>>>(xyz, frame_ptr, n, bounds.as<uint32_t>());
+  PG_LAUNCH_CHECK();
+  random_voxel_keys_kernel<<<ceil_div(n, 256), 256, 0, s>>>(xyz, frame_ptr, num_frames, n, voxel_size_host[0], voxel_size_host[1],
+                                                            voxel_size_host[2], shift_dev, bounds.as<uint32_t>(),
+                                                            keys_a.as<uint64_t>(), vals_a.as<int32_t>(), err.as<int>());
+  PG_LAUNCH_CHECK();
+  int frame_bits = 1;
+  while ((1 << frame_bits) < num_frames + 1) ++frame_bits;
+  size_t b1 = 0, b2 = 0, b3 = 0;
+  PG_CUDA_OK(cub::DeviceRadixSort::SortPairs(nullptr, b1, keys_a.as<uint64_t>(), keys_b.as<uint64_t>(), vals_a.as<int32_t>(),
+                                             vals_b.as<int32_t>(), int(n), 0, 48 + frame_bits, s));
+  PG_CUDA_OK(cub::DeviceScan::InclusiveSum(nullptr, b2, head.as<int32_t>(), head_scan.as<int32_t>(), int(n), s));
+  PG_CUDA_OK(cub::DeviceRadixSort::SortPairs(nullptr, b3, keys2a.as<uint64_t>(), keys2b.as<uint64_t>(), vals2a.as<int32_t>(),
+                                             vals2b.as<int32_t>(), int(n), 0, 32 + frame_bits, s));
+  PG_CUDA_OK(tmp.alloc(std::max(b1, std::max(b2, b3)), s));
+  PG_CUDA_OK(cub::DeviceRadixSort::SortPairs(tmp.ptr, b1, keys_a.as<uint64_t>(), keys_b.as<uint64_t>(), vals_a.as<int32_t>(),
+                                             vals_b.as<int32_t>(), int(n), 0, 48 + frame_bits, s));
+  count_launch(4);
+  head_flags_kernel<<<ceil_div(n, 256), 256, 0, s>>>(keys_b.as<uint64_t>(), n, head.as<int32_t>());
+  PG_LAUNCH_CHECK();
+  PG_CUDA_OK(cub::DeviceScan::InclusiveSum(tmp.ptr, b2, head.as<int32_t>(), head_scan.as<int32_t>(), int(n), s));
+  count_launch(2);
+  cell_table_kernel<<<ceil_div(n, 256), 256, 0, s>>>(keys_b.as<uint64_t>(), head_scan.as<int32_t>(), n, cell_key.as<uint64_t>(),
+                                                      cell_start.as<int32_t>());
+  PG_LAUNCH_CHECK();
+  const int32_t* num_cells = head_scan.as<int32_t>() + (n - 1);
+  voxel_first_keys_kernel<<<ceil_div(n, 256), 256, 0, s>>>(cell_key.as<uint64_t>(), cell_start.as<int32_t>(), vals_b.as<int32_t>(),
+                                                            num_cells, n, num_frames, keys2a.as<uint64_t>(), vals2a.as<int32_t>());
+  PG_LAUNCH_CHECK();
+  PG_CUDA_OK(cub::DeviceRadixSort::SortPairs(tmp.ptr, b3, keys2a.as<uint64_t>(), keys2b.as<uint64_t>(), vals2a.as<int32_t>(),
+                                             vals2b.as<int32_t>(), int(n), 0, 32 + frame_bits, s));
+  count_launch(4);
+  random_pick_kernel<<<ceil_div(n, 256), 256, 0, s>>>(vals2b.as<int32_t>(), cell_start.as<int32_t>(), vals_b.as<int32_t>(),
+                                                       num_cells, uniform, capacity, out_keypoint_idx);
+  PG_LAUNCH_CHECK();
+  random_frame_ranges_kernel<<<ceil_div(num_frames + 1, 128), 128, 0, s>>>(keys2b.as<uint64_t>(), num_cells, num_frames,
+                                                                            out_kp_frame_ptr);
+  PG_LAUNCH_CHECK();
+  int32_t h[2] = {0, 0};
+  PG_CUDA_OK(cudaMemcpyAsync(&h[0], num_cells, sizeof(int32_t), cudaMemcpyDeviceToHost, s));
+  PG_CUDA_OK(cudaMemcpyAsync(&h[1], err.ptr, sizeof(int32_t), cudaMemcpyDeviceToHost, s));
+  PG_CUDA_OK(cudaStreamSynchronize(s));
+  if (int rc = graph_error(h[1])) return rc;
+  *out_num_keypoints_host = h[0];
+  if (h[0] > capacity) {
+    set_error("keypoint buffer too small: need %d, capacity %lld", h[0], (long long)capacity);
+    return PG_ERR_CAPACITY;
+  }
+  return PG_OK;
+}
+
+extern "C" int pg_cap_neighbors(const int32_t* row_ptr, const int32_t* src, int64_t num_rows, int32_t num_neighbors,
+                                uint32_t seed, int32_t* out_row_ptr, int32_t* out_src, int32_t* out_dst, int64_t capacity,
+                                int64_t* out_num_edges_host, void* stream) {
+  cudaStream_t s = static_cast<cudaStream_t>(stream);
+  PG_REQUIRE(row_ptr && out_row_ptr && out_num_edges_host && num_rows >= 1 && num_neighbors >= 1,
+             "pg_cap_neighbors: bad argument");
+  Temp counts, tmp;
+  PG_CUDA_OK(counts.alloc(sizeof(int32_t) * (num_rows + 1), s));
+  capped_counts_kernel<<<ceil_div(num_rows + 1, 256), 256, 0, s>>>(row_ptr, num_rows, num_neighbors, counts.as<int32_t>());
+  PG_LAUNCH_CHECK();
+  size_t bytes = 0;
+  PG_CUDA_OK(cub::DeviceScan::ExclusiveSum(nullptr, bytes, counts.as<int32_t>(), out_row_ptr, int(num_rows + 1), s));
+  PG_CUDA_OK(tmp.alloc(bytes, s));
+  PG_CUDA_OK(cub::DeviceScan::ExclusiveSum(tmp.ptr, bytes, counts.as<int32_t>(), out_row_ptr, int(num_rows + 1), s));
+  count_launch(2);
+  int32_t h_e = 0;
+  PG_CUDA_OK(cudaMemcpyAsync(&h_e, out_row_ptr + num_rows, sizeof(int32_t), cudaMemcpyDeviceToHost, s));
+  PG_CUDA_OK(cudaStreamSynchronize(s));
+  *out_num_edges_host = h_e;
+  if (h_e > capacity) {
+    set_error("edge buffer too small: need %d, capacity %lld", h_e, (long long)capacity);
+    return PG_ERR_CAPACITY;
+  }
+  if (h_e == 0) return PG_OK;
+  PG_REQUIRE(src && out_src && out_dst, "pg_cap_neighbors: null edge buffer");
+  cap_rows_kernel<<<ceil_div(num_rows * 32, 256), 256, 0, s>>>(row_ptr, src, num_rows, num_neighbors, seed, out_row_ptr, out_src,
+                                                               out_dst);
+  PG_LAUNCH_CHECK();
+  return PG_OK;
+}

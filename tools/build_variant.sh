@@ -5,7 +5,7 @@ set -e
 name=$1; shift
 cd "$(dirname "$0")/../point-gnn_b200/csrc"
 mkdir -p build/var_$name ../../lab
-for f in pg_api pg_graph pg_ops pg_edge_simt pg_tc; do
+for f in pg_api pg_graph pg_ops pg_edge_simt pg_tc pg_post pg_input; do
   /usr/local/cuda/bin/nvcc -O3 -std=c++17 -lineinfo -gencode arch=compute_100a,code=sm_100a -Xcompiler -fPIC \
     -Xcompiler -fvisibility=hidden --expt-relaxed-constexpr -Xptxas -v -DPG_LAB "$@" -c $f.cu -o build/var_$name/$f.o \
     2> build/var_$name/$f.ptxas.log &

@@ -33,6 +33,12 @@ bs = [torch.from_numpy(w[s + '/biases']).cuda(), torch.from_numpy(w[s + '_1/bias
 src, dst = edges[1][:, 0].contiguous(), edges[1][:, 1].contiguous()
 print('K', k, 'E1', src.numel())
 layer = _lib.PreparedLayer(_lib.PG_LAYER_EDGE_GNN, ws, bs, [303, 300, 300], prec)
+if prec == 1 and not os.environ.get('PG_TC_TRACE'):
+    ref = _lib.PreparedLayer(_lib.PG_LAYER_EDGE_GNN, ws, bs, [303, 300, 300], 0).edge_mlp_max(
+        feats, coords[1], coords[1], None, src, dst, k, trusted=True)
+    got = layer.edge_mlp_max(feats, coords[1], coords[1], None, src, dst, k, trusted=True)
+    print('max |tensor-core - fp32 FFMA| = %.3g (empty segments equal: %s)' % (
+        float((got - ref).abs()[ref > -1e30].max()), bool(((got < -1e30) == (ref < -1e30)).all())))
 for _ in range(2):
     layer.edge_mlp_max(feats, coords[1], coords[1], None, src, dst, k, trusted=True)
 torch.cuda.synchronize()
