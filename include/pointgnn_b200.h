@@ -161,6 +161,36 @@ PG_API int pg_multi_level_graph(const float* xyz, const int32_t* frame_ptr, int3
                          int64_t capacity0, int32_t* out_row_ptr1, int32_t* out_src1, int32_t* out_dst1,
                          int64_t capacity1, int64_t* out_sizes_host, void* stream);
 
+/*
+ * Training-time graph path (train.py:88-90 with configs/*_train_config: downsample_method 'random',
+ * add_rnd3d true, num_neighbors 256).  The reference draws from Python / NumPy global generators, so
+ * these two calls take their randomness as ARGUMENTS; everything else is reproduced exactly.
+ *
+ * pg_random_keypoints = multi_layer_downsampling_random for one scale (graph_gen.py:92-153):
+ *   voxel index of every point: floor_divide(p - frame_min, voxel) in float32 (shift_host == NULL, add_rnd3d
+ *   false, :124-126) or floor_divide(p - frame_min + voxel * shift, voxel) in float64 (:127-130), shift_host =
+ *   (host) [num_frames][3] the np.random.random((1,3)) draw of each frame;
+ *   one keypoint per occupied voxel, voxels in order of first appearance (the dict order of :133-139);
+ *   keypoint o = the floor(uniform[o] * count)-th point (ascending index) of its voxel - uniform [capacity]
+ *   device fp32 in [0,1) stands in for random.choice (:143-146).
+ * Outputs as pg_voxel_keypoints.
+ */
+PG_API int pg_random_keypoints(const float* xyz, const int32_t* frame_ptr, int32_t num_frames,
+                        int64_t num_points, const double* voxel_size_host, const double* shift_host,
+                        const float* uniform, int32_t* out_keypoint_idx, int64_t capacity,
+                        int32_t* out_kp_frame_ptr, int64_t* out_num_keypoints_host, void* stream);
+
+/*
+ * The random neighbour cap of gen_disjointed_rnn_local_graph_v3 (graph_gen.py:210-214) applied to a CSR graph
+ * (row_ptr [num_rows+1], src [E], rows ascending as pg_radius_graph emits them): rows with at most
+ * num_neighbors entries are copied, longer rows keep exactly num_neighbors distinct entries - those with the
+ * smallest hash(seed, row, src) priority, a uniformly random subset for a random seed (np.random.choice(...,
+ * replace=False)) - in ascending source order.  *out_num_edges_host = E'.
+ */
+PG_API int pg_cap_neighbors(const int32_t* row_ptr, const int32_t* src, int64_t num_rows, int32_t num_neighbors,
+                     uint32_t seed, int32_t* out_row_ptr, int32_t* out_src, int32_t* out_dst,
+                     int64_t capacity, int64_t* out_num_edges_host, void* stream);
+
 /* ------------------------------------------------------------------------ *
  * GNN ops  (reference models/gnn.py)
  * ------------------------------------------------------------------------ */

@@ -201,3 +201,66 @@ def batch_graphs(frames):
         b_edges.append(np.vstack(vertices))
     b_coord = [np.vstack([n_coord[b][lvl] for b in range(len(frames))]) for lvl in range(level_num)]
     return np.vstack(n_in), b_coord, b_kp, b_edges
+
+
+# ---------------------------------------------------------------------------------------------
+# training-time path (graph_gen.py:92-153, 210-214) with the randomness made explicit
+# ---------------------------------------------------------------------------------------------
+def multi_layer_downsampling_random(points_xyz, base_voxel_size, levels=(1,), add_rnd3d=False, shifts=None,
+                                    uniforms=None):
+    """graph_gen.py:92-153 with its two random sources as arguments: ``shifts[i]`` = the np.random.random((1,3))
+    draw of level i (add_rnd3d), ``uniforms[i][o]`` in [0,1) picks the point of the o-th voxel (first-appearance
+    order) as seq[floor(u * len(seq))] - what random.choice does with its own generator.  Same arithmetic as the
+    reference: float32 floor-division without the shift, float64 with it.
+    -> (vertex_coord_list, keypoint_indices_list)."""
+    points_xyz = np.asarray(points_xyz)
+    xyz_offset = np.asarray([np.amin(points_xyz, axis=0)])
+    vertex_coord_list = [points_xyz]
+    keypoint_indices_list = []
+    last_level = 0
+    for li, level in enumerate(levels):
+        last = vertex_coord_list[-1]
+        if np.isclose(last_level, level):
+            vertex_coord_list.append(np.copy(last))
+            keypoint_indices_list.append(np.expand_dims(np.arange(len(last)), axis=1))
+        else:
+            if not add_rnd3d:
+                xyz_idx = (last - xyz_offset) // (base_voxel_size * level)
+            else:
+                xyz_idx = (last - xyz_offset + base_voxel_size * level * np.asarray(shifts[li]).reshape(1, 3)) \
+                    // (base_voxel_size * level)
+            xyz_idx = xyz_idx.astype(np.int32)
+            dim_x, dim_y, _ = np.amax(xyz_idx, axis=0) + 1
+            keys = xyz_idx[:, 0] + xyz_idx[:, 1] * dim_x + xyz_idx[:, 2] * dim_y * dim_x
+            voxels = {}
+            for pidx, key in enumerate(keys.tolist()):
+                voxels.setdefault(key, []).append(pidx)
+            chosen = []
+            for o, key in enumerate(voxels):
+                seq = voxels[key]
+                pick = min(int(np.float32(uniforms[li][o]) * np.float32(len(seq))), len(seq) - 1)
+                chosen.append(seq[pick])
+            vertex_coord_list.append(last[chosen])
+            keypoint_indices_list.append(np.expand_dims(np.array(chosen), axis=1))
+        last_level = level
+    return vertex_coord_list, keypoint_indices_list
+
+
+def check_neighbor_cap(full_edges, capped_edges, num_neighbors):
+    """Invariants of graph_gen.py:210-214 that do not depend on the draw: per destination, rows of at most
+    num_neighbors entries are unchanged, longer rows keep exactly num_neighbors DISTINCT members of the row."""
+    full_edges, capped_edges = np.asarray(full_edges), np.asarray(capped_edges)
+    ndst = int(max(full_edges[:, 1].max(), capped_edges[:, 1].max())) + 1 if len(full_edges) else 0
+    f_cnt = np.bincount(full_edges[:, 1], minlength=ndst)
+    c_cnt = np.bincount(capped_edges[:, 1], minlength=ndst)
+    assert np.array_equal(c_cnt, np.minimum(f_cnt, num_neighbors)), 'row lengths'
+    full_set = set(map(tuple, full_edges.tolist()))
+    cap_list = list(map(tuple, capped_edges.tolist()))
+    assert len(set(cap_list)) == len(cap_list), 'duplicate edge'
+    assert all(e in full_set for e in cap_list), 'edge outside the radius graph'
+    short = f_cnt <= num_neighbors
+    keep = short[full_edges[:, 1]]
+    want = set(map(tuple, full_edges[keep].tolist()))
+    got = set(e for e in cap_list if short[e[1]])
+    assert want == got, 'an uncapped row changed'
+    return int((~short).sum())

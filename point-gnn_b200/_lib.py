@@ -40,6 +40,11 @@ SIGNATURES = {
                                             ctypes.c_double, ctypes.c_double, c_i32p, c_i64, c_i32p, c_f32p,
                                             c_i32p, c_i32p, c_i32p, c_i64, c_i32p, c_i32p, c_i32p, c_i64,
                                             ctypes.POINTER(c_i64), ctypes.c_void_p]),
+    'pg_random_keypoints': (ctypes.c_int, [c_f32p, c_i32p, c_i32, c_i64, ctypes.POINTER(ctypes.c_double),
+                                           ctypes.POINTER(ctypes.c_double), c_f32p, c_i32p, c_i64, c_i32p,
+                                           ctypes.POINTER(c_i64), ctypes.c_void_p]),
+    'pg_cap_neighbors': (ctypes.c_int, [c_i32p, c_i32p, c_i64, c_i32, ctypes.c_uint32, c_i32p, c_i32p, c_i32p, c_i64,
+                                        ctypes.POINTER(c_i64), ctypes.c_void_p]),
     'pg_scatter_max': (ctypes.c_int, [c_f32p, c_i32p, c_i64, c_i32, c_i64, c_f32p, ctypes.c_void_p]),
     'pg_gather_rows': (ctypes.c_int, [c_f32p, c_i64, c_i32, c_i32p, c_i64, c_f32p, ctypes.c_void_p]),
     'pg_fully_connected': (ctypes.c_int, [c_f32p, c_i64, c_i32, c_f32p, c_f32p, c_i32, c_i32, c_f32p, c_f32p,
@@ -160,6 +165,43 @@ def voxel_keypoints(xyz, frame_ptr, voxel_size):
                                   num_frames, n, vs, _ptr(out_idx, torch.int32, 'out'), n,
                                   _ptr(out_fp, torch.int32, 'out_fp'), ctypes.byref(k), _stream()))
     return out_idx[:k.value], out_fp
+
+
+def random_keypoints(xyz, frame_ptr, voxel_size, shift, uniform):
+    """pg_random_keypoints.  shift: None or [F,3] float64 host array; uniform: [N] CUDA fp32 in [0,1).
+    -> (keypoint_idx [K] int32, kp_frame_ptr [F+1] int32)."""
+    import numpy as np
+    lib = load()
+    n = xyz.shape[0]
+    num_frames = frame_ptr.numel() - 1
+    out_idx = torch.empty(n, dtype=torch.int32, device=xyz.device)
+    out_fp = torch.empty(num_frames + 1, dtype=torch.int32, device=xyz.device)
+    vs = (ctypes.c_double * 3)(*[float(v) for v in voxel_size])
+    sh = None
+    if shift is not None:
+        sh_arr = np.ascontiguousarray(shift, dtype=np.float64).reshape(num_frames, 3)
+        sh = sh_arr.ctypes.data_as(ctypes.POINTER(ctypes.c_double))
+    k = c_i64(0)
+    _check(lib.pg_random_keypoints(_ptr(xyz, torch.float32, 'xyz'), _ptr(frame_ptr, torch.int32, 'frame_ptr'), num_frames,
+                                   n, vs, sh, _ptr(uniform, torch.float32, 'uniform'), _ptr(out_idx, torch.int32, 'out'), n,
+                                   _ptr(out_fp, torch.int32, 'out_fp'), ctypes.byref(k), _stream()))
+    return out_idx[:k.value], out_fp
+
+
+def cap_neighbors(row_ptr, edges, num_neighbors, seed):
+    """pg_cap_neighbors on the (row_ptr, [2,E] edges) pair of radius_graph.  -> (row_ptr', [2,E'] edges)."""
+    lib = load()
+    num_rows = row_ptr.numel() - 1
+    e = edges.shape[1]
+    out_rp = torch.empty_like(row_ptr)
+    buf = torch.empty((2, max(e, 1)), dtype=torch.int32, device=edges.device)
+    n = c_i64(0)
+    src = edges[0].contiguous() if e else edges.new_zeros(1)
+    _check(lib.pg_cap_neighbors(_ptr(row_ptr, torch.int32, 'row_ptr'), _ptr(src, torch.int32, 'src'), num_rows,
+                                int(num_neighbors), ctypes.c_uint32(int(seed) & 0xffffffff),
+                                _ptr(out_rp, torch.int32, 'out_rp'), ctypes.c_void_p(buf[0].data_ptr()),
+                                ctypes.c_void_p(buf[1].data_ptr()), buf.shape[1], ctypes.byref(n), _stream()))
+    return out_rp, buf[:, :n.value]
 
 
 _edge_capacity = {}

@@ -8,9 +8,14 @@
 
 Inputs may be NumPy arrays (the reference's calling convention, run.py:219-222: arrays are
 copied to the GPU, results copied back as NumPy) or torch CUDA tensors (results stay on the
-device).  The deterministic inference path is implemented (``add_rnd3d=False``,
-``downsample_method='center'``, ``num_neighbors <= 0``); the training-time random variants
-(graph_gen.py:24-39, 92-153, 210-214) draw from Python's RNG and are out of scope.
+device).  Built: the deterministic inference path (``add_rnd3d=False``, ``downsample_method='center'``,
+``num_neighbors <= 0``) and the training-time path of train.py:88-90 with configs/*_train_config
+(``downsample_method='random'`` with or without ``add_rnd3d``, ``num_neighbors > 0``,
+graph_gen.py:92-153, 210-214).  The random path takes its randomness from NumPy's global generator for
+the per-frame grid shift - the same ``np.random.random((1, 3))`` draw as the reference - and from this
+module's CUDA generator (``set_seed``) for the per-voxel choice and the neighbour cap, where the
+reference uses Python's ``random`` / ``np.random.choice``: results are equal in distribution, not draw
+by draw.  ``add_rnd3d`` with the centroid method (graph_gen.py:24-39) is not built.
 
 Extra, backwards-compatible keyword ``frame_ptr``: a [F+1] int array batching F frames in one
 call; the result is then exactly what the reference's ``batch_data`` (train.py:135-171) builds
@@ -23,6 +28,22 @@ import numpy as np
 import torch
 
 from .. import _lib
+
+
+_rng = {'gen': None}
+
+
+def set_seed(seed):
+    """Seed of the generator behind the random keypoint choice and the random neighbour cap."""
+    g = torch.Generator(device=_device())
+    g.manual_seed(int(seed))
+    _rng['gen'] = g
+
+
+def _generator():
+    if _rng['gen'] is None:
+        set_seed(torch.initial_seed() & 0x7fffffff)
+    return _rng['gen']
 
 
 def _device():
@@ -100,17 +121,66 @@ def _downsampling_select(cloud, base_voxel_size, levels, add_rnd3d):
     return vertex_coord_list, keypoint_indices_list, frame_ptr_list
 
 
+def multi_layer_downsampling_random(points_xyz, base_voxel_size, levels=[1], add_rnd3d=False):
+    """graph_gen.py:92-153.  -> (vertex_coord_list, keypoint_indices_list)."""
+    cloud = _Cloud(points_xyz)
+    vertex_coord_list, keypoint_indices_list, _ = _downsampling_random(cloud, base_voxel_size, levels, add_rnd3d)
+    if cloud.numpy_io:
+        vertex_coord_list = [v.cpu().numpy() for v in vertex_coord_list]
+        keypoint_indices_list = [k.cpu().numpy().astype(np.int64) for k in keypoint_indices_list]
+    return vertex_coord_list, keypoint_indices_list
+
+
+def _downsampling_random(cloud, base_voxel_size, levels, add_rnd3d, uniform=None, shifts=None):
+    """Device-side body of multi_layer_downsampling_random.  ``uniform`` / ``shifts`` (tests): explicit random
+    numbers instead of draws from the generators."""
+    vertex_coord_list = [cloud.xyz]
+    frame_ptr_list = [cloud.frame_ptr]
+    keypoint_indices_list = []
+    last_level = 0
+    num_frames = cloud.frame_ptr.numel() - 1
+    for li, level in enumerate(levels):
+        base_points = vertex_coord_list[-1]
+        if np.isclose(level, last_level):
+            vertex_coord_list.append(base_points)
+            frame_ptr_list.append(frame_ptr_list[-1])
+            kidx = torch.arange(base_points.shape[0], dtype=torch.int32, device=base_points.device)[:, None]
+            kidx._pg_trusted = (int(base_points.shape[0]), kidx._version)
+            keypoint_indices_list.append(kidx)
+        else:
+            # graph_gen.py:115: the PREVIOUS level is voxelised (not the original cloud as in the centroid method)
+            shift = None
+            if add_rnd3d:       # one np.random.random((1, 3)) per frame, as each fetch_data call draws (train.py:88-90)
+                shift = shifts[li] if shifts is not None else np.vstack(
+                    [np.random.random((1, 3)) for _ in range(num_frames)])
+            u = uniform[li] if uniform is not None else torch.rand(base_points.shape[0], generator=_generator(),
+                                                                   device=base_points.device, dtype=torch.float32)
+            idx, kp_fp = _lib.random_keypoints(base_points, frame_ptr_list[-1], _voxel_vector(base_voxel_size, level),
+                                               shift, u)
+            vertex_coord_list.append(_lib.gather_rows(base_points, idx))
+            frame_ptr_list.append(kp_fp)
+            kidx = idx[:, None]
+            kidx._pg_trusted = (int(base_points.shape[0]), kidx._version)
+            keypoint_indices_list.append(kidx)
+        last_level = level
+    return vertex_coord_list, keypoint_indices_list, frame_ptr_list
+
+
 def _radius_edges(points, point_fp, centers, center_fp, radius, num_neighbors,
-                  neighbors_downsample_method='random', scale=None):
-    if num_neighbors > 0:
-        raise NotImplementedError('num_neighbors > 0 is the training-time random neighbour cap '
-                                  '(graph_gen.py:210-214); inference configs use -1')
+                  neighbors_downsample_method='random', scale=None, cap_seed=None):
+    if num_neighbors > 0 and neighbors_downsample_method != 'random':
+        raise NotImplementedError('only neighbors_downsample_method="random" exists in the reference (graph_gen.py:211)')
     if scale is not None and not np.all(np.asarray(scale, dtype=np.float64) == 1.0):
         # graph_gen.py:203-206 divides in float64 and builds the tree on float64 coordinates; dividing in
         # float32 here would move boundary edges.  No shipped config passes `scale`.
         raise NotImplementedError('per-axis `scale` of gen_disjointed_rnn_local_graph_v3 is not built '
                                   '(unused by every shipped config)')
-    _, edges = _lib.radius_graph(points, point_fp, centers, center_fp, radius)
+    row_ptr, edges = _lib.radius_graph(points, point_fp, centers, center_fp, radius)
+    if num_neighbors > 0:
+        # graph_gen.py:210-214: rows longer than num_neighbors keep a random subset of that size
+        seed = cap_seed if cap_seed is not None else int(torch.randint(0, 2 ** 31 - 1, (1,), generator=_generator(),
+                                                                      device=points.device))
+        _, edges = _lib.cap_neighbors(row_ptr, edges, num_neighbors, seed)
     edges = edges.t()     # [E,2] view whose columns (src, dst) are contiguous
     # index ranges are guaranteed by construction: lets model.predict skip the per-layer range check
     edges._pg_trusted = (int(points.shape[0]), int(centers.shape[0]), edges._version)
@@ -164,20 +234,24 @@ def gen_multi_level_local_graph_v3(points_xyz, base_voxel_size, level_configs, a
     """graph_gen.py:155-195.  -> (vertex_coord_list, keypoint_indices_list, edges_list)."""
     if isinstance(base_voxel_size, list):
         base_voxel_size = np.array(base_voxel_size)
-    if downsample_method != 'center':
-        raise NotImplementedError("downsample_method='random' is training-only (graph_gen.py:92-153)")
+    if downsample_method not in ('center', 'random'):
+        raise KeyError(downsample_method)
     cloud = _Cloud(points_xyz, frame_ptr)
     scales = [config['graph_scale'] for config in level_configs]
     for config in level_configs:
         if config['graph_gen_method'] != 'disjointed_rnn_local_graph_v3':
             raise KeyError(config['graph_gen_method'])
-    if _is_two_level(level_configs, add_rnd3d) and cloud.xyz.shape[0] > 0:
+    if downsample_method == 'center' and _is_two_level(level_configs, add_rnd3d) and cloud.xyz.shape[0] > 0:
         # the structure of every shipped config: ONE library call, one host round trip
         vertex_coord_list, keypoint_indices_list, edges_list, frame_ptr_list = _two_level_graph(
             cloud, base_voxel_size, level_configs)
     else:
-        vertex_coord_list, keypoint_indices_list, frame_ptr_list = _downsampling_select(
-            cloud, base_voxel_size, scales, add_rnd3d)
+        if downsample_method == 'center':
+            vertex_coord_list, keypoint_indices_list, frame_ptr_list = _downsampling_select(
+                cloud, base_voxel_size, scales, add_rnd3d)
+        else:       # graph_gen.py:179-181
+            vertex_coord_list, keypoint_indices_list, frame_ptr_list = _downsampling_random(
+                cloud, base_voxel_size, scales, add_rnd3d)
         edges_list = []
         for config in level_configs:
             graph_level = config['graph_level']

@@ -133,13 +133,12 @@ def test_per_axis_voxel_and_training_paths_raise(car):
     kw['base_voxel_size'] = [0.8, 0.6, 1.0]                   # graph_gen.py:172-173
     got = graph_gen.gen_multi_level_local_graph_v3(xyz, **kw)
     _check_graph(xyz, kw, got)
-    with pytest.raises(NotImplementedError):
+    with pytest.raises(NotImplementedError):      # random grid shift with the CENTROID method (graph_gen.py:24-39): not built
         graph_gen.gen_multi_level_local_graph_v3(xyz, 0.8, car.graph_kwargs['level_configs'], add_rnd3d=True)
-    with pytest.raises(NotImplementedError):
-        graph_gen.gen_multi_level_local_graph_v3(xyz, 0.8, car.graph_kwargs['level_configs'],
-                                                 downsample_method='random')
-    with pytest.raises(NotImplementedError):
-        graph_gen.gen_disjointed_rnn_local_graph_v3(xyz, xyz[:10], 1.0, 256)
+    with pytest.raises(NotImplementedError):      # per-axis `scale` (graph_gen.py:203-206): not built
+        graph_gen.gen_disjointed_rnn_local_graph_v3(xyz, xyz[:10], 1.0, -1, scale=[1.0, 2.0, 1.0])
+    with pytest.raises(KeyError):
+        graph_gen.gen_multi_level_local_graph_v3(xyz, 0.8, car.graph_kwargs['level_configs'], downsample_method='nope')
 
 
 def test_large_cloud_properties(car):

@@ -174,8 +174,48 @@ def kitti_goldens():
     print('kitti: points in image', pts.xyz.shape, 'result lines', text.count('\n') - 1)
 
 
+def graph_random_goldens():
+    """tests/golden/graph_random.npz: the reference's OWN multi_layer_downsampling_random (graph_gen.py:92-153) with its
+    two random sources patched to recorded numbers: np.random.random -> `shift`, random.choice(seq) ->
+    seq[floor(u[o] * len(seq))] for the o-th call.  The CUDA path gets the same numbers as arguments and must return
+    the same keypoints, with and without add_rnd3d."""
+    import random as _random
+    ref = reference_graph.load()
+    xyz, _ = synth.lidar_frame(3, 8000)
+    rng = np.random.default_rng(0)
+    out = {'xyz': xyz}
+    for add in (False, True):
+        shift = rng.random((1, 3))
+        u = rng.random(len(xyz)).astype(np.float32)
+        counter = {'o': 0}
+
+        def fake_choice(seq):
+            o = counter['o']
+            counter['o'] += 1
+            return seq[min(int(np.float32(u[o]) * np.float32(len(seq))), len(seq) - 1)]
+
+        orig_choice, orig_rand = _random.choice, np.random.random
+        _random.choice = fake_choice
+        np.random.random = lambda size=None: shift.copy()
+        try:
+            vc, kp = ref.multi_layer_downsampling_random(xyz, 0.8, [1, 1], add_rnd3d=add)
+        finally:
+            _random.choice, np.random.random = orig_choice, orig_rand
+        tag = 'rnd3d' if add else 'plain'
+        out['shift_' + tag] = shift
+        out['u_' + tag] = u
+        out['kp_' + tag] = kp[0][:, 0].astype(np.int32)
+        vc2, kp2 = graph.multi_layer_downsampling_random(xyz, 0.8, [1, 1], add_rnd3d=add, shifts=[shift, None],
+                                                         uniforms=[u, None])
+        assert np.array_equal(kp[0], kp2[0]) and np.array_equal(vc[1], vc2[1]), 'oracle restatement != reference'
+        print('graph_random', tag, 'keypoints', len(kp[0]))
+    np.savez_compressed(os.path.join(GOLDEN, 'graph_random.npz'), **out)
+
+
 if __name__ == '__main__':
     which = sys.argv[1] if len(sys.argv) > 1 else 'all'
+    if which in ('all', 'graph_random'):
+        graph_random_goldens()
     if which in ('all', 'gnn'):
         main()
     if which in ('all', 'post'):
