@@ -271,8 +271,10 @@ def multi_level_graph(xyz, frame_ptr, voxel_size, radius0, radius1):
             if k > kcap:      # the edge counts were computed on a truncated keypoint set: scale them up too
                 cap0, cap1 = max(cap0, int(n0 * 1.3 * k / kcap) + 1024), max(cap1, int(n1 * 1.7 * k / kcap) + 1024)
                 kcap = int(k * 1.25) + 64
-            else:
+            elif n0 > cap0 or n1 > cap1:
                 cap0, cap1 = max(cap0, int(n0 * 1.25) + 1024), max(cap1, int(n1 * 1.25) + 1024)
+            else:             # the internal hit-parking buffer (10 x the edge capacity) overflowed
+                cap0, cap1 = 2 * int(cap0), 2 * int(cap1)
             continue
         _check(code)
         break

@@ -28,6 +28,7 @@ constexpr double kCellSlack = 1.0001;  // cell edge = radius * slack, keeps +-1 
 constexpr int kErrRange = 1;       // cloud extent exceeds the key bits
 constexpr int kErrFramePtr = 2;    // point frame_ptr does not run from 0 to N
 constexpr int kErrCenterPtr = 4;   // centre frame_ptr does not run from 0 to K
+constexpr int kErrParking = 8;     // pg_multi_level_graph: hit parking buffer too small (retry with larger edge capacity)
 
 __host__ __device__ inline uint64_t make_key(uint32_t frame, uint32_t iz, uint32_t iy, uint32_t ix) {
   return (uint64_t(frame) << 48) | (uint64_t(iz) << 32) | (uint64_t(iy) << 16) | uint64_t(ix);
@@ -305,6 +306,86 @@ __global__ void __launch_bounds__(256) radius_query_kernel(
   }
 }
 
+// ---- single-traversal variant (pg_multi_level_graph) -------------------------------------------------------------
+// Pass A, one THREAD per centre: the nine sorted-point ranges of its 3 x 3 x 3 cell neighbourhood (18 ints) and
+// their total length = an upper bound of the row length.  No point is touched.
+__global__ void radius_candidates_kernel(SortedGrid g, GridSpec spec, const uint32_t* __restrict__ bounds,
+                                         const float* __restrict__ centers, const int32_t* __restrict__ center_frame_ptr,
+                                         int num_frames, int64_t num_centers_cap, const int32_t* __restrict__ num_centers_dev,
+                                         int32_t* __restrict__ ranges, int32_t* __restrict__ cand, int* __restrict__ err) {
+  const int64_t c = int64_t(blockIdx.x) * blockDim.x + threadIdx.x;
+  if (c > num_centers_cap) return;
+  const int64_t num_centers = min(int64_t(*num_centers_dev), num_centers_cap);
+  if (c >= num_centers) {
+    cand[c] = 0;
+    return;
+  }
+  if (c == 0 && (center_frame_ptr[0] != 0 || int64_t(center_frame_ptr[num_frames]) != int64_t(*num_centers_dev)))
+    atomicOr(err, kErrCenterPtr);
+  const int f = find_frame(center_frame_ptr, num_frames, c);
+  long long ix, iy, iz;
+  cell_of(spec, bounds, f, centers[3 * c], centers[3 * c + 1], centers[3 * c + 2], &ix, &iy, &iz);
+  const long long x0 = max(ix - 1, 0ll), x1 = min(ix + 1, (long long)kAxisMax);
+  int total = 0, k = 0;
+  for (long long zz = iz - 1; zz <= iz + 1; ++zz) {
+    for (long long yy = iy - 1; yy <= iy + 1; ++yy, ++k) {
+      int b = 0, e = 0;
+      if (x0 <= x1 && zz >= 0 && zz <= kAxisMax && yy >= 0 && yy <= kAxisMax)
+        row_range(g, uint32_t(f), uint32_t(zz), uint32_t(yy), uint32_t(x0), uint32_t(x1), &b, &e);
+      ranges[c * 18 + 2 * k] = b;
+      ranges[c * 18 + 2 * k + 1] = e;
+      total += e - b;
+    }
+  }
+  cand[c] = total;
+}
+
+// Pass B, one WARP per centre: the only traversal of the points.  Hits are parked, compacted in traversal order, at
+// tmp[cand_off[c] ...] (cand_off = exclusive scan of the candidate counts, so the slots never overlap); counts[c]
+// = row length.  The row sort then reads the parked hits and writes the final CSR row.
+__global__ void __launch_bounds__(256) radius_collect_kernel(SortedGrid g, const float* __restrict__ centers,
+                                                             int64_t num_centers_cap,
+                                                             const int32_t* __restrict__ num_centers_dev, double r2,
+                                                             const int32_t* __restrict__ ranges,
+                                                             const int32_t* __restrict__ cand_off, int64_t tmp_capacity,
+                                                             int32_t* __restrict__ tmp, int32_t* __restrict__ counts,
+                                                             unsigned long long* __restrict__ total64, int* __restrict__ err) {
+  const int lane = threadIdx.x & 31;
+  const int64_t c = (int64_t(blockIdx.x) * blockDim.x + threadIdx.x) >> 5;
+  const int64_t num_centers = min(int64_t(*num_centers_dev), num_centers_cap);
+  if (c >= num_centers) return;
+  if (int64_t(cand_off[num_centers_cap]) > tmp_capacity) {     // the parking buffer is too small: reported by the host
+    if (c == 0 && lane == 0) atomicOr(err, kErrParking);
+    return;
+  }
+  const double cx = double(centers[3 * c]), cy = double(centers[3 * c + 1]), cz = double(centers[3 * c + 2]);
+  const int base = cand_off[c];
+  int total = 0;
+  int rb = 0, re = 0;
+  if (lane < 18) rb = ranges[c * 18 + lane];
+  for (int k = 0; k < 9; ++k) {
+    const int b = __shfl_sync(0xffffffffu, rb, 2 * k), e = __shfl_sync(0xffffffffu, rb, 2 * k + 1);
+    (void)re;
+    for (int i0 = b; i0 < e; i0 += 32) {
+      const int i = i0 + lane;
+      bool hit = false;
+      int idx = 0;
+      if (i < e) {
+        const float4 p = g.pts[i];
+        hit = dist2_rn(cx, cy, cz, p.x, p.y, p.z) <= r2;
+        idx = __float_as_int(p.w);
+      }
+      const uint32_t m = __ballot_sync(0xffffffffu, hit);
+      if (hit) tmp[base + total + __popc(m & ((1u << lane) - 1u))] = idx;
+      total += __popc(m);
+    }
+  }
+  if (lane == 0) {
+    counts[c] = total;
+    atomicAdd(total64, (unsigned long long)total);
+  }
+}
+
 // Sort every CSR row ascending (canonical order) and expand the destination index.
 // Bitonic network in its "all comparators ascending" form (flip stage i^(k-1), then half-cleaners
 // i^j): with every comparator ascending, virtual +inf padding at the tail never moves, so rows of
@@ -315,9 +396,13 @@ constexpr int kWarpRowMax = 1024;   // rows up to this length are sorted by one 
 // One warp per CSR row: classic bitonic network in the warp's private slice of shared memory, padded with
 // INT_MAX to a power of two, __syncwarp between stages (no block barrier: KITTI-shape rows have ~100-600
 // entries, and the block-per-row version spent its time in 36+ __syncthreads per row).  Also expands dst.
+// `in` / `in_off` (optional): the unsorted hits of row r sit at in[in_off[r] ...] (radius_collect_kernel) instead of
+// in src[row_ptr[r] ...]; the sorted row is always written to src.
 __global__ void __launch_bounds__(256) sort_rows_warp_kernel(const int32_t* __restrict__ row_ptr, int64_t num_rows,
                                                               int32_t* __restrict__ src, int32_t* __restrict__ dst,
-                                                              int* __restrict__ has_long_rows, int64_t capacity) {
+                                                              int* __restrict__ has_long_rows, int64_t capacity,
+                                                              const int32_t* __restrict__ in = nullptr,
+                                                              const int32_t* __restrict__ in_off = nullptr) {
   __shared__ int32_t srows[8][kWarpRowMax];
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   if (int64_t(row_ptr[num_rows]) > capacity) return;      // the edge buffer was too small: nothing was filled
@@ -328,11 +413,16 @@ __global__ void __launch_bounds__(256) sort_rows_warp_kernel(const int32_t* __re
     if (dst != nullptr)
       for (int i = lane; i < len; i += 32) dst[b + i] = int32_t(r);
     if (len > kWarpRowMax && lane == 0) *has_long_rows = 1;   // tells sort_rows_kernel there is work for it
-    if (len <= 1 || len > kWarpRowMax) continue;      // long rows: sort_rows_kernel
+    if (len > kWarpRowMax) continue;                  // long rows: sort_rows_kernel
+    const int32_t* rin = in ? in + in_off[r] : src + b;
+    if (len <= 1) {
+      if (in && len == 1 && lane == 0) src[b] = rin[0];
+      continue;
+    }
     int n = 2;
     while (n < len) n <<= 1;
     __syncwarp();
-    for (int i = lane; i < n; i += 32) a[i] = i < len ? src[b + i] : 0x7fffffff;
+    for (int i = lane; i < n; i += 32) a[i] = i < len ? rin[i] : 0x7fffffff;
     __syncwarp();
     for (int k = 2; k <= n; k <<= 1) {
       for (int j = k >> 1; j > 0; j >>= 1) {
@@ -351,7 +441,9 @@ __global__ void __launch_bounds__(256) sort_rows_warp_kernel(const int32_t* __re
 
 __global__ void __launch_bounds__(256) sort_rows_kernel(const int32_t* __restrict__ row_ptr, int64_t num_rows,
                                                          int32_t* __restrict__ src, int32_t* __restrict__ dst,
-                                                         const int* __restrict__ has_long_rows, int64_t capacity) {
+                                                         const int* __restrict__ has_long_rows, int64_t capacity,
+                                                         const int32_t* __restrict__ in = nullptr,
+                                                         const int32_t* __restrict__ in_off = nullptr) {
   extern __shared__ int32_t srow[];
   if (*has_long_rows == 0 || int64_t(row_ptr[num_rows]) > capacity) return;                      // the usual case: every row was sorted by a warp
   for (int64_t r = blockIdx.x; r < num_rows; r += gridDim.x) {
@@ -363,8 +455,11 @@ __global__ void __launch_bounds__(256) sort_rows_kernel(const int32_t* __restric
     while (n < len) n <<= 1;
     const bool in_smem = len <= kRowSortMax;
     int32_t* a = in_smem ? srow : src + b;
+    const int32_t* rin = in ? in + in_off[r] : src + b;
     if (in_smem) {
-      for (int i = threadIdx.x; i < len; i += blockDim.x) srow[i] = src[b + i];
+      for (int i = threadIdx.x; i < len; i += blockDim.x) srow[i] = rin[i];
+    } else if (in) {
+      for (int i = threadIdx.x; i < len; i += blockDim.x) src[b + i] = rin[i];     // sorted in place in global memory
     }
     __syncthreads();
     for (int k = 2; k <= n; k <<= 1) {
@@ -474,6 +569,10 @@ int graph_error(int err) {
   if (err & kErrRange) {
     set_error("point cloud extent exceeds %d grid cells per axis", kAxisMax + 1);
     return PG_ERR_RANGE;
+  }
+  if (err & kErrParking) {
+    set_error("radius graph: hit parking buffer too small for this cloud; repeat with a larger edge capacity");
+    return PG_ERR_CAPACITY;
   }
   return PG_OK;
 }
@@ -641,33 +740,42 @@ static int radius_level_device(RadiusPlan& plan, const float* centers, const int
                                int64_t kp_capacity, const int32_t* num_centers_dev, int32_t* out_row_ptr,
                                int32_t* out_src, int32_t* out_dst, int64_t capacity, unsigned long long* total64,
                                cudaStream_t s) {
-  Temp counts, tmp, has_long;
+  // candidates per row are ~6.5x the hits (27 cells of edge r against the ball of radius r); the parking buffer is
+  // sized from the caller's edge capacity and its overflow is reported like an edge-buffer overflow
+  const int64_t tmp_capacity = std::min<int64_t>(capacity * 10 + 4096, (int64_t(1) << 31) - 1);
+  Temp counts, cand, cand_off, ranges, parked, tmp, has_long;
   PG_CUDA_OK(counts.alloc(sizeof(int32_t) * (kp_capacity + 1), s));
   PG_CUDA_OK(cudaMemsetAsync(counts.ptr, 0, sizeof(int32_t) * (kp_capacity + 1), s));
-  const int qblocks = int(ceil_div(kp_capacity * 32, 256));
-  radius_query_kernel<false><<<qblocks, 256, 0, s>>>(plan.grid.view, plan.spec, plan.grid.bounds.as<uint32_t>(), centers,
-                                                     center_frame_ptr, num_frames, kp_capacity, num_centers_dev, plan.r2,
-                                                     counts.as<int32_t>(), nullptr, nullptr, 0, plan.grid.err.as<int>(),
-                                                     total64);
+  PG_CUDA_OK(cand.alloc(sizeof(int32_t) * (kp_capacity + 1), s));
+  PG_CUDA_OK(cand_off.alloc(sizeof(int32_t) * (kp_capacity + 1), s));
+  PG_CUDA_OK(ranges.alloc(sizeof(int32_t) * 18 * kp_capacity, s));
+  PG_CUDA_OK(parked.alloc(sizeof(int32_t) * tmp_capacity, s));
+  radius_candidates_kernel<<<ceil_div(kp_capacity + 1, 128), 128, 0, s>>>(
+      plan.grid.view, plan.spec, plan.grid.bounds.as<uint32_t>(), centers, center_frame_ptr, num_frames, kp_capacity,
+      num_centers_dev, ranges.as<int32_t>(), cand.as<int32_t>(), plan.grid.err.as<int>());
   PG_LAUNCH_CHECK();
   size_t bytes = 0;
-  PG_CUDA_OK(cub::DeviceScan::ExclusiveSum(nullptr, bytes, counts.as<int32_t>(), out_row_ptr, int(kp_capacity + 1), s));
+  PG_CUDA_OK(cub::DeviceScan::ExclusiveSum(nullptr, bytes, cand.as<int32_t>(), cand_off.as<int32_t>(), int(kp_capacity + 1), s));
   PG_CUDA_OK(tmp.alloc(bytes, s));
+  PG_CUDA_OK(cub::DeviceScan::ExclusiveSum(tmp.ptr, bytes, cand.as<int32_t>(), cand_off.as<int32_t>(), int(kp_capacity + 1), s));
+  count_launch(2);
+  radius_collect_kernel<<<ceil_div(kp_capacity * 32, 256), 256, 0, s>>>(
+      plan.grid.view, centers, kp_capacity, num_centers_dev, plan.r2, ranges.as<int32_t>(), cand_off.as<int32_t>(),
+      tmp_capacity, parked.as<int32_t>(), counts.as<int32_t>(), total64, plan.grid.err.as<int>());
+  PG_LAUNCH_CHECK();
   PG_CUDA_OK(cub::DeviceScan::ExclusiveSum(tmp.ptr, bytes, counts.as<int32_t>(), out_row_ptr, int(kp_capacity + 1), s));
   count_launch(2);
   // rows beyond the real number of centres are empty, so row_ptr[c] == E for every c >= K
-  radius_query_kernel<true><<<qblocks, 256, 0, s>>>(plan.grid.view, plan.spec, plan.grid.bounds.as<uint32_t>(), centers,
-                                                    center_frame_ptr, num_frames, kp_capacity, num_centers_dev, plan.r2,
-                                                    nullptr, out_row_ptr, out_src, capacity, nullptr, nullptr);
-  PG_LAUNCH_CHECK();
   PG_CUDA_OK(has_long.alloc(sizeof(int), s));
   PG_CUDA_OK(cudaMemsetAsync(has_long.ptr, 0, sizeof(int), s));
   const int wblocks = int(std::min<int64_t>(ceil_div(kp_capacity, 8), int64_t(num_sms()) * 6));
-  sort_rows_warp_kernel<<<wblocks, 256, 0, s>>>(out_row_ptr, kp_capacity, out_src, out_dst, has_long.as<int>(), capacity);
+  sort_rows_warp_kernel<<<wblocks, 256, 0, s>>>(out_row_ptr, kp_capacity, out_src, out_dst, has_long.as<int>(), capacity,
+                                                parked.as<int32_t>(), cand_off.as<int32_t>());
   PG_LAUNCH_CHECK();
   const int blocks = int(std::min<int64_t>(kp_capacity, int64_t(num_sms()) * 4));
   sort_rows_kernel<<<blocks, 256, kRowSortMax * sizeof(int32_t), s>>>(out_row_ptr, kp_capacity, out_src, out_dst,
-                                                                      has_long.as<int>(), capacity);
+                                                                      has_long.as<int>(), capacity, parked.as<int32_t>(),
+                                                                      cand_off.as<int32_t>());
   PG_LAUNCH_CHECK();
   return PG_OK;
 }

@@ -557,6 +557,100 @@ __device__ __forceinline__ void gnn_rows_producer(const TcParams& p, const SmemM
   }
 }
 
+// A-operand producer of the dense layers (PROD_ROWS), four lanes per matrix row: lane (rr, c) of warp wg loads the
+// 16-byte slice c of the k-step for rows 32 wg + rr + 8 i (i = 0..3), so that one LDG.128 covers 8 rows x 64
+// contiguous bytes (8 cache lines) instead of 32 rows x 16 bytes (32 lines) - the change that took the fused edge
+// kernel's producers off the L1 wavefront limit (DESIGN.md optimisation log #4), applied to row_gemm_tc_kernel.
+// Two groups of four warps, group g produces ring iterations g, g + 2, ...; two register buffers ping-pong.
+__device__ __forceinline__ void rows4_producer(const TcParams& p, const SmemMap& sm, int pt, int lane, uint32_t rank,
+                                               int64_t cluster_id, int64_t num_clusters) {
+  const int g = pt >> 7, wg = (pt >> 5) & 3;
+  const int rr = lane >> 2, c = lane & 3;
+  const uint32_t a_off0 = uint32_t(wg * 4) * 256u + uint32_t(c >> 1) * 128u + uint32_t(rr) * 16u + uint32_t(c & 1) * 8u;
+  const int64_t my_tiles = (p.num_pair_tiles - cluster_id + num_clusters - 1) / num_clusters;
+  if (my_tiles <= 0) return;
+  const int ks = p.ks;
+  // row pointers of this lane's four rows in tile jj (rows past the end read row 0: the epilogue drops them)
+  auto row_ptrs = [&](int64_t jj, const float* (&rp)[4]) {
+    const int64_t base = (cluster_id + jj * num_clusters) * 256 + int64_t(rank) * kTileRows + wg * 32 + rr;
+#pragma unroll
+    for (int i = 0; i < 4; ++i) {
+      const int64_t row = base + 8 * i;
+      rp[i] = p.P + (row < p.num_rows ? row : 0) * int64_t(p.ldp) + c * 4;
+    }
+  };
+  auto load = [&](float4 (&q)[4], const float* const (&rp)[4], int ss) {
+    const bool in_k = ss * 16 + c * 4 + 4 <= p.k_real;
+#pragma unroll
+    for (int i = 0; i < 4; ++i) q[i] = in_k ? ldg_nc_pinned(rp[i] + ss * 16) : make_float4(0.f, 0.f, 0.f, 0.f);
+  };
+  int64_t j = 0;
+  int s = g;
+  uint32_t stage = uint32_t(g), phase = 0;
+  const float* rp_cur[4];
+  const float* rp_nxt[4];
+  row_ptrs(0, rp_cur);
+  row_ptrs(1, rp_nxt);
+  auto advance = [&](int64_t& jj, int& ss) {
+    ss += 2;
+    if (ss >= ks) { ss -= ks; ++jj; }
+  };
+  auto fetch = [&](float4 (&q)[4], int64_t jj, int ss) {
+    if (jj >= my_tiles) return;
+    if (jj == j) load(q, rp_cur, ss); else load(q, rp_nxt, ss);
+  };
+  auto step = [&](float4 (&q)[4]) {
+    uint2 hi[4], lo[4];
+#pragma unroll
+    for (int i = 0; i < 4; ++i) {
+      split_bf16x2(q[i].x, q[i].y, &hi[i].x, &lo[i].x);
+      split_bf16x2(q[i].z, q[i].w, &hi[i].y, &lo[i].y);
+    }
+    mbar_wait(&sm.bar_empty[stage], phase ^ 1u);
+    uint8_t* st = sm.a + stage * kStageBytes + a_off0;
+#pragma unroll
+    for (int i = 0; i < 4; ++i) {
+      *reinterpret_cast<uint2*>(st + i * 256) = hi[i];
+      *reinterpret_cast<uint2*>(st + i * 256 + kStageBytes / 2) = lo[i];
+    }
+    fence_proxy_async_smem();
+    __syncwarp();
+    if (lane == 0) mbar_arrive_cluster(&sm.bar_full[stage], 0);
+    stage += 2;
+    if (stage >= uint32_t(kStages)) { stage -= kStages; phase ^= 1u; }
+    int64_t j1 = j, j2;
+    int s1 = s, s2;
+    advance(j1, s1);
+    j2 = j1;
+    s2 = s1;
+    advance(j2, s2);
+    fetch(q, j2, s2);
+    asm volatile("" ::: "memory");
+    if (j1 != j) {
+#pragma unroll
+      for (int i = 0; i < 4; ++i) rp_cur[i] = rp_nxt[i];
+      row_ptrs(j1 + 1, rp_nxt);
+    }
+    j = j1;
+    s = s1;
+  };
+  float4 qa[4], qb[4];
+  load(qa, rp_cur, s);
+  {
+    int64_t j1 = 0;
+    int s1 = s;
+    advance(j1, s1);
+    fetch(qb, j1, s1);
+  }
+  asm volatile("" ::: "memory");
+  while (true) {
+    step(qa);
+    if (j >= my_tiles) break;
+    step(qb);
+    if (j >= my_tiles) break;
+  }
+}
+
 template <int kProd, int kEpi>
 __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kThreads, 1) row_gemm_tc_kernel(TcParams p) {
   // No-swizzle operands, bulk copies and mbarriers only need 16-byte alignment; the carve-up is
@@ -729,7 +823,8 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kThreads, 1) row_gem
     // =================================== producer warps =======================================
     cluster_sync();   // [sync A]
     const int pt = threadIdx.x - (kEpiWarps + 1) * 32;   // 0..255
-    gnn_rows_producer<kProd>(p, sm, pt, lane, rank, cluster_id, num_clusters);
+    if (kProd == PROD_ROWS) rows4_producer(p, sm, pt, lane, rank, cluster_id, num_clusters);
+    else gnn_rows_producer<kProd>(p, sm, pt, lane, rank, cluster_id, num_clusters);
   }
 
   // ---- teardown ------------------------------------------------------------------------------
