@@ -860,9 +860,10 @@ __device__ __forceinline__ void segmax_load_ids(const TcParams& p, int64_t tile_
 // kernel gives each lane quarter two warps with 4 blocks each so that more TMEM loads are in flight).
 template <int kBlocks>
 __device__ __forceinline__ void segmax_d1_transposed(const TcParams& p, uint32_t tmem, uint32_t d1_col, uint32_t rank,
-                                                     int quarter, int lane, int blk0, const int (&ids)[kBlocks]) {
+                                                     int quarter, int lane, int blk0, const int (&ids)[kBlocks],
+                                                     int f0 = 0) {
   const uint32_t lane_base = uint32_t(quarter * 32) << 16;
-  const int f = int(rank) * 128 + quarter * 32 + lane;
+  const int f = f0 + int(rank) * 128 + quarter * 32 + lane;   // f0: first output feature of this M = 256 block
   const bool f_ok = f < p.n;
   const float bias_f = f_ok ? __ldg(p.bias + f) : 0.0f;
   auto flush = [&](int cur, float m) {
@@ -1487,6 +1488,10 @@ struct ChainParams {
   uint32_t wimg_rank_bytes;
   int num_phases;
   uint32_t its_per_tile;
+  // store mode (himg != nullptr): there is no segment max; the LAST phase is drained like a mid stage (bias, relu,
+  // BF16 split) and written to global memory as the ready-made operand stages of pool_last_tc_kernel:
+  // block ((pair tile * 2 + rank) * chunks + chunk) of kStageBytes, same layout as a ring stage
+  uint8_t* himg;
   ChainPhase ph[kChainMaxPhases];
 };
 
@@ -1579,6 +1584,7 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kChainThreads, 1) ml
   const int64_t cluster_id = blockIdx.x >> 1;
   const int64_t num_clusters = gridDim.x >> 1;
   const int P = cp.num_phases;
+  const bool store = cp.himg != nullptr;
 
   // ---- prologue ------------------------------------------------------------------------------
   for (int i = threadIdx.x; i < 5 * cp.k0; i += kChainThreads) sm.first[i] = cp.first[i];
@@ -1591,7 +1597,7 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kChainThreads, 1) ml
     for (int i = 0; i < kChainMaxPhases; ++i) {
       mbar_init(&sm.bar_d_full[i], 1);
       // readers of D_i: the eight mid-stage warps, or (last phase) the four producer / final-stage warps
-      mbar_init(&sm.bar_d_empty[i], i == cp.num_phases - 1 ? 2 * kChainProdWarps : 2 * kEpiWarps);
+      mbar_init(&sm.bar_d_empty[i], (i == cp.num_phases - 1 && cp.himg == nullptr) ? 2 * kChainProdWarps : 2 * kEpiWarps);
     }
     mbar_init(sm.bar_a0_full, 2 * kChainProdWarps);
     mbar_init(sm.bar_a0_empty, 1);
@@ -1652,7 +1658,7 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kChainThreads, 1) ml
             const uint64_t da_lo = da_hi + uint64_t((kStageBytes / 2) >> 4);
             const uint64_t db_hi = b_hi0 + kb, db_lo = b_lo0 + kb;
             if (elect_one()) {
-              if (ph == P - 1) {
+              if (ph == P - 1 && !store) {
                 // last layer TRANSPOSED: D1t[feature, edge] = W^T (A, M = 256 features) x h^T (B, N = 256 edges);
                 // features 256.. stay row-major (M = 256 edges, N = n2)
                 mma_bf16<2>(d1, db_hi, da_hi, idesc_t, s > 0);
@@ -1691,9 +1697,11 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kChainThreads, 1) ml
     uint32_t tile_iter = 0;
     for (int64_t tile = cluster_id; tile < p.num_pair_tiles; tile += num_clusters, ++tile_iter) {
       // ---- mid stages: D_ph -> bias, relu -> A operand of phase ph + 1 ---------------------------
-      for (int ph = 0; ph + 1 < P; ++ph) {
+      const int mids = store ? P : P - 1;
+      for (int ph = 0; ph < mids; ++ph) {
         const ChainPhase& c = cp.ph[ph];
-        const uint32_t it0 = tile_iter * cp.its_per_tile + cp.ph[ph + 1].it_off;
+        const bool to_global = ph + 1 == P;    // store mode only
+        const uint32_t it0 = to_global ? 0u : tile_iter * cp.its_per_tile + cp.ph[ph + 1].it_off;
         const float* bias = sm.mid_bias + c.bias_off;
         const int chunks = (c.n1 + c.n2) >> 4;                // == k-steps of phase ph + 1
         mbar_wait(&sm.bar_d_full[ph], tile_iter & 1u);
@@ -1712,7 +1720,10 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kChainThreads, 1) ml
             h[4 * j4 + 3] = fmaxf(__uint_as_float(v[4 * j4 + 3]) + b.w, 0.0f);
           }
           if (ci + 2 < chunks) tmem_ld16(tmem + lane_base + c.d_col + uint32_t((ci + 2) * 16), v);
-          chain_publish(sm, it0 + uint32_t(ci), a_off, h, lane);
+          if (to_global)
+            chain_write(cp.himg + ((size_t(tile) * 2 + rank) * size_t(chunks) + size_t(ci)) * kStageBytes + a_off, h);
+          else
+            chain_publish(sm, it0 + uint32_t(ci), a_off, h, lane);
         }
         tmem_ld_wait();
         tc_fence_before();
@@ -1769,6 +1780,7 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kChainThreads, 1) ml
     uint32_t tile_iter = 0;
     for (int64_t tile = cluster_id; tile < p.num_pair_tiles; tile += num_clusters, ++tile_iter) {
       if (tile + num_clusters < p.num_pair_tiles) produce(tile + num_clusters, tile_iter + 1);
+      if (store) continue;
       int ids[8];
       segmax_load_ids<8>(p, tile * 256, lane, 0, ids);
       mbar_wait(&sm.bar_d_full[P - 1], tile_iter & 1u);
@@ -1787,6 +1799,206 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kChainThreads, 1) ml
   __syncthreads();
   cluster_sync();
   if (warp == kMmaWarp) tmem_dealloc<2>(tmem, 512);
+}
+
+// ================================================================================================
+// pool_last_tc_kernel - the LAST layer of a point-set pooling MLP that is too wide for the chain kernel
+// (ped_cyl: 256 -> 512, /root/reference/configs/ped_cyl_auto_T3_trainval_config:50-56) + the segment max.
+//
+// The chain kernel (store mode) has left h = relu(previous layer), already split into BF16 hi / lo and laid
+// out as UMMA operand stages, in global memory: one contiguous kStageBytes block per (pair tile, CTA rank,
+// k-step).  So this kernel has no producer arithmetic at all: one thread per CTA streams the blocks into a
+// stage ring with cp.async.bulk, the tensor core computes D[feature, edge] = W^T (A, M = 256 features over
+// the pair, resident in shared memory, hi + lo) x h^T (B, N = 256 edges), BF16x3, and four warps reduce the
+// accumulator per destination exactly as the GNN kernel does (segmax_d1_transposed).  D is double
+// buffered (2 x 256 TMEM columns): the drain of tile t overlaps the MMAs of tile t + 1.
+// Output features are processed in blocks of 256 ("halves"): cluster c owns half c % halves and the tiles
+// c / halves, + clusters / halves, ...; the clusters of one tile run side by side, so the second read of a
+// stage block hits L2.
+//
+// A bulk copy can only signal a barrier of the CTA it writes to, the MMA of the pair is issued by the
+// leader CTA and reads BOTH CTAs' stages: a relay thread per CTA waits for the local copy and arrives on
+// the leader's `full` barrier (count 2).
+constexpr int kLastEpiWarps = 4;                 // warps 0-3: TMEM lane quarter = warp id
+constexpr int kLastMmaWarp = 4;
+constexpr int kLastTmaWarp = 5;
+constexpr int kLastRelayWarp = 6;
+constexpr int kLastThreads = 7 * 32;
+constexpr int kLastMaxStages = 12;
+
+struct LastParams {
+  TcParams seg;            // out, n (row stride and feature bound), bias [halves * 256], dst, num_rows, num_dst, err, num_pair_tiles
+  const uint8_t* himg;     // operand stages written by mlp_chain_tc_kernel (store mode)
+  const uint8_t* wimg;     // per (half, rank): [hi part | lo part] of 128 feature rows, K-major core matrices
+  uint32_t part_bytes;
+  int ks;                  // k-steps (K / 16)
+  int halves;              // blocks of 256 output features
+  int nstages;
+};
+
+struct LastSmem {
+  uint8_t* w;
+  uint8_t* a;
+  uint64_t* bar_tx;        // [nstages] local: the bulk copy of the stage has landed
+  uint64_t* bar_full;      // [nstages] (leader) both CTAs' copies have landed
+  uint64_t* bar_empty;     // [nstages] the MMAs reading the stage are complete
+  uint64_t* bar_d_full;    // [2]
+  uint64_t* bar_d_empty;   // [2] (leader)
+  uint64_t* bar_wres;
+  uint32_t* tmem;
+};
+
+__host__ __device__ inline size_t last_smem_layout(uint8_t* base, uint32_t part_bytes, int nstages, LastSmem* m) {
+  size_t off = 0;
+  auto take = [&](size_t bytes) { size_t o = off; off += (bytes + 127) & ~size_t(127); return o; };
+  const size_t o_w = take(2 * size_t(part_bytes));
+  const size_t o_a = take(size_t(nstages) * kStageBytes);
+  const size_t o_bar = take((3 * size_t(nstages) + 5) * sizeof(uint64_t));
+  const size_t o_tmem = take(16);
+  if (m != nullptr) {
+    m->w = base + o_w;
+    m->a = base + o_a;
+    uint64_t* bars = reinterpret_cast<uint64_t*>(base + o_bar);
+    m->bar_tx = bars;
+    m->bar_full = bars + nstages;
+    m->bar_empty = bars + 2 * nstages;
+    m->bar_d_full = bars + 3 * nstages;
+    m->bar_d_empty = bars + 3 * nstages + 2;
+    m->bar_wres = bars + 3 * nstages + 4;
+    m->tmem = reinterpret_cast<uint32_t*>(base + o_tmem);
+  }
+  return off;
+}
+
+__global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kLastThreads, 1) pool_last_tc_kernel(LastParams lp) {
+  extern __shared__ __align__(128) uint8_t smem_raw[];
+  LastSmem sm;
+  last_smem_layout(smem_raw, lp.part_bytes, lp.nstages, &sm);
+  const TcParams& p = lp.seg;
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const uint32_t rank = cluster_ctarank();
+  const int64_t cluster_id = blockIdx.x >> 1;
+  const int64_t num_clusters = gridDim.x >> 1;
+  const int half = int(cluster_id % lp.halves);
+  const int64_t tile0 = cluster_id / lp.halves;
+  const int64_t tstride = num_clusters / lp.halves;      // the host launches a multiple of `halves` clusters
+  const int nst = lp.nstages, ks = lp.ks;
+
+  if (threadIdx.x == 0) {
+    for (int i = 0; i < nst; ++i) {
+      mbar_init(&sm.bar_tx[i], 1);
+      mbar_init(&sm.bar_full[i], 2);
+      mbar_init(&sm.bar_empty[i], 1);
+    }
+    for (int b = 0; b < 2; ++b) {
+      mbar_init(&sm.bar_d_full[b], 1);
+      mbar_init(&sm.bar_d_empty[b], 2 * kLastEpiWarps);
+    }
+    mbar_init(sm.bar_wres, 1);
+    fence_barrier_init();
+  }
+  if (warp == kLastMmaWarp) {
+    tmem_alloc<2>(sm.tmem, 512);
+    tmem_relinquish<2>();
+  }
+  tc_fence_before();
+  __syncthreads();
+  cluster_sync();
+  tc_fence_after();
+  const uint32_t tmem = *sm.tmem;
+
+  if (warp == kLastMmaWarp) {
+    if (lane == 0) {
+      const uint32_t bytes = 2 * lp.part_bytes;
+      mbar_arrive_expect_tx(sm.bar_wres, bytes);
+      bulk_g2s(sm.w, lp.wimg + (size_t(half) * 2 + rank) * bytes, bytes, sm.bar_wres);
+      mbar_wait(sm.bar_wres, 0);
+    }
+    __syncwarp();
+    cluster_sync();   // [sync A] both CTAs' weights are resident
+    if (rank == 0) {
+      const uint32_t tmem_u = __shfl_sync(0xffffffffu, tmem, 0);
+      const uint32_t idesc = make_idesc_bf16(256, 256);
+      const uint32_t sbo_w = uint32_t(ks * 2) * 128u;
+      const uint64_t w_hi0 = make_smem_desc(smem_u32(sm.w), 128, sbo_w);
+      const uint64_t w_lo0 = make_smem_desc(smem_u32(sm.w) + lp.part_bytes, 128, sbo_w);
+      const uint64_t h_hi0 = make_smem_desc(smem_u32(sm.a), 128, 256);
+      uint32_t stage = 0, phase = 0, tile_iter = 0;
+      for (int64_t tile = tile0; tile < p.num_pair_tiles; tile += tstride, ++tile_iter) {
+        const uint32_t buf = tile_iter & 1u, use = tile_iter >> 1;
+        const uint32_t d = tmem_u + buf * 256u;
+        mbar_wait(&sm.bar_d_empty[buf], (use & 1u) ^ 1u);
+        tc_fence_after();
+        uint64_t kb = 0;
+        for (int s = 0; s < ks; ++s, kb += 16) {
+          mbar_wait(&sm.bar_full[stage], phase);
+          tc_fence_after();
+          const uint64_t h_hi = h_hi0 + uint64_t(stage * (kStageBytes >> 4));
+          const uint64_t h_lo = h_hi + uint64_t((kStageBytes / 2) >> 4);
+          if (elect_one()) {
+            mma_bf16<2>(d, w_hi0 + kb, h_hi, idesc, s > 0);
+            mma_bf16<2>(d, w_hi0 + kb, h_lo, idesc, true);
+            mma_bf16<2>(d, w_lo0 + kb, h_hi, idesc, true);
+            mma_commit_2cta(&sm.bar_empty[stage], 0x3);
+          }
+          __syncwarp();
+          if (++stage == uint32_t(nst)) { stage = 0; phase ^= 1u; }
+        }
+        if (elect_one()) mma_commit_2cta(&sm.bar_d_full[buf], 0x3);
+        __syncwarp();
+      }
+    }
+    __syncwarp();
+  } else if (warp == kLastTmaWarp) {
+    cluster_sync();   // [sync A]
+    if (lane == 0) {
+      uint32_t stage = 0, phase = 0;
+      for (int64_t tile = tile0; tile < p.num_pair_tiles; tile += tstride) {
+        const uint8_t* src = lp.himg + (size_t(tile) * 2 + rank) * size_t(ks) * kStageBytes;
+        for (int s = 0; s < ks; ++s, src += kStageBytes) {
+          mbar_wait(&sm.bar_empty[stage], phase ^ 1u);
+          mbar_arrive_expect_tx(&sm.bar_tx[stage], kStageBytes);
+          bulk_g2s(sm.a + stage * kStageBytes, src, kStageBytes, &sm.bar_tx[stage]);
+          if (++stage == uint32_t(nst)) { stage = 0; phase ^= 1u; }
+        }
+      }
+    }
+    __syncwarp();
+  } else if (warp == kLastRelayWarp) {
+    cluster_sync();   // [sync A]
+    if (lane == 0) {
+      uint32_t stage = 0, phase = 0;
+      for (int64_t tile = tile0; tile < p.num_pair_tiles; tile += tstride) {
+        for (int s = 0; s < ks; ++s) {
+          mbar_wait(&sm.bar_tx[stage], phase);
+          mbar_arrive_cluster(&sm.bar_full[stage], 0);
+          if (++stage == uint32_t(nst)) { stage = 0; phase ^= 1u; }
+        }
+      }
+    }
+    __syncwarp();
+  } else {
+    // =================================== epilogue warps =======================================
+    cluster_sync();   // [sync A]
+    const int quarter = warp;
+    uint32_t tile_iter = 0;
+    for (int64_t tile = tile0; tile < p.num_pair_tiles; tile += tstride, ++tile_iter) {
+      const uint32_t buf = tile_iter & 1u, use = tile_iter >> 1;
+      int ids[8];
+      segmax_load_ids<8>(p, tile * 256, lane, 0, ids);
+      mbar_wait(&sm.bar_d_full[buf], use & 1u);
+      tc_fence_after();
+      segmax_d1_transposed<8>(p, tmem, buf * 256u, rank, quarter, lane, 0, ids, half * 256);
+      tc_fence_before();
+      __syncwarp();
+      if (lane == 0) mbar_arrive_cluster_relaxed(&sm.bar_d_empty[buf], 0);
+    }
+  }
+
+  tc_fence_before();
+  __syncthreads();
+  cluster_sync();
+  if (warp == kLastMmaWarp) tmem_dealloc<2>(tmem, 512);
 }
 
 size_t tc_smem_bytes(int kp, int np, int prod = PROD_GNN) {
@@ -1953,9 +2165,14 @@ struct PreparedEdge {
   ChainParams cp{};
   size_t chain_smem = 0;
   Temp c_first, c_img, c_mid, c_bias;
+  // POOL, last layer too wide for the chain: chain in store mode + pool_last_tc_kernel
+  bool split_last = false;
+  LastParams lp{};
+  size_t last_smem = 0;
+  Temp l_img;
 };
 
-int prepare_chain(PreparedEdge& e, cudaStream_t s, bool* ok);
+int prepare_chain(PreparedEdge& e, cudaStream_t s, bool split_last, bool* ok);
 
 int prepare_edge(PreparedEdge& e, int mode, int c_in, const float* const* weights, const float* const* biases,
                  const int32_t* dims, int num_layers, bool want_tc, cudaStream_t s) {
@@ -1972,8 +2189,12 @@ int prepare_edge(PreparedEdge& e, int mode, int c_in, const float* const* weight
   if (!want_tc || !pg_tc_available()) return PG_OK;
   if (mode == PG_EDGE_POOL) {
     bool ok = false;
-    if (c_in == 1)
-      if (int rc = prepare_chain(e, s, &ok)) return rc;
+    if (c_in == 1) {
+      if (int rc = prepare_chain(e, s, false, &ok)) return rc;
+      // e.g. ped_cyl 4 -> 32 -> 64 -> 128 -> 256 -> 512: every layer but the last on the chain kernel
+      if (!ok)
+        if (int rc = prepare_chain(e, s, true, &ok)) return rc;
+    }
     if (ok) e.path = EDGE_CHAIN;
     return PG_OK;
   }
@@ -2017,11 +2238,12 @@ int prepare_edge(PreparedEdge& e, int mode, int c_in, const float* const* weight
 }
 
 // PointSetPooling's per-edge MLP + segment max on the chain kernel: shapes, images, parameter block.
-int prepare_chain(PreparedEdge& e, cudaStream_t s, bool* ok) {
+// split_last: the chain covers layers 2 .. L-1 in store mode and pool_last_tc_kernel does layer L + the max.
+int prepare_chain(PreparedEdge& e, cudaStream_t s, bool split_last, bool* ok) {
   *ok = false;
   const int num_layers = e.num_layers;
   const int32_t* dims = e.dims.data();
-  const int P = num_layers - 1;
+  const int P = num_layers - 1 - (split_last ? 1 : 0);
   if (P < 1 || P > kChainMaxPhases || dims[0] != 4) return PG_OK;
   const int k0 = dims[1];
   if (k0 % 16 != 0 || k0 > kChainMaxK0) return PG_OK;
@@ -2031,12 +2253,13 @@ int prepare_chain(PreparedEdge& e, cudaStream_t s, bool* ok) {
   for (int ph = 0; ph < P; ++ph) {
     const int k = dims[ph + 1], n = dims[ph + 2];
     const int np = (n + 15) / 16 * 16;
-    if (k % 16 != 0 || np > 512 || (ph + 1 < P && n % 16 != 0)) return PG_OK;
+    const bool last = ph + 1 == P;
+    const bool mid = !last || split_last;           // drained as the A operand of a following layer
+    if (k % 16 != 0 || np > 512 || (mid && n % 16 != 0)) return PG_OK;
     ChainPhase& c = cp.ph[ph];
     c.ks = k / 16;
-    const bool last = ph + 1 == P;
-    // the last phase is computed transposed for its first 256 features: always a full M = 256 tile
-    c.n1 = last ? 256 : std::min(np, 256);
+    // the last phase of a full chain is computed transposed for its first 256 features: always a full M = 256 tile
+    c.n1 = mid ? std::min(np, 256) : 256;
     c.n2 = std::max(0, np - 256);
     const int np_eff = c.n1 + c.n2;
     c.d_col = d_col;
@@ -2048,7 +2271,7 @@ int prepare_chain(PreparedEdge& e, cudaStream_t s, bool* ok) {
     d_col += uint32_t(np_eff);
     b_off += 2 * c.part_bytes;
     if (ph > 0) it_off += uint32_t(c.ks);      // the ring carries the k-steps of phases >= 1 only
-    if (ph + 1 < P) bias_off += uint32_t(np);
+    if (mid) bias_off += uint32_t(np);
   }
   if (d_col > 512) return PG_OK;
   cp.num_phases = P;
@@ -2058,9 +2281,25 @@ int prepare_chain(PreparedEdge& e, cudaStream_t s, bool* ok) {
   cp.k0 = k0;
   e.chain_smem = chain_smem_layout(nullptr, cp.wimg_rank_bytes, k0, cp.mid_bias_floats, nullptr);
   if (e.chain_smem > 227 * 1024) return PG_OK;
+
+  const int n = dims[num_layers];
+  LastParams& lp = e.lp;
+  lp = LastParams{};
+  if (split_last) {
+    const int k = dims[num_layers - 1];            // == N of the chain's last phase (a multiple of 16, checked above)
+    if (k > 256 || n < 8) return PG_OK;
+    lp.ks = k / 16;
+    lp.halves = (n + 255) / 256;
+    lp.part_bytes = uint32_t(16) * uint32_t(k / 8) * 128u;   // 128 feature rows of one rank, hi or lo
+    lp.nstages = 0;
+    for (int st = kLastMaxStages; st >= 3; --st)
+      if (last_smem_layout(nullptr, lp.part_bytes, st, nullptr) <= 227 * 1024) { lp.nstages = st; break; }
+    if (lp.nstages == 0 || num_sms() / 2 < lp.halves) return PG_OK;
+    e.last_smem = last_smem_layout(nullptr, lp.part_bytes, lp.nstages, nullptr);
+  }
+  e.split_last = split_last;
   *ok = true;
 
-  const int n = dims[num_layers], np_last = cp.ph[P - 1].n1 + cp.ph[P - 1].n2;
   PG_CUDA_OK(e.c_first.alloc(sizeof(float) * 5 * k0, s));
   PG_CUDA_OK(cudaMemcpyAsync(e.c_first.ptr, e.w[0], sizeof(float) * 4 * k0, cudaMemcpyDeviceToDevice, s));
   PG_CUDA_OK(cudaMemcpyAsync(e.c_first.as<float>() + 4 * k0, e.b[0], sizeof(float) * k0, cudaMemcpyDeviceToDevice, s));
@@ -2072,19 +2311,37 @@ int prepare_chain(PreparedEdge& e, cudaStream_t s, bool* ok) {
                                                            c.n1, c.n2, e.c_img.as<uint8_t>() + c.b_off, c.part_bytes,
                                                            cp.wimg_rank_bytes);
     PG_LAUNCH_CHECK();
-    if (ph + 1 < P) {
+    if (ph + 1 < P || split_last) {
       pad_rows_kernel<<<2, 256, 0, s>>>(e.b[ph + 1], 1, dims[ph + 2], c.n1 + c.n2, e.c_mid.as<float>() + c.bias_off);
       PG_LAUNCH_CHECK();
     }
   }
-  PG_CUDA_OK(e.c_bias.alloc(sizeof(float) * np_last, s));
-  pad_rows_kernel<<<2, 256, 0, s>>>(e.b[num_layers - 1], 1, n, np_last, e.c_bias.as<float>());
-  PG_LAUNCH_CHECK();
   cp.first = e.c_first.as<float>();
   cp.mid_bias = e.c_mid.as<float>();
   cp.wimg = e.c_img.as<uint8_t>();
-  cp.seg.bias = e.c_bias.as<float>();
   cp.seg.n = n;
+  if (split_last) {
+    const int k = dims[num_layers - 1];
+    PG_CUDA_OK(e.c_bias.alloc(sizeof(float) * lp.halves * 256, s));
+    pad_rows_kernel<<<2, 256, 0, s>>>(e.b[num_layers - 1], 1, n, lp.halves * 256, e.c_bias.as<float>());
+    PG_LAUNCH_CHECK();
+    PG_CUDA_OK(e.l_img.alloc(size_t(lp.halves) * 4 * lp.part_bytes, s));
+    for (int h = 0; h < lp.halves; ++h) {
+      pack_w2_kernel<<<std::min(num_sms(), 64), 256, 0, s>>>(e.w[num_layers - 1] + 256 * h, k, std::min(256, n - 256 * h), n, k,
+                                                             256, 0, e.l_img.as<uint8_t>() + size_t(h) * 4 * lp.part_bytes,
+                                                             lp.part_bytes, 2 * lp.part_bytes);
+      PG_LAUNCH_CHECK();
+    }
+    lp.wimg = e.l_img.as<uint8_t>();
+    lp.seg.bias = e.c_bias.as<float>();
+    lp.seg.n = n;
+    return PG_OK;
+  }
+  const int np_last = cp.ph[P - 1].n1 + cp.ph[P - 1].n2;
+  PG_CUDA_OK(e.c_bias.alloc(sizeof(float) * np_last, s));
+  pad_rows_kernel<<<2, 256, 0, s>>>(e.b[num_layers - 1], 1, n, np_last, e.c_bias.as<float>());
+  PG_LAUNCH_CHECK();
+  cp.seg.bias = e.c_bias.as<float>();
   cp.seg.np = np_last;
   cp.seg.n1 = cp.ph[P - 1].n1;
   cp.seg.n2 = cp.ph[P - 1].n2;
@@ -2115,29 +2372,56 @@ int apply_edge(const PreparedEdge& e, const float* features, const float* xyz_sr
   PG_CUDA_OK(cudaMemsetAsync(t_err.ptr, 0, sizeof(int), s));
   if (int rc = fill_async(out, num_dst * n, -FLT_MAX, s)) return rc;
   if (e.path == EDGE_CHAIN) {
-    ChainParams cp = e.cp;
-    cp.feat = features;
-    TcParams& p = cp.seg;
-    p.xyz_src = xyz_src;
-    p.xyz_dst = xyz_dst;
-    p.dst_index = dst_index;
-    p.src = src;
-    p.dst = dst;
-    p.num_rows = num_edges;
-    p.num_src = num_src;
-    p.num_dst = num_dst;
-    p.out = out;
-    p.err = t_err.as<int>();
-    p.num_pair_tiles = ceil_div(num_edges, 2 * kTileRows);
     static bool attr_done = false;
     if (!attr_done) {
       PG_CUDA_OK(cudaFuncSetAttribute(mlp_chain_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
+      PG_CUDA_OK(cudaFuncSetAttribute(pool_last_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
       attr_done = true;
     }
-    const int clusters = int(std::min<int64_t>(p.num_pair_tiles, num_sms() / 2));
-    mlp_chain_tc_kernel<<<2 * clusters, kChainThreads, e.chain_smem, s>>>(cp);
-    PG_LAUNCH_CHECK();
-    g_tc_launches[0].fetch_add(1, std::memory_order_relaxed);
+    // split mode: the intermediate operand image takes 4 * K bytes per edge -> bounded slices of the edge list
+    // (a destination whose edges straddle two slices is merged by the atomic max like any tile boundary)
+    const int64_t slice_edges = e.split_last ? (int64_t(8) << 20) : num_edges;
+    Temp t_himg;
+    if (e.split_last)
+      PG_CUDA_OK(t_himg.alloc(size_t(ceil_div(std::min(slice_edges, num_edges), 2 * kTileRows)) * 2 * e.lp.ks * kStageBytes, s));
+    for (int64_t e0 = 0; e0 < num_edges; e0 += slice_edges) {
+      const int64_t ne = std::min(slice_edges, num_edges - e0);
+      ChainParams cp = e.cp;
+      cp.feat = features;
+      TcParams& p = cp.seg;
+      p.xyz_src = xyz_src;
+      p.xyz_dst = xyz_dst;
+      p.dst_index = dst_index;
+      p.src = src + e0;
+      p.dst = dst + e0;
+      p.num_rows = ne;
+      p.num_src = num_src;
+      p.num_dst = num_dst;
+      p.out = out;
+      p.err = t_err.as<int>();
+      p.num_pair_tiles = ceil_div(ne, 2 * kTileRows);
+      cp.himg = e.split_last ? t_himg.as<uint8_t>() : nullptr;
+      const int clusters = int(std::min<int64_t>(p.num_pair_tiles, num_sms() / 2));
+      mlp_chain_tc_kernel<<<2 * clusters, kChainThreads, e.chain_smem, s>>>(cp);
+      PG_LAUNCH_CHECK();
+      g_tc_launches[0].fetch_add(1, std::memory_order_relaxed);
+      if (e.split_last) {
+        LastParams lp = e.lp;
+        lp.himg = t_himg.as<uint8_t>();
+        TcParams& q = lp.seg;
+        q.dst = dst + e0;
+        q.num_rows = ne;
+        q.num_dst = num_dst;
+        q.out = out;
+        q.err = t_err.as<int>();
+        q.num_pair_tiles = p.num_pair_tiles;
+        int lc = int(std::min<int64_t>(q.num_pair_tiles * lp.halves, num_sms() / 2));
+        lc = std::max(lp.halves, lc / lp.halves * lp.halves);
+        pool_last_tc_kernel<<<2 * lc, kLastThreads, e.last_smem, s>>>(lp);
+        PG_LAUNCH_CHECK();
+        g_tc_launches[0].fetch_add(1, std::memory_order_relaxed);
+      }
+    }
     return finish_index_check(t_err, num_src, num_dst, s);
   }
   // GNN edge layer: hoisted per-vertex GEMM, then the fused gather / second layer / segment max kernel

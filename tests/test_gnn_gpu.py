@@ -193,9 +193,9 @@ def test_predict_matches_golden(name, precision, request):
     if precision == 'bf16x3':
         # the tensor-core kernels must really have run: 3 GNN iterations (+ the car pooling layer) are
         # fused tcgen05 edge launches, and the wide per-vertex layers go through the dense tcgen05
-        # kernel (no silent FFMA fallback).  The ped pooling MLP (256 -> 512 last layer) exceeds the
-        # resident-weight budget and stays on the fp32 fused kernel.
-        assert _lib.tc_launch_count(0) - tc0[0] == (4 if name == 'car' else 3)
+        # kernel (no silent FFMA fallback).  The ped pooling MLP (4 -> 32 -> 64 -> 128 -> 256 -> 512) is two
+        # launches: the chain kernel up to 256 (store mode) + pool_last_tc_kernel (256 -> 512 + segment max).
+        assert _lib.tc_launch_count(0) - tc0[0] == (4 if name == 'car' else 5)
         assert _lib.tc_launch_count(1) - tc0[1] >= 10
     assert isinstance(logits, np.ndarray) and logits.shape == g.gnn['logits'].shape
     assert boxes.shape == g.gnn['boxes'].shape
@@ -448,3 +448,46 @@ def test_tc_edge_kernel_shapes_and_tails(d, c_in):
             assert np.array_equal(got == np.finfo(np.float32).min, empty), (case, prec)
             err = np.abs(got - want)[~empty].max() if (~empty).any() else 0.0
             assert err < (2e-4 if prec == 0 else 1e-3), (d, case, prec, err)
+
+
+@pytest.mark.parametrize('dims', [(4, 32, 64, 128, 300), (4, 32, 64, 128, 256, 512), (4, 32, 64, 128, 256, 300),
+                                  (4, 16, 64, 200), (4, 32, 128, 64)])
+def test_tc_pool_chain_shapes_and_tails(dims):
+    """The point-set pooling MLP on tensor cores: the full chain kernel (car shape), the chain in store mode +
+    pool_last_tc_kernel (ped shape 256 -> 512, and a last layer that only half fills its second 256-feature
+    block), tails, one-edge / tile-spanning / empty segments, keypoint indirection."""
+    _need('bf16x3')
+    from pointgnn_b200 import _lib
+    rng = np.random.default_rng(sum(dims))
+    nv, nk = 900, 400
+    launches = 2 if (len(dims) == 6) else 1
+    ws = [(rng.standard_normal((dims[i], dims[i + 1])) / np.sqrt(dims[i])).astype(np.float32) for i in range(len(dims) - 1)]
+    bs = [(rng.standard_normal(dims[i + 1]) * 0.1).astype(np.float32) for i in range(len(dims) - 1)]
+    for case, (e, pattern) in enumerate(((1, 'one'), (255, 'long'), (256, 'long'), (257, 'short'), (5000, 'mixed'),
+                                         (70000, 'mixed'))):
+        if pattern == 'one':
+            dst = np.array([3])
+        elif pattern == 'long':
+            dst = np.sort(rng.integers(0, 3, e))
+        elif pattern == 'short':
+            dst = np.sort(rng.integers(0, nk, e))
+        else:
+            dst = np.sort(np.concatenate([rng.integers(0, nk, e // 2), rng.integers(10, 14, e - e // 2)]))
+        src = rng.integers(0, nv, e)
+        f = rng.random((nv, 1)).astype(np.float32)
+        x = (rng.standard_normal((nv, 3)) * 20).astype(np.float32)
+        kp = rng.integers(0, nv, nk)
+        h = np.concatenate([f[src], x[src] - x[kp[dst]]], axis=1)
+        for w, b in zip(ws, bs):
+            h = np.maximum(h @ w + b, 0)
+        want = ognn.graph_scatter_max_fn(h, dst, nk)
+        before = _lib.tc_launch_count(0)
+        got = _lib.edge_mlp_max(0, _cuda(f), _cuda(x), _cuda(x), _cuda(kp.astype(np.int32)), _cuda(src.astype(np.int32)),
+                                _cuda(dst.astype(np.int32)), nk, [_cuda(w) for w in ws], [_cuda(b) for b in bs],
+                                precision=1).cpu().numpy()
+        assert _lib.tc_launch_count(0) - before == launches, (dims, case)
+        empty = want == np.finfo(np.float32).min
+        assert np.array_equal(got == np.finfo(np.float32).min, empty), (dims, case)
+        scale = max(1.0, float(np.abs(want[~empty]).max())) if (~empty).any() else 1.0
+        err = np.abs(got - want)[~empty].max() if (~empty).any() else 0.0
+        assert err < 1e-3 * scale, (dims, case, err, scale)
