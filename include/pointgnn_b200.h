@@ -104,6 +104,31 @@ PG_API int pg_voxel_keypoints(const float* xyz, const int32_t* frame_ptr, int32_
                        void* stream);
 
 /*
+ * multi_layer_downsampling for ONE scale (graph_gen.py:11-47, Open3D branch :41-45): the fp64 centroid of
+ * every occupied voxel of the cloud, per frame in ascending linear-voxel-key order (the oracle's canonical
+ * order; Open3D's own order is unspecified).
+ *   out_centroids [capacity,3] fp64 (device), out_frame_ptr [num_frames+1], out_num_host (host) = K.
+ * Synchronises the stream; PG_ERR_CAPACITY as pg_voxel_keypoints.
+ */
+PG_API int pg_voxel_centroids(const float* xyz, const int32_t* frame_ptr, int32_t num_frames,
+                       int64_t num_points, const double* voxel_size_host, double* out_centroids,
+                       int64_t capacity, int32_t* out_frame_ptr, int64_t* out_num_host, void* stream);
+
+/*
+ * multi_layer_downsampling_select for a level whose scale differs from the previous level's
+ * (graph_gen.py:82-88) in the general case of several distinct scales (graph_gen.py:17-23,76-88): the
+ * voxel centroids of the ORIGINAL cloud `xyz` (:41-45), each snapped to the nearest vertex of the
+ * PREVIOUS level `base_xyz` [num_base,3] / `base_frame_ptr` (kd_tree 1-NN, :84-87; fp64 distance, ties ->
+ * lowest index, same frame only).  out_keypoint_idx [K] are GLOBAL rows of base_xyz.  With base == xyz
+ * this equals pg_voxel_keypoints.  Other arguments and errors as pg_voxel_keypoints.
+ */
+PG_API int pg_voxel_keypoints_select(const float* xyz, const int32_t* frame_ptr, int32_t num_frames,
+                              int64_t num_points, const double* voxel_size_host, const float* base_xyz,
+                              const int32_t* base_frame_ptr, int64_t num_base, int32_t* out_keypoint_idx,
+                              int64_t capacity, int32_t* out_kp_frame_ptr,
+                              int64_t* out_num_keypoints_host, void* stream);
+
+/*
  * Radius-neighbour graph = gen_disjointed_rnn_local_graph_v3
  * (graph_gen.py:197-220; ball_tree radius_neighbors, fp64 predicate
  * ((dx*dx+dy*dy)+dz*dz) <= r*r on float32-valued coordinates, inclusive), with

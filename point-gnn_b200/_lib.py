@@ -30,6 +30,11 @@ SIGNATURES = {
     'pg_tc_launch_count': (c_i64, [c_i32]),
     'pg_voxel_keypoints': (ctypes.c_int, [c_f32p, c_i32p, c_i32, c_i64, ctypes.POINTER(ctypes.c_double),
                                           c_i32p, c_i64, c_i32p, ctypes.POINTER(c_i64), ctypes.c_void_p]),
+    'pg_voxel_centroids': (ctypes.c_int, [c_f32p, c_i32p, c_i32, c_i64, ctypes.POINTER(ctypes.c_double),
+                                          ctypes.c_void_p, c_i64, c_i32p, ctypes.POINTER(c_i64), ctypes.c_void_p]),
+    'pg_voxel_keypoints_select': (ctypes.c_int, [c_f32p, c_i32p, c_i32, c_i64, ctypes.POINTER(ctypes.c_double),
+                                                 c_f32p, c_i32p, c_i64, c_i32p, c_i64, c_i32p,
+                                                 ctypes.POINTER(c_i64), ctypes.c_void_p]),
     'pg_radius_graph_count': (ctypes.c_int, [c_f32p, c_i32p, c_f32p, c_i32p, c_i32, c_i64, c_i64,
                                              ctypes.c_double, c_i32p, ctypes.POINTER(c_i64), ctypes.c_void_p]),
     'pg_radius_graph_fill': (ctypes.c_int, [c_f32p, c_i32p, c_f32p, c_i32p, c_i32, c_i64, c_i64,
@@ -164,6 +169,38 @@ def voxel_keypoints(xyz, frame_ptr, voxel_size):
     _check(lib.pg_voxel_keypoints(_ptr(xyz, torch.float32, 'xyz'), _ptr(frame_ptr, torch.int32, 'frame_ptr'),
                                   num_frames, n, vs, _ptr(out_idx, torch.int32, 'out'), n,
                                   _ptr(out_fp, torch.int32, 'out_fp'), ctypes.byref(k), _stream()))
+    return out_idx[:k.value], out_fp
+
+
+def voxel_centroids(xyz, frame_ptr, voxel_size):
+    """pg_voxel_centroids -> (centroids [K,3] float64, frame_ptr [F+1] int32)."""
+    lib = load()
+    n = xyz.shape[0]
+    num_frames = frame_ptr.numel() - 1
+    out = torch.empty((n, 3), dtype=torch.float64, device=xyz.device)
+    out_fp = torch.empty(num_frames + 1, dtype=torch.int32, device=xyz.device)
+    vs = (ctypes.c_double * 3)(*[float(v) for v in voxel_size])
+    k = c_i64(0)
+    _check(lib.pg_voxel_centroids(_ptr(xyz, torch.float32, 'xyz'), _ptr(frame_ptr, torch.int32, 'frame_ptr'),
+                                  num_frames, n, vs, _ptr(out, torch.float64, 'out'), n,
+                                  _ptr(out_fp, torch.int32, 'out_fp'), ctypes.byref(k), _stream()))
+    return out[:k.value], out_fp
+
+
+def voxel_keypoints_select(xyz, frame_ptr, voxel_size, base_xyz, base_frame_ptr):
+    """pg_voxel_keypoints_select -> (keypoint_idx [K] int32 rows of base_xyz, kp_frame_ptr [F+1] int32)."""
+    lib = load()
+    n = xyz.shape[0]
+    num_frames = frame_ptr.numel() - 1
+    out_idx = torch.empty(n, dtype=torch.int32, device=xyz.device)
+    out_fp = torch.empty(num_frames + 1, dtype=torch.int32, device=xyz.device)
+    vs = (ctypes.c_double * 3)(*[float(v) for v in voxel_size])
+    k = c_i64(0)
+    _check(lib.pg_voxel_keypoints_select(_ptr(xyz, torch.float32, 'xyz'), _ptr(frame_ptr, torch.int32, 'frame_ptr'),
+                                         num_frames, n, vs, _ptr(base_xyz, torch.float32, 'base_xyz'),
+                                         _ptr(base_frame_ptr, torch.int32, 'base_frame_ptr'), base_xyz.shape[0],
+                                         _ptr(out_idx, torch.int32, 'out'), n, _ptr(out_fp, torch.int32, 'out_fp'),
+                                         ctypes.byref(k), _stream()))
     return out_idx[:k.value], out_fp
 
 

@@ -238,6 +238,87 @@ __global__ void voxel_keypoint_kernel(SortedGrid g, GridSpec spec, const uint32_
   if (v < capacity) out_idx[v] = best_idx;
 }
 
+// ---- general multi-scale keypoints (graph_gen.py:11-47 + :49-90 with more than one distinct scale) -------------
+// multi_layer_downsampling voxelises the ORIGINAL cloud at every scale; multi_layer_downsampling_select then snaps
+// each centroid to the nearest vertex of the PREVIOUS level (kd_tree 1-NN on base_points).  Two kernels: the fp64
+// centroid of every occupied voxel, and an exact nearest-point query against a second grid built over the base
+// points.
+__global__ void voxel_centroid_kernel(SortedGrid g, double* __restrict__ out_centroid, int32_t* __restrict__ out_frame,
+                                      int64_t capacity) {
+  const int v = blockIdx.x * blockDim.x + threadIdx.x;
+  if (v >= __ldg(g.num_cells) || v >= capacity) return;
+  const int s = g.cell_start[v], e = g.cell_start[v + 1];
+  double sx = 0.0, sy = 0.0, sz = 0.0;
+  for (int i = s; i < e; ++i) {  // ascending point order (stable sort)
+    const float4 p = g.pts[i];
+    sx = __dadd_rn(sx, double(p.x));
+    sy = __dadd_rn(sy, double(p.y));
+    sz = __dadd_rn(sz, double(p.z));
+  }
+  const double cnt = double(e - s);
+  out_centroid[3 * int64_t(v) + 0] = __ddiv_rn(sx, cnt);
+  out_centroid[3 * int64_t(v) + 1] = __ddiv_rn(sy, cnt);
+  out_centroid[3 * int64_t(v) + 2] = __ddiv_rn(sz, cnt);
+  if (out_frame) out_frame[v] = int32_t(g.cell_key[v] >> 48);
+}
+
+// nearest base point (fp64 squared distance, ties -> lowest index) of query q inside its own frame.
+// Growing boxes of cells until one holds a point, then ONE exact pass over every cell the ball of that radius touches.
+__global__ void nearest_point_kernel(SortedGrid g, GridSpec spec, const uint32_t* __restrict__ bounds,
+                                     const int32_t* __restrict__ base_frame_ptr, const double* __restrict__ q_xyz,
+                                     const int32_t* __restrict__ q_frame, const int32_t* __restrict__ num_q,
+                                     int64_t capacity, int32_t* __restrict__ out_idx, int* __restrict__ err) {
+  const int64_t q = int64_t(blockIdx.x) * blockDim.x + threadIdx.x;
+  if (q >= int64_t(__ldg(num_q)) || q >= capacity) return;
+  const uint32_t f = uint32_t(q_frame[q]);
+  if (base_frame_ptr[f + 1] == base_frame_ptr[f]) {   // a frame with voxels but no base vertex
+    atomicOr(err, kErrCenterPtr);
+    out_idx[q] = 0;
+    return;
+  }
+  const double cx = q_xyz[3 * q], cy = q_xyz[3 * q + 1], cz = q_xyz[3 * q + 2];
+  const double ox = double(ordered_to_float(bounds[3 * f + 0])) - spec.cell[0] * spec.origin_off;
+  const double oy = double(ordered_to_float(bounds[3 * f + 1])) - spec.cell[1] * spec.origin_off;
+  const double oz = double(ordered_to_float(bounds[3 * f + 2])) - spec.cell[2] * spec.origin_off;
+  double best = DBL_MAX;
+  int best_idx = 0x7fffffff;
+  auto scan = [&](long long x0, long long x1, long long y0, long long y1, long long z0, long long z1) {
+    x0 = max(x0, 0ll); y0 = max(y0, 0ll); z0 = max(z0, 0ll);
+    x1 = min(x1, (long long)kAxisMax); y1 = min(y1, (long long)kAxisMax); z1 = min(z1, (long long)kAxisMax);
+    if (x0 > x1) return;
+    for (long long iz = z0; iz <= z1; ++iz)
+      for (long long iy = y0; iy <= y1; ++iy) {
+        int b, en;
+        row_range(g, f, uint32_t(iz), uint32_t(iy), uint32_t(x0), uint32_t(x1), &b, &en);
+        for (int i = b; i < en; ++i) {
+          const float4 p = g.pts[i];
+          const double d = dist2_rn(cx, cy, cz, p.x, p.y, p.z);
+          const int idx = __float_as_int(p.w);
+          if (d < best || (d == best && idx < best_idx)) { best = d; best_idx = idx; }
+        }
+      }
+  };
+  const long long ix = (long long)floor((cx - ox) / spec.cell[0]);
+  const long long iy = (long long)floor((cy - oy) / spec.cell[1]);
+  const long long iz = (long long)floor((cz - oz) / spec.cell[2]);
+  // the frame is not empty, so a box that covers the whole key space terminates the loop
+  for (long long r = 1; best == DBL_MAX; r *= 2) {
+    scan(ix - r, ix + r, iy - r, iy + r, iz - r, iz + r);
+    if (r > 4ll * (kAxisMax + 1) + llabs(ix) + llabs(iy) + llabs(iz)) break;
+  }
+  if (best == DBL_MAX) {
+    atomicOr(err, kErrRange);
+    out_idx[q] = 0;
+    return;
+  }
+  // every point closer than sqrt(best) lies in a cell overlapping the box centroid +- reach
+  const double reach = sqrt(best) * (1.0 + 1e-9) + 1e-12;
+  scan((long long)floor((cx - reach - ox) / spec.cell[0]), (long long)floor((cx + reach - ox) / spec.cell[0]),
+       (long long)floor((cy - reach - oy) / spec.cell[1]), (long long)floor((cy + reach - oy) / spec.cell[1]),
+       (long long)floor((cz - reach - oz) / spec.cell[2]), (long long)floor((cz + reach - oz) / spec.cell[2]));
+  out_idx[q] = best_idx;
+}
+
 __global__ void frame_ranges_kernel(const uint64_t* __restrict__ cell_key, const int32_t* __restrict__ num_cells,
                                     int num_frames, int32_t* __restrict__ out_frame_ptr) {
   const int f = blockIdx.x * blockDim.x + threadIdx.x;
@@ -624,6 +705,90 @@ extern "C" int pg_voxel_keypoints(const float* xyz, const int32_t* frame_ptr, in
   PG_CUDA_OK(cudaMemcpyAsync(&h[1], grid.err.ptr, sizeof(int32_t), cudaMemcpyDeviceToHost, s));
   PG_CUDA_OK(cudaStreamSynchronize(s));
   if (int rc = graph_error(h[1])) return rc;
+  *out_num_keypoints_host = h[0];
+  if (h[0] > capacity) {
+    set_error("keypoint buffer too small: need %d, capacity %lld", h[0], (long long)capacity);
+    return PG_ERR_CAPACITY;
+  }
+  return PG_OK;
+}
+
+// multi_layer_downsampling for one scale (graph_gen.py:41-45): the fp64 voxel centroids themselves.
+extern "C" int pg_voxel_centroids(const float* xyz, const int32_t* frame_ptr, int32_t num_frames, int64_t num_points,
+                                  const double* voxel_size_host, double* out_centroids, int64_t capacity,
+                                  int32_t* out_frame_ptr, int64_t* out_num_host, void* stream) {
+  cudaStream_t s = static_cast<cudaStream_t>(stream);
+  PG_REQUIRE(xyz && frame_ptr && voxel_size_host && out_centroids && out_frame_ptr && out_num_host,
+             "pg_voxel_centroids: null argument");
+  PG_REQUIRE(voxel_size_host[0] > 0 && voxel_size_host[1] > 0 && voxel_size_host[2] > 0, "voxel size must be positive");
+  GridSpec spec;
+  spec.cell[0] = voxel_size_host[0];
+  spec.cell[1] = voxel_size_host[1];
+  spec.cell[2] = voxel_size_host[2];
+  spec.origin_off = 0.5;
+  BuiltGrid grid;
+  if (int rc = build_grid(xyz, frame_ptr, num_frames, num_points, spec, s, &grid)) return rc;
+  voxel_centroid_kernel<<<ceil_div(num_points, 128), 128, 0, s>>>(grid.view, out_centroids, nullptr, capacity);
+  PG_LAUNCH_CHECK();
+  frame_ranges_kernel<<<ceil_div(num_frames + 1, 128), 128, 0, s>>>(grid.view.cell_key, grid.view.num_cells, num_frames,
+                                                                     out_frame_ptr);
+  PG_LAUNCH_CHECK();
+  int32_t h[2] = {0, 0};
+  PG_CUDA_OK(cudaMemcpyAsync(&h[0], grid.view.num_cells, sizeof(int32_t), cudaMemcpyDeviceToHost, s));
+  PG_CUDA_OK(cudaMemcpyAsync(&h[1], grid.err.ptr, sizeof(int32_t), cudaMemcpyDeviceToHost, s));
+  PG_CUDA_OK(cudaStreamSynchronize(s));
+  if (int rc = graph_error(h[1])) return rc;
+  *out_num_host = h[0];
+  if (h[0] > capacity) {
+    set_error("centroid buffer too small: need %d, capacity %lld", h[0], (long long)capacity);
+    return PG_ERR_CAPACITY;
+  }
+  return PG_OK;
+}
+
+// multi_layer_downsampling_select for a scale that differs from the previous level's (graph_gen.py:82-88):
+// voxel centroids of the ORIGINAL cloud, each snapped to the nearest vertex of the previous level `base_xyz`.
+extern "C" int pg_voxel_keypoints_select(const float* xyz, const int32_t* frame_ptr, int32_t num_frames, int64_t num_points,
+                                         const double* voxel_size_host, const float* base_xyz,
+                                         const int32_t* base_frame_ptr, int64_t num_base, int32_t* out_keypoint_idx,
+                                         int64_t capacity, int32_t* out_kp_frame_ptr, int64_t* out_num_keypoints_host,
+                                         void* stream) {
+  cudaStream_t s = static_cast<cudaStream_t>(stream);
+  PG_REQUIRE(xyz && frame_ptr && voxel_size_host && base_xyz && base_frame_ptr && out_keypoint_idx && out_kp_frame_ptr &&
+                 out_num_keypoints_host,
+             "pg_voxel_keypoints_select: null argument");
+  PG_REQUIRE(voxel_size_host[0] > 0 && voxel_size_host[1] > 0 && voxel_size_host[2] > 0, "voxel size must be positive");
+  GridSpec spec;
+  spec.cell[0] = voxel_size_host[0];
+  spec.cell[1] = voxel_size_host[1];
+  spec.cell[2] = voxel_size_host[2];
+  spec.origin_off = 0.5;
+  BuiltGrid grid, base;
+  if (int rc = build_grid(xyz, frame_ptr, num_frames, num_points, spec, s, &grid)) return rc;
+  Temp cent, cframe;
+  PG_CUDA_OK(cent.alloc(sizeof(double) * 3 * num_points, s));
+  PG_CUDA_OK(cframe.alloc(sizeof(int32_t) * num_points, s));
+  voxel_centroid_kernel<<<ceil_div(num_points, 128), 128, 0, s>>>(grid.view, cent.as<double>(), cframe.as<int32_t>(),
+                                                                    num_points);
+  PG_LAUNCH_CHECK();
+  frame_ranges_kernel<<<ceil_div(num_frames + 1, 128), 128, 0, s>>>(grid.view.cell_key, grid.view.num_cells, num_frames,
+                                                                     out_kp_frame_ptr);
+  PG_LAUNCH_CHECK();
+  GridSpec bspec = spec;       // search grid over the base vertices, same cell size
+  bspec.origin_off = 0.0;
+  if (int rc = build_grid(base_xyz, base_frame_ptr, num_frames, num_base, bspec, s, &base)) return rc;
+  nearest_point_kernel<<<ceil_div(num_points, 128), 128, 0, s>>>(base.view, bspec, base.bounds.as<uint32_t>(), base_frame_ptr,
+                                                                   cent.as<double>(), cframe.as<int32_t>(),
+                                                                   grid.view.num_cells, capacity, out_keypoint_idx,
+                                                                   base.err.as<int>());
+  PG_LAUNCH_CHECK();
+  int32_t h[3] = {0, 0, 0};
+  PG_CUDA_OK(cudaMemcpyAsync(&h[0], grid.view.num_cells, sizeof(int32_t), cudaMemcpyDeviceToHost, s));
+  PG_CUDA_OK(cudaMemcpyAsync(&h[1], grid.err.ptr, sizeof(int32_t), cudaMemcpyDeviceToHost, s));
+  PG_CUDA_OK(cudaMemcpyAsync(&h[2], base.err.ptr, sizeof(int32_t), cudaMemcpyDeviceToHost, s));
+  PG_CUDA_OK(cudaStreamSynchronize(s));
+  if (int rc = graph_error(h[1])) return rc;
+  if (int rc = graph_error(h[2])) return rc;
   *out_num_keypoints_host = h[0];
   if (h[0] > capacity) {
     set_error("keypoint buffer too small: need %d, capacity %lld", h[0], (long long)capacity);

@@ -856,11 +856,37 @@ __device__ __forceinline__ void segmax_load_ids(const TcParams& p, int64_t tile_
   }
 }
 
-// The warp drains kBlocks blocks of 32 edge columns starting at block blk0 (8 blocks = the whole tile; the GNN
-// kernel gives each lane quarter two warps with 4 blocks each so that more TMEM loads are in flight).
+// Destination runs of kBlocks blocks of 32 edge columns (lane j of the warp holds the destination of column j of
+// each block).  Computed BEFORE the warp waits for the accumulator: the shuffles / votes are long-latency
+// instructions and would otherwise sit on the drain's critical path (the tensor core idles while D1 is drained).
+template <int kBlocks>
+struct SegRuns {
+  int my[kBlocks];          // this lane's column's destination (-1: beyond the edge list or out of range)
+  int first[kBlocks];       // destination of column 0 of the block
+  uint32_t bits[kBlocks];   // bit j: column j starts a new destination run (j >= 1)
+};
+
+template <int kBlocks>
+__device__ __forceinline__ void segmax_prepare(const TcParams& p, const int (&ids)[kBlocks], int lane, SegRuns<kBlocks>& r) {
+#pragma unroll
+  for (int c = 0; c < kBlocks; ++c) {
+    int my = ids[c];
+    if (my >= p.num_dst || my < -1) { *p.err = 1; my = -1; }
+    const int pv = __shfl_up_sync(0xffffffffu, my, 1);
+    r.my[c] = my;
+    r.bits[c] = __ballot_sync(0xffffffffu, lane != 0 && my != pv);
+    r.first[c] = __shfl_sync(0xffffffffu, my, 0);
+  }
+}
+
+// The warp drains kBlocks blocks of 32 edge columns starting at block blk0 (8 blocks = the whole tile).
+// Thread = TMEM lane = output feature; the running max of the current destination is carried in a register
+// across blocks and flushed with one 128-byte coalesced atomicMax per (destination run, 32 features).
+// A block without a boundary is 16 three-input maxima; a block with one is handled in groups of 8 columns, and
+// only the group that contains the boundary goes element by element (all branches are warp uniform).
 template <int kBlocks>
 __device__ __forceinline__ void segmax_d1_transposed(const TcParams& p, uint32_t tmem, uint32_t d1_col, uint32_t rank,
-                                                     int quarter, int lane, int blk0, const int (&ids)[kBlocks],
+                                                     int quarter, int lane, int blk0, const SegRuns<kBlocks>& runs,
                                                      int f0 = 0) {
   const uint32_t lane_base = uint32_t(quarter * 32) << 16;
   const int f = f0 + int(rank) * 128 + quarter * 32 + lane;   // f0: first output feature of this M = 256 block
@@ -870,71 +896,75 @@ __device__ __forceinline__ void segmax_d1_transposed(const TcParams& p, uint32_t
     if (cur >= 0 && f_ok && m > -FLT_MAX)
       atomicMax(reinterpret_cast<int*>(p.out + int64_t(cur) * p.n + f), __float_as_int(fmaxf(m + bias_f, 0.0f)));
   };
-  {
-    const uint32_t tbase = tmem + lane_base + d1_col + uint32_t(blk0 * 32);
-    uint32_t va[32], vb[32];
-    int cur = -1;
-    float m = -FLT_MAX;
-    auto block = [&](const uint32_t (&v)[32], int my) {
-      if (my >= p.num_dst || my < -1) { *p.err = 1; my = -1; }
-      const int pv = __shfl_up_sync(0xffffffffu, my, 1);
-      const uint32_t bits = __ballot_sync(0xffffffffu, lane != 0 && my != pv);
-      const int first = __shfl_sync(0xffffffffu, my, 0);
-      if (first != cur) {
-        flush(cur, m);
-        cur = first;
-        m = -FLT_MAX;
-      }
-      if (bits == 0) {
-        float t0 = fmaxf(__uint_as_float(v[0]), __uint_as_float(v[1]));
-        float t1 = fmaxf(__uint_as_float(v[2]), __uint_as_float(v[3]));
-#pragma unroll
-        for (int j = 4; j < 32; j += 2) {
-          t0 = fmaxf(t0, __uint_as_float(v[j]));
-          t1 = fmaxf(t1, __uint_as_float(v[j + 1]));
-        }
-        m = fmaxf(m, fmaxf(t0, t1));
-      } else {
-        int sb = 0;
-#pragma unroll 1
-        while (true) {
-          const uint32_t rest = bits >> (sb + 1);
-          const int eb = rest ? sb + __ffs(rest) : 32;
-          float t = -FLT_MAX;
-#pragma unroll
-          for (int j = 0; j < 32; ++j) t = fmaxf(t, (j >= sb && j < eb) ? __uint_as_float(v[j]) : -FLT_MAX);
-          m = fmaxf(m, t);
-          if (eb >= 32) break;
-          flush(cur, m);
-          cur = __shfl_sync(0xffffffffu, my, eb);
-          m = -FLT_MAX;
-          sb = eb;
-        }
-      }
-    };
-    tmem_ld32(tbase, va);
-#pragma unroll
-    for (int c = 0; c < kBlocks; c += 2) {
-      tmem_ld_wait();
-      tmem_ld32(tbase + uint32_t((c + 1) * 32), vb);
-      block(va, ids[c]);
-      tmem_ld_wait();
-      if (c + 2 < kBlocks) tmem_ld32(tbase + uint32_t((c + 2) * 32), va);
-      block(vb, ids[c + 1]);
+  const uint32_t tbase = tmem + lane_base + d1_col + uint32_t(blk0 * 32);
+  uint32_t va[32], vb[32];
+  int cur = -1;
+  float m = -FLT_MAX;
+  auto block = [&](const uint32_t (&v)[32], int my, int first, uint32_t bits) {
+    if (first != cur) {
+      flush(cur, m);
+      cur = first;
+      m = -FLT_MAX;
     }
-    flush(cur, m);
+    if (bits == 0) {
+      float t0 = fmaxf(__uint_as_float(v[0]), __uint_as_float(v[1]));
+      float t1 = fmaxf(__uint_as_float(v[2]), __uint_as_float(v[3]));
+#pragma unroll
+      for (int j = 4; j < 32; j += 2) {
+        t0 = fmaxf(t0, __uint_as_float(v[j]));
+        t1 = fmaxf(t1, __uint_as_float(v[j + 1]));
+      }
+      m = fmaxf(m, fmaxf(t0, t1));
+    } else {
+#pragma unroll
+      for (int g = 0; g < 4; ++g) {
+        if (((bits >> (8 * g)) & 0xffu) == 0) {
+          float t0 = fmaxf(__uint_as_float(v[8 * g]), __uint_as_float(v[8 * g + 1]));
+          float t1 = fmaxf(__uint_as_float(v[8 * g + 2]), __uint_as_float(v[8 * g + 3]));
+          t0 = fmaxf(t0, fmaxf(__uint_as_float(v[8 * g + 4]), __uint_as_float(v[8 * g + 5])));
+          t1 = fmaxf(t1, fmaxf(__uint_as_float(v[8 * g + 6]), __uint_as_float(v[8 * g + 7])));
+          m = fmaxf(m, fmaxf(t0, t1));
+        } else {
+#pragma unroll
+          for (int j = 8 * g; j < 8 * g + 8; ++j) {
+            if ((bits >> j) & 1u) {
+              flush(cur, m);
+              cur = __shfl_sync(0xffffffffu, my, j);
+              m = -FLT_MAX;
+            }
+            m = fmaxf(m, __uint_as_float(v[j]));
+          }
+        }
+      }
+    }
+  };
+  tmem_ld32(tbase, va);
+#pragma unroll
+  for (int c = 0; c < kBlocks; c += 2) {
+    tmem_ld_wait();
+    tmem_ld32(tbase + uint32_t((c + 1) * 32), vb);
+    block(va, runs.my[c], runs.first[c], runs.bits[c]);
+    tmem_ld_wait();
+    if (c + 2 < kBlocks) tmem_ld32(tbase + uint32_t((c + 2) * 32), va);
+    block(vb, runs.my[c + 1], runs.first[c + 1], runs.bits[c + 1]);
   }
+  flush(cur, m);
 }
 
 // Segment max of a ROW-MAJOR accumulator D2[edge lanes, n2 feature columns at column d2_col] (output
 // features 256 ..) for ONE warp: one redux.sync.max.f32 per column and destination run.
 // (the warp takes the 16-column chunks ci0, ci0 + ci_step, ...)
 // `row` = the edge whose accumulator row sits in this TMEM lane (-1: none - lanes 16..31 of an M = 128 tile).
+// `d_row` = destination of that edge, loaded by the caller (well ahead of the drain: a global load costs ~1 us
+// under the producers' gather traffic) - see segmax_d2_load.
+__device__ __forceinline__ int segmax_d2_load(const TcParams& p, int64_t row) {
+  return (row >= 0 && row < p.num_rows) ? __ldg(p.dst + row) : -1;
+}
 __device__ __forceinline__ void segmax_d2_rowmajor(const TcParams& p, uint32_t tmem, uint32_t d2_col, int quarter, int lane,
-                                                   int64_t row, int ci0 = 0, int ci_step = 1) {
+                                                   int d_row, int ci0 = 0, int ci_step = 1) {
   const uint32_t lane_base = uint32_t(quarter * 32) << 16;
   {
-    int d = (row >= 0 && row < p.num_rows) ? __ldg(p.dst + row) : -1;
+    int d = d_row;
     if (d < 0 || d >= p.num_dst) d = -1;
     const int prev = __shfl_up_sync(0xffffffffu, d, 1);
     const uint32_t bits = __ballot_sync(0xffffffffu, lane != 0 && prev != d);
@@ -1054,7 +1084,21 @@ __device__ __forceinline__ void seg_producer(const TcParams& p, const SegSmem& s
                                              int64_t cluster_id, int64_t num_clusters) {
   const int g = pt >> 7, wg = (pt >> 5) & 3;
   const int r = pt & 127;                     // the row whose per-tile context this thread computes
+#ifndef PG_SEG_LANEMAP
+#define PG_SEG_LANEMAP 1
+#endif
+#ifndef PG_SEG_PREFETCH
+#define PG_SEG_PREFETCH 2      // own-iterations between the request of a P slice and its use (register buffers)
+#endif
+#if PG_SEG_LANEMAP
+  // production mapping: rows 32 wg + rr + 8 i (i = 0..3), k-slice c.  Lanes 0-15 take slices 0/1, lanes 16-31 slices
+  // 2/3, so that the 64-bit stores of a half warp cover 128 CONTIGUOUS bytes of the stage (one core matrix): with the
+  // natural (rr = lane / 4, c = lane % 4) order a half warp wrote 2 x 64 bytes 128 bytes apart = the same 16 banks twice
+  // (2-way conflict on every store; ncu: 39 % of the kernel's shared wavefronts were conflict replays).
+  const int rr = (lane >> 1) & 7, c = ((lane >> 4) << 1) | (lane & 1);
+#else
   const int rr = lane >> 2, c = lane & 3;     // production mapping: rows 32 wg + rr + 8 i (i = 0..3), k-slice c
+#endif
   float4* ctx = sm.ctx + g * 128;
   int* sin = sm.si_next + g * 128;
   const int row0 = wg * 32 + rr;
@@ -1122,7 +1166,13 @@ __device__ __forceinline__ void seg_producer(const TcParams& p, const SegSmem& s
 #pragma unroll
     for (int i = 0; i < 4; ++i) {
       const int si = (jj == j) ? __float_as_int(ctx[row0 + 8 * i].w) : sin[row0 + 8 * i];
+#if defined(PG_LAB) && defined(PG_SEG_NOLOAD)     // lab experiment (wrong results): no gather at all
+      q[i] = make_float4(float(si), 1.0f, 2.0f, float(ss));
+#elif defined(PG_LAB) && defined(PG_SEG_SAMEROW)  // lab experiment (wrong results): every row gathers vertex (tile row)
+      q[i] = ldg_nc_pinned(pbase + uint32_t((row0 + 8 * i) * p.ldp + ss * 16) + 0 * si);
+#else
       q[i] = ldg_nc_pinned(pbase + uint32_t(si * p.ldp + ss * 16));   // element offset < 2^31 (checked at launch)
+#endif
     }
   };
   auto step = [&](float4 (&q)[4]) {
@@ -1142,10 +1192,15 @@ __device__ __forceinline__ void seg_producer(const TcParams& p, const SegSmem& s
 #pragma unroll
     for (int i = 0; i < 4; ++i) {
       const float4 cx = ctx[row0 + 8 * i];
+#if defined(PG_LAB) && defined(PG_SEG_NOCOORD)    // lab experiment (wrong results): no coordinate term
+      const float v0 = fmaxf(q[i].x + cx.x, 0.0f), v1 = fmaxf(q[i].y + wx.x, 0.0f);
+      const float v2 = fmaxf(q[i].z + wy.x, 0.0f), v3 = fmaxf(q[i].w + wz.x, 0.0f);
+#else
       const float v0 = fmaxf(fmaf(cx.z, wz.x, fmaf(cx.y, wy.x, fmaf(cx.x, wx.x, q[i].x))), 0.0f);
       const float v1 = fmaxf(fmaf(cx.z, wz.y, fmaf(cx.y, wy.y, fmaf(cx.x, wx.y, q[i].y))), 0.0f);
       const float v2 = fmaxf(fmaf(cx.z, wz.z, fmaf(cx.y, wy.z, fmaf(cx.x, wx.z, q[i].z))), 0.0f);
       const float v3 = fmaxf(fmaf(cx.z, wz.w, fmaf(cx.y, wy.w, fmaf(cx.x, wx.w, q[i].w))), 0.0f);
+#endif
       split_bf16x2_trunc(v0, v1, &hi[i].x, &lo[i].x);
       split_bf16x2_trunc(v2, v3, &hi[i].y, &lo[i].y);
     }
@@ -1166,7 +1221,8 @@ __device__ __forceinline__ void seg_producer(const TcParams& p, const SegSmem& s
     advance(j1, s1);
     j2 = j1;
     s2 = s1;
-    advance(j2, s2);
+#pragma unroll
+    for (int a = 1; a < PG_SEG_PREFETCH; ++a) advance(j2, s2);
     fetch(q, j2, s2);
     asm volatile("" ::: "memory");       // the refill stays here, ahead of the next iteration's compute
     if (j1 != j && j1 < my_tiles) {
@@ -1180,12 +1236,19 @@ __device__ __forceinline__ void seg_producer(const TcParams& p, const SegSmem& s
     s = s1;
   };
   float4 qa[4], qb[4];
+#if PG_SEG_PREFETCH == 3
+  float4 qc[4];
+#endif
   fetch(qa, 0, s);
   {
     int j1 = 0;
     int s1 = s;
     advance(j1, s1);
     fetch(qb, j1, s1);
+#if PG_SEG_PREFETCH == 3
+    advance(j1, s1);
+    fetch(qc, j1, s1);
+#endif
   }
   asm volatile("" ::: "memory");
   while (true) {
@@ -1193,6 +1256,10 @@ __device__ __forceinline__ void seg_producer(const TcParams& p, const SegSmem& s
     if (j >= my_tiles) break;
     step(qb);
     if (j >= my_tiles) break;
+#if PG_SEG_PREFETCH == 3
+    step(qc);
+    if (j >= my_tiles) break;
+#endif
   }
 }
 
@@ -1396,34 +1463,44 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kSegThreads, 1) seg_
     }
     cluster_sync();   // [sync A]
     uint32_t tile_iter = 0;
-    for (int64_t tile = tile0; tile < tile_end; tile += tstride, ++tile_iter) {
-      const uint32_t buf = d2_stride ? (tile_iter & 1u) : 0u;
-      // destination ids of the eight 32-column blocks of D1 in TMEM order: half a = edges 0..63 and 128..191 of the
-      // tile (rows 0..63 of CTA 0 and of CTA 1), half b = edges 64..127 and 192..255
-      int ids_a[4], ids_b[4];
+    // destination ids of the eight 32-column blocks of D1 in TMEM order: half a = edges 0..63 and 128..191 of the
+    // tile (rows 0..63 of CTA 0 and of CTA 1), half b = edges 64..127 and 192..255; d2 = destination of the edge in
+    // this thread's D2 lane.  Loaded one tile ahead (while D2 of the previous tile is drained).
+    int ids_a[4], ids_b[4], d2 = -1;
+    auto load_ids = [&](int64_t tile) {
 #pragma unroll
       for (int c = 0; c < 4; ++c) {
         const int64_t ea = tile * 256 + (c < 2 ? c * 32 : 128 + (c - 2) * 32) + lane;
         const int64_t eb = ea + 64;
-        ids_a[c] = ea < p.num_rows ? __ldg(p.dst + ea) : -1;
-        ids_b[c] = eb < p.num_rows ? __ldg(p.dst + eb) : -1;
+        ids_a[c] = (tile < tile_end && ea < p.num_rows) ? __ldg(p.dst + ea) : -1;
+        ids_b[c] = (tile < tile_end && eb < p.num_rows) ? __ldg(p.dst + eb) : -1;
       }
+      if (p.n2 > 0)
+        d2 = tile < tile_end ? segmax_d2_load(p, tile * 256 + int64_t(rank) * kTileRows + quarter * 32 + lane) : -1;
+    };
+    load_ids(tile0);
+    for (int64_t tile = tile0; tile < tile_end; tile += tstride, ++tile_iter) {
+      const uint32_t buf = d2_stride ? (tile_iter & 1u) : 0u;
+      SegRuns<4> runs_a, runs_b;
+      segmax_prepare<4>(p, ids_a, lane, runs_a);
+      segmax_prepare<4>(p, ids_b, lane, runs_b);
+      const int d2_cur = d2;
       if (warp == kSegEpiWarp0 && lane == 0) PG_TRACE(3 + 2 * rank, tile_iter, 0);
       mbar_wait(sm.bar_tmem_full, tile_iter & 1u);
       if (warp == kSegEpiWarp0 && lane == 0) PG_TRACE(3 + 2 * rank, tile_iter, 1);
       tc_fence_after();
-      segmax_d1_transposed<4>(p, tmem, 0u, rank, quarter, lane, 0, ids_a);
+      segmax_d1_transposed<4>(p, tmem, 0u, rank, quarter, lane, 0, runs_a);
       tc_fence_before();
       __syncwarp();
       if (lane == 0) mbar_arrive_cluster_relaxed(&sm.bar_d1_empty[0], 0);
-      segmax_d1_transposed<4>(p, tmem, 0u, rank, quarter, lane, 4, ids_b);
+      segmax_d1_transposed<4>(p, tmem, 0u, rank, quarter, lane, 4, runs_b);
       tc_fence_before();
       __syncwarp();
       if (lane == 0) mbar_arrive_cluster_relaxed(&sm.bar_d1_empty[1], 0);
       if (warp == kSegEpiWarp0 && lane == 0) PG_TRACE(3 + 2 * rank, tile_iter, 2);
+      load_ids(tile + tstride);
       if (p.n2 > 0) {
-        segmax_d2_rowmajor(p, tmem, kD2Col + buf * d2_stride, quarter, lane,
-                           tile * 256 + int64_t(rank) * kTileRows + quarter * 32 + lane);
+        segmax_d2_rowmajor(p, tmem, kD2Col + buf * d2_stride, quarter, lane, d2_cur);
         tc_fence_before();
         __syncwarp();
         if (lane == 0) mbar_arrive_cluster_relaxed(&sm.bar_d2_empty[buf], 0);
@@ -1783,11 +1860,14 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kChainThreads, 1) ml
       if (store) continue;
       int ids[8];
       segmax_load_ids<8>(p, tile * 256, lane, 0, ids);
+      SegRuns<8> runs;
+      segmax_prepare<8>(p, ids, lane, runs);
       mbar_wait(&sm.bar_d_full[P - 1], tile_iter & 1u);
       tc_fence_after();
-      segmax_d1_transposed<8>(p, tmem, d_last, rank, quarter, lane, 0, ids);
+      segmax_d1_transposed<8>(p, tmem, d_last, rank, quarter, lane, 0, runs);
       if (p.n2 > 0)
-        segmax_d2_rowmajor(p, tmem, d_last + 256u, quarter, lane, tile * 256 + int64_t(rank) * kTileRows + quarter * 32 + lane);
+        segmax_d2_rowmajor(p, tmem, d_last + 256u, quarter, lane,
+                           segmax_d2_load(p, tile * 256 + int64_t(rank) * kTileRows + quarter * 32 + lane));
       tc_fence_before();
       __syncwarp();
       if (lane == 0) mbar_arrive_cluster_relaxed(&sm.bar_d_empty[P - 1], 0);
@@ -1986,9 +2066,11 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kLastThreads, 1) poo
       const uint32_t buf = tile_iter & 1u, use = tile_iter >> 1;
       int ids[8];
       segmax_load_ids<8>(p, tile * 256, lane, 0, ids);
+      SegRuns<8> runs;
+      segmax_prepare<8>(p, ids, lane, runs);
       mbar_wait(&sm.bar_d_full[buf], use & 1u);
       tc_fence_after();
-      segmax_d1_transposed<8>(p, tmem, buf * 256u, rank, quarter, lane, 0, ids, half * 256);
+      segmax_d1_transposed<8>(p, tmem, buf * 256u, rank, quarter, lane, 0, runs, half * 256);
       tc_fence_before();
       __syncwarp();
       if (lane == 0) mbar_arrive_cluster_relaxed(&sm.bar_d_empty[buf], 0);

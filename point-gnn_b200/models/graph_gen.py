@@ -4,7 +4,8 @@
 * ``get_graph_generate_fn``              graph_gen.py:222-227
 * ``gen_multi_level_local_graph_v3``     graph_gen.py:155-195
 * ``gen_disjointed_rnn_local_graph_v3``  graph_gen.py:197-220
-* ``multi_layer_downsampling_select``    graph_gen.py:49-90  (+ :11-47 voxel centroids)
+* ``multi_layer_downsampling``           graph_gen.py:11-47  (voxel centroids, any list of scales)
+* ``multi_layer_downsampling_select``    graph_gen.py:49-90  (any list of scales)
 
 Inputs may be NumPy arrays (the reference's calling convention, run.py:219-222: arrays are
 copied to the GPU, results copied back as NumPy) or torch CUDA tensors (results stay on the
@@ -78,6 +79,28 @@ def _voxel_vector(base_voxel_size, level):
     return np.broadcast_to(v, (3,)).astype(np.float64)
 
 
+def multi_layer_downsampling(points_xyz, base_voxel_size, levels=[1], add_rnd3d=False):
+    """graph_gen.py:11-47 (Open3D branch).  -> list: the cloud, then per level the fp64 voxel centroids of the
+    ORIGINAL cloud at that scale (a level with the previous level's scale repeats the previous entry, :21-22).
+    Centroid order: ascending linear voxel key per frame (Open3D's own order is unspecified)."""
+    if add_rnd3d:
+        raise NotImplementedError('add_rnd3d=True with the centroid method (graph_gen.py:24-39) is not built; '
+                                  'the training configs use downsample_method="random"')
+    cloud = _Cloud(points_xyz)
+    downsampled_list = [cloud.xyz]
+    last_level = 0
+    for level in levels:
+        if np.isclose(last_level, level):
+            downsampled_list.append(downsampled_list[-1].clone())
+        else:
+            cent, _ = _lib.voxel_centroids(cloud.xyz, cloud.frame_ptr, _voxel_vector(base_voxel_size, level))
+            downsampled_list.append(cent)
+        last_level = level
+    if cloud.numpy_io:
+        downsampled_list = [np.asarray(points_xyz)] + [d.cpu().numpy() for d in downsampled_list[1:]]
+    return downsampled_list
+
+
 def multi_layer_downsampling_select(points_xyz, base_voxel_size, levels=[1], add_rnd3d=False):
     """graph_gen.py:49-90.  -> (vertex_coord_list, keypoint_indices_list)."""
     cloud = _Cloud(points_xyz)
@@ -108,14 +131,18 @@ def _downsampling_select(cloud, base_voxel_size, levels, add_rnd3d):
             keypoint_indices_list.append(kidx)
         else:
             # graph_gen.py:41-45 voxelises the ORIGINAL cloud, :84-88 snaps to the previous level.
-            # All shipped configs have one distinct scale, where previous level == original cloud.
-            if base_points is not cloud.xyz:
-                raise NotImplementedError('more than one distinct downsampling scale')
-            idx, kp_fp = _lib.voxel_keypoints(cloud.xyz, cloud.frame_ptr, _voxel_vector(base_voxel_size, level))
-            vertex_coord_list.append(_lib.gather_rows(cloud.xyz, idx))
+            voxel = _voxel_vector(base_voxel_size, level)
+            if base_points is cloud.xyz:
+                # every shipped config: one distinct scale, previous level == original cloud (one grid, one kernel)
+                idx, kp_fp = _lib.voxel_keypoints(cloud.xyz, cloud.frame_ptr, voxel)
+            else:
+                # a second distinct scale (graph_gen.py:17-23, 76-88): nearest vertex of the previous level
+                idx, kp_fp = _lib.voxel_keypoints_select(cloud.xyz, cloud.frame_ptr, voxel, base_points,
+                                                         frame_ptr_list[-1])
+            vertex_coord_list.append(_lib.gather_rows(base_points, idx))
             frame_ptr_list.append(kp_fp)
             kidx = idx[:, None]
-            kidx._pg_trusted = (int(cloud.xyz.shape[0]), kidx._version)      # rows of the level it was snapped to
+            kidx._pg_trusted = (int(base_points.shape[0]), kidx._version)    # rows of the level it was snapped to
             keypoint_indices_list.append(kidx)
         last_level = level
     return vertex_coord_list, keypoint_indices_list, frame_ptr_list

@@ -159,3 +159,55 @@ def test_large_cloud_properties(car):
     bwd = e1[:, 1] * k + e1[:, 0]
     assert np.array_equal(np.sort(fwd), np.sort(bwd))
     _check_graph(xyz, car.graph_kwargs, (coords, kp, edges))
+
+
+def test_multiscale_downsampling_vs_reference_golden():
+    """General multi-scale keypoint selection (a second and third distinct scale: the voxel centroids of the ORIGINAL
+    cloud snapped to the nearest vertex of the PREVIOUS level, graph_gen.py:17-23, 41-45, 76-88) against the
+    reference's own multi_layer_downsampling_select / multi_layer_downsampling (tests/golden/graph_multiscale.npz)."""
+    import os
+    from pointgnn_b200.models import graph_gen
+    g = np.load(os.path.join(os.path.dirname(__file__), 'golden', 'graph_multiscale.npz'))
+    levels = [float(v) for v in g['levels']]
+    coords, kp = graph_gen.multi_layer_downsampling_select(g['xyz'], float(g['base_voxel_size']), levels)
+    cents = graph_gen.multi_layer_downsampling(g['xyz'], float(g['base_voxel_size']), levels)
+    assert coords[0].dtype == np.float32 and kp[0].dtype == np.int64 and kp[0].shape[1] == 1
+    for i in range(len(levels)):
+        assert np.array_equal(kp[i][:, 0], g['kp_%d' % i]), i
+        assert np.array_equal(coords[i + 1], g['coords_%d' % (i + 1)]), i
+        assert cents[i + 1].dtype == np.float64 or i == 2
+        assert np.array_equal(np.asarray(cents[i + 1], dtype=np.float64), g['centroids_%d' % (i + 1)]), i
+
+
+def test_multiscale_graph_batched_vs_oracle():
+    """A three-level graph with two distinct scales, several frames in one call (frame_ptr), against the oracle frame
+    by frame with the batch_data offsets (train.py:135-171)."""
+    from pointgnn_b200.models import graph_gen
+    cfg = [
+        {'graph_gen_kwargs': {'num_neighbors': -1, 'radius': 1.0}, 'graph_gen_method': 'disjointed_rnn_local_graph_v3',
+         'graph_level': 0, 'graph_scale': 1},
+        {'graph_gen_kwargs': {'num_neighbors': -1, 'radius': 2.5}, 'graph_gen_method': 'disjointed_rnn_local_graph_v3',
+         'graph_level': 1, 'graph_scale': 2.5},
+        {'graph_gen_kwargs': {'num_neighbors': -1, 'radius': 4.0}, 'graph_gen_method': 'disjointed_rnn_local_graph_v3',
+         'graph_level': 2, 'graph_scale': 2.5},
+    ]
+    clouds = [synth.lidar_frame(40 + i, n)[0] for i, n in enumerate((3000, 1, 2500))]
+    fp = np.concatenate([[0], np.cumsum([len(c) for c in clouds])]).astype(np.int32)
+    coords, kp, edges, fps = graph_gen.gen_multi_level_local_graph_v3(
+        np.vstack(clouds), 0.5, cfg, frame_ptr=fp, return_frame_ptr=True)
+    off = [0, 0, 0, 0]
+    eo = [0, 0, 0]
+    for c in clouds:
+        co, ko, ed = graph.gen_multi_level_local_graph_v3(c, 0.5, cfg)
+        for lvl in range(3):
+            n_prev, n_cur = len(co[lvl]), len(co[lvl + 1])
+            assert np.array_equal(coords[lvl + 1][off[lvl + 1]:off[lvl + 1] + n_cur], co[lvl + 1])
+            assert np.array_equal(kp[lvl][off[lvl + 1]:off[lvl + 1] + n_cur, 0], ko[lvl][:, 0] + off[lvl])
+            e = ed[lvl] + np.array([[off[lvl], off[lvl + 1]]])
+            assert np.array_equal(edges[lvl][eo[lvl]:eo[lvl] + len(e)], e), lvl
+            eo[lvl] += len(e)
+        for lvl in range(4):
+            off[lvl] += len(co[lvl])
+    for lvl in range(3):
+        assert eo[lvl] == len(edges[lvl])
+        assert int(fps[lvl + 1][-1]) == len(coords[lvl + 1])

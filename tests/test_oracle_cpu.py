@@ -186,3 +186,20 @@ def test_all_shipped_checkpoints_load_and_run_through_the_oracle():
         assert np.allclose(probs.sum(axis=1), 1.0, atol=1e-5)
         seen += 1
     assert seen == 7
+
+
+def test_oracle_multiscale_matches_reference_golden():
+    """Several distinct downsampling scales (graph_gen.py:17-23, 76-88): tests/golden/graph_multiscale.npz is the
+    reference's own multi_layer_downsampling_select (unspecified orders canonicalised, tools/make_golden.py)."""
+    import os
+    g = np.load(os.path.join(os.path.dirname(__file__), 'golden', 'graph_multiscale.npz'))
+    levels = [float(v) for v in g['levels']]
+    coords, kp = graph.multi_layer_downsampling_select(g['xyz'], float(g['base_voxel_size']), levels)
+    cents = graph.multi_layer_downsampling(g['xyz'], float(g['base_voxel_size']), levels)
+    assert int(g['tie_rows']) > 0          # the fixture does exercise the tie rule
+    for i in range(len(levels)):
+        assert np.array_equal(kp[i][:, 0], g['kp_%d' % i])
+        assert np.array_equal(np.asarray(coords[i + 1], dtype=np.float32), g['coords_%d' % (i + 1)])
+        assert np.array_equal(np.asarray(cents[i + 1], dtype=np.float64), g['centroids_%d' % (i + 1)])
+    # level 2 repeats level 1's scale: identity (graph_gen.py:76-81)
+    assert np.array_equal(kp[2][:, 0], np.arange(len(kp[1])))

@@ -212,10 +212,84 @@ def graph_random_goldens():
     np.savez_compressed(os.path.join(GOLDEN, 'graph_random.npz'), **out)
 
 
+def graph_multiscale_goldens():
+    """tests/golden/graph_multiscale.npz: the reference's OWN multi_layer_downsampling_select (graph_gen.py:49-90, with
+    multi_layer_downsampling :11-47) for SEVERAL distinct scales - which cloud is voxelised, which level is searched,
+    the index layout are the reference running.  Two calls inside it have an UNSPECIFIED order upstream and are
+    canonicalised: (1) open3d.voxel_down_sample (:41-45; Open3D 0.7 is not installable) is served by the oracle's
+    restated voxel rule (ascending voxel key); (2) the kd_tree 1-NN (:84-86) is scikit-learn's own query, but where
+    several base vertices are EXACTLY equidistant in fp64 - every voxel with two points: its centroid is their
+    midpoint - scikit-learn returns whichever its tree visits first (version dependent); the wrapper returns the
+    lowest index among those exact minimisers.  The fixture records how many rows needed (2)."""
+    import sys as _sys
+    from sklearn.neighbors import NearestNeighbors as _SkNN
+    ref = reference_graph.load()
+    o3d = _sys.modules['open3d']
+
+    class _Pcd(object):
+        points = None
+    o3d.PointCloud = _Pcd
+    o3d.Vector3dVector = lambda a: np.asarray(a)
+    o3d.voxel_down_sample = lambda pcd, voxel_size: type('R', (), {'points': graph.voxel_down_sample(pcd.points, voxel_size)})()
+    stats = {'queries': 0, 'ties': 0}
+
+    class _CanonicalTies(object):
+        def __init__(self, n_neighbors=1, algorithm='kd_tree', n_jobs=1):
+            assert n_neighbors == 1 and algorithm == 'kd_tree'
+            self._nn = _SkNN(n_neighbors=1, algorithm=algorithm, n_jobs=n_jobs)
+
+        def fit(self, x):
+            self._x = np.asarray(x, dtype=np.float64)
+            self._nn.fit(x)
+            return self
+
+        def kneighbors(self, q, return_distance=False):
+            assert not return_distance
+            dist, idx = self._nn.kneighbors(q, return_distance=True)
+            q64 = np.asarray(q, dtype=np.float64)
+            out = idx.copy()
+            for j in range(len(q64)):
+                c = self._nn.radius_neighbors(q64[j:j + 1], radius=dist[j, 0] * (1 + 1e-9) + 1e-12,
+                                              return_distance=False)[0]
+                d = self._x[c] - q64[j]
+                d2 = (d[:, 0] * d[:, 0] + d[:, 1] * d[:, 1]) + d[:, 2] * d[:, 2]
+                best = np.sort(c[d2 == d2.min()])
+                assert idx[j, 0] in best, 'scikit-learn returned a non-minimiser'
+                stats['queries'] += 1
+                stats['ties'] += int(len(best) > 1)
+                out[j, 0] = best[0]
+            return out
+
+    xyz, _ = synth.lidar_frame(11, 12000)
+    levels = [1, 2, 2, 4.5]
+    orig = ref.NearestNeighbors
+    ref.NearestNeighbors = _CanonicalTies
+    try:
+        vc, kp = ref.multi_layer_downsampling_select(xyz, 0.4, levels)
+    finally:
+        ref.NearestNeighbors = orig
+    vo, ko = graph.multi_layer_downsampling_select(xyz, 0.4, levels)
+    out = {'xyz': xyz, 'levels': np.asarray(levels, dtype=np.float64), 'base_voxel_size': np.float64(0.4),
+           'tie_rows': np.int64(stats['ties']), 'query_rows': np.int64(stats['queries'])}
+    for i in range(len(levels)):
+        assert np.array_equal(np.asarray(vc[i + 1]), np.asarray(vo[i + 1])), 'oracle coordinates != reference (level %d)' % i
+        assert np.array_equal(np.asarray(kp[i]), np.asarray(ko[i])), 'oracle index != reference (level %d)' % i
+        out['coords_%d' % (i + 1)] = np.asarray(vc[i + 1], dtype=np.float32)
+        out['kp_%d' % i] = np.asarray(kp[i])[:, 0].astype(np.int32)
+        print('graph_multiscale level', i, 'scale', levels[i], 'vertices', len(kp[i]))
+    print('graph_multiscale: %d of %d 1-NN queries had exactly tied minimisers' % (stats['ties'], stats['queries']))
+    cents = ref.multi_layer_downsampling(xyz, 0.4, levels)
+    for i in range(len(levels)):
+        out['centroids_%d' % (i + 1)] = np.asarray(cents[i + 1], dtype=np.float64)
+    np.savez_compressed(os.path.join(GOLDEN, 'graph_multiscale.npz'), **out)
+
+
 if __name__ == '__main__':
     which = sys.argv[1] if len(sys.argv) > 1 else 'all'
     if which in ('all', 'graph_random'):
         graph_random_goldens()
+    if which in ('all', 'graph_multiscale'):
+        graph_multiscale_goldens()
     if which in ('all', 'gnn'):
         main()
     if which in ('all', 'post'):

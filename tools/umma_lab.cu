@@ -313,6 +313,142 @@ static int run_rate(int n1, int n2, int kp, int per_stage) {
   return 0;
 }
 
+
+// ---- TMEM drain rate: how fast can warps read a 128-lane x 256-column fp32 accumulator? -----------------
+//   umma_lab drain <warps 4|8> <variant>
+// variant 0: x32 loads, one at a time (ld, wait, 32 max)   1: x32, next load issued before the maxes (as pg_tc.cu)
+//         2: x64 double buffered   3: x128 one at a time   4: x32, three loads in flight   5: x16 one at a time
+__device__ __forceinline__ void ld64(uint32_t a, uint32_t (&v)[64]) {
+  asm volatile(
+      "tcgen05.ld.sync.aligned.32x32b.x64.b32 {%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, "
+      "%16, %17, %18, %19, %20, %21, %22, %23, %24, %25, %26, %27, %28, %29, %30, %31, "
+      "%32, %33, %34, %35, %36, %37, %38, %39, %40, %41, %42, %43, %44, %45, %46, %47, "
+      "%48, %49, %50, %51, %52, %53, %54, %55, %56, %57, %58, %59, %60, %61, %62, %63}, [%64];"
+      : "=r"(v[0]), "=r"(v[1]), "=r"(v[2]), "=r"(v[3]), "=r"(v[4]), "=r"(v[5]), "=r"(v[6]), "=r"(v[7]), "=r"(v[8]),
+        "=r"(v[9]), "=r"(v[10]), "=r"(v[11]), "=r"(v[12]), "=r"(v[13]), "=r"(v[14]), "=r"(v[15]), "=r"(v[16]),
+        "=r"(v[17]), "=r"(v[18]), "=r"(v[19]), "=r"(v[20]), "=r"(v[21]), "=r"(v[22]), "=r"(v[23]), "=r"(v[24]),
+        "=r"(v[25]), "=r"(v[26]), "=r"(v[27]), "=r"(v[28]), "=r"(v[29]), "=r"(v[30]), "=r"(v[31]), "=r"(v[32]),
+        "=r"(v[33]), "=r"(v[34]), "=r"(v[35]), "=r"(v[36]), "=r"(v[37]), "=r"(v[38]), "=r"(v[39]), "=r"(v[40]),
+        "=r"(v[41]), "=r"(v[42]), "=r"(v[43]), "=r"(v[44]), "=r"(v[45]), "=r"(v[46]), "=r"(v[47]), "=r"(v[48]),
+        "=r"(v[49]), "=r"(v[50]), "=r"(v[51]), "=r"(v[52]), "=r"(v[53]), "=r"(v[54]), "=r"(v[55]), "=r"(v[56]),
+        "=r"(v[57]), "=r"(v[58]), "=r"(v[59]), "=r"(v[60]), "=r"(v[61]), "=r"(v[62]), "=r"(v[63])
+      : "r"(a)
+      : "memory");
+}
+template <int N>
+__device__ __forceinline__ float vmax(const uint32_t (&v)[N], float m) {
+#pragma unroll
+  for (int j = 0; j < N; ++j) m = fmaxf(m, __uint_as_float(v[j]));
+  return m;
+}
+
+__global__ void __launch_bounds__(256) drain_kernel(int variant, int reps, float* out, long long* cycles) {
+  __shared__ uint32_t tmem_base;
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31, nwarps = blockDim.x >> 5;
+  if (warp == 0) {
+    tmem_alloc<1>(&tmem_base, 512);
+    tmem_relinquish<1>();
+  }
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem = tmem_base;
+  const int quarter = warp & 3, part = warp >> 2, parts = nwarps / 4;
+  const int cols = 256 / parts;                               // columns this warp drains per repetition
+  const uint32_t t0 = tmem + (uint32_t(quarter * 32) << 16) + uint32_t(part * cols);
+  float m = -1e30f;
+  __syncthreads();
+  const long long c0 = clock64();
+  for (int r = 0; r < reps; ++r) {
+    if (variant == 0) {
+      for (int c = 0; c < cols; c += 32) {
+        uint32_t v[32];
+        tmem_ld32(t0 + c, v);
+        tmem_ld_wait();
+        m = vmax(v, m);
+      }
+    } else if (variant == 1) {
+      uint32_t va[32], vb[32];
+      tmem_ld32(t0, va);
+      for (int c = 0; c < cols; c += 64) {
+        tmem_ld_wait();
+        tmem_ld32(t0 + c + 32, vb);
+        m = vmax(va, m);
+        tmem_ld_wait();
+        if (c + 64 < cols) tmem_ld32(t0 + c + 64, va);
+        m = vmax(vb, m);
+      }
+    } else if (variant == 2) {
+      uint32_t va[64], vb[64];
+      ld64(t0, va);
+      for (int c = 0; c < cols; c += 128) {
+        tmem_ld_wait();
+        if (c + 64 < cols) ld64(t0 + c + 64, vb);
+        m = vmax(va, m);
+        tmem_ld_wait();
+        if (c + 128 < cols) ld64(t0 + c + 128, va);
+        if (c + 64 < cols) m = vmax(vb, m);
+      }
+    } else if (variant == 3) {
+      for (int c = 0; c < cols; c += 128) {
+        uint32_t va[64], vb[64];
+        ld64(t0 + c, va);
+        if (c + 64 < cols) ld64(t0 + c + 64, vb);
+        tmem_ld_wait();
+        m = vmax(va, m);
+        if (c + 64 < cols) m = vmax(vb, m);
+      }
+    } else if (variant == 4) {
+      uint32_t va[32], vb[32], vc[32], vd[32];
+      for (int c = 0; c < cols; c += 128) {
+        tmem_ld32(t0 + c, va);
+        if (c + 32 < cols) tmem_ld32(t0 + c + 32, vb);
+        if (c + 64 < cols) tmem_ld32(t0 + c + 64, vc);
+        if (c + 96 < cols) tmem_ld32(t0 + c + 96, vd);
+        tmem_ld_wait();
+        m = vmax(va, m);
+        if (c + 32 < cols) m = vmax(vb, m);
+        if (c + 64 < cols) m = vmax(vc, m);
+        if (c + 96 < cols) m = vmax(vd, m);
+      }
+    } else {
+      for (int c = 0; c < cols; c += 16) {
+        uint32_t v[16];
+        tmem_ld16(t0 + c, v);
+        tmem_ld_wait();
+        m = vmax(v, m);
+      }
+    }
+  }
+  const long long c1 = clock64();
+  out[blockIdx.x * blockDim.x + threadIdx.x] = m;
+  if (threadIdx.x == 0) cycles[blockIdx.x] = c1 - c0;
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 0) tmem_dealloc<1>(tmem, 512);
+}
+
+static int run_drain(int warps, int variant) {
+  float* out;
+  long long* c;
+  const int blocks = 148, reps = 200;
+  CK(cudaMalloc(&out, sizeof(float) * blocks * 256));
+  CK(cudaMalloc(&c, 8 * blocks));
+  drain_kernel<<<blocks, warps * 32>>>(variant, reps, out, c);
+  CK(cudaGetLastError());
+  CK(cudaDeviceSynchronize());
+  drain_kernel<<<blocks, warps * 32>>>(variant, reps, out, c);
+  CK(cudaDeviceSynchronize());
+  std::vector<long long> h(blocks);
+  CK(cudaMemcpy(h.data(), c, 8 * blocks, cudaMemcpyDeviceToHost));
+  double avg = 0;
+  for (long long v : h) avg += double(v) / blocks;
+  const double per = avg / reps;
+  printf("drain warps=%d variant=%d: %.0f cycles per 128 KB (128 lanes x 256 columns) = %.1f B/clk per SM\n", warps, variant,
+         per, 131072.0 / per);
+  return 0;
+}
+
 int main(int argc, char** argv) {
   if (argc < 2) return 1;
   cudaDeviceProp prop;
@@ -320,6 +456,7 @@ int main(int argc, char** argv) {
   if (!strcmp(argv[1], "1cta")) return run_gemm(1, argc > 2 ? atoi(argv[2]) : 0);
   if (!strcmp(argv[1], "2cta")) return run_gemm(2, argc > 2 ? atoi(argv[2]) : 0);
   if (!strcmp(argv[1], "redux")) return run_redux();
+  if (!strcmp(argv[1], "drain")) return run_drain(atoi(argv[2]), atoi(argv[3]));
   if (!strcmp(argv[1], "rate")) return run_rate(atoi(argv[2]), atoi(argv[3]), atoi(argv[4]), atoi(argv[5]));
   return 1;
 }
