@@ -103,7 +103,8 @@ struct TcParams {
   float* out;             // SEGMAX: [num_dst, n] pre-filled with -FLT_MAX;  STORE: [num_rows, ldo]
   int ldo;
   int act;                // STORE: 0 linear, 1 relu
-  const float* residual;  // STORE: optional [num_rows, n]
+  const float* residual;  // STORE: optional [num_rows, ldr]
+  int ldr;                //        its row stride (0 = n)
   int* err;
   int64_t num_pair_tiles;
   unsigned long long* trace;   // optional (PG_TC_TRACE): [role 0..7][slot 0..127][3] globaltimer ns, cluster 0 only
@@ -313,7 +314,7 @@ __device__ __forceinline__ void epi_chunk_store(const TcParams& p, uint32_t tadd
   tmem_ld_wait();
   if (!row_ok) return;
   float* o = p.out + row * p.ldo + c_out;
-  const float* res = p.residual ? p.residual + row * p.n + c_out : nullptr;
+  const float* res = p.residual ? p.residual + row * (p.ldr ? p.ldr : p.n) + c_out : nullptr;
   const bool vec = ((p.n & 3) == 0) && ((p.ldo & 3) == 0);
 #pragma unroll
   for (int j4 = 0; j4 < 16; j4 += 4) {
@@ -1334,7 +1335,14 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kSegThreads, 1) seg_
       constexpr uint64_t kHalfB = uint64_t((8u * 256u) >> 4);   // rows 64.. of a stage: 8 row groups of 256 bytes
       const uint32_t w_tm0 = tmem_u + p.tm_w_col;
       const bool has2 = p.n2 > 0;
-      const int sa = min(p.ks, nst - 1);        // k-steps issued in the three-pass prologue of a tile
+      // Measured (profiles/r2_seg_prologue_depth.txt): the stages of the prologue stay pinned until pass 3 releases them,
+      // and with 12 of the 13 ring stages pinned the producers stood still for ~4.5 us per tile and then delivered the next
+      // tile's first stages one by one (1.69 ms per launch; no split at all: 1.53 ms).  Six stages cover the second half
+      // of the drain (6 x ~100 ns of half-a MMAs) and leave the producers seven: 1.43 ms.
+#ifndef PG_SEG_SA
+#define PG_SEG_SA 6
+#endif
+      const int sa = min(min(p.ks, nst - 1), PG_SEG_SA);   // k-steps issued in the three-pass prologue of a tile
       uint32_t tile_iter = 0, stage = 0, phase = 0;
 #ifdef PG_LAB
       uint32_t it = 0;
@@ -1352,21 +1360,30 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kSegThreads, 1) seg_
           tc_fence_after();
         }
         {
+          // all `sa` stages first (a ready barrier costs one probe; interleaving a probe with every three small MMAs
+          // made this pass MMA-warp-issue bound: ~250 ns per k-step for 55 ns of tensor work, so that pass 2 started
+          // 2 us after the half-a drain had finished), then the MMAs back to back
           uint32_t st = stage, ph = phase;
-          uint64_t kb = 0;
-          for (int s = 0; s < sa; ++s, kb += 16) {
+          for (int s = 0; s < sa; ++s) {
             if (lane == 0) PG_TRACE(0, it + s, 0);
             mbar_wait(&sm.bar_full[st], ph);
             if (lane == 0) PG_TRACE(0, it + s, 1);
-            tc_fence_after();
-            const uint64_t h_hi = h_desc(st), h_lo = h_hi + uint64_t((kStageBytes / 2) >> 4);
-            if (has2 && elect_one()) {
-              mma_bf16<2>(d2, h_hi, w_hi2 + kb, idesc2, s > 0);
-              mma_bf16<2>(d2, h_lo, w_hi2 + kb, idesc2, true);
-              mma_bf16<2>(d2, h_hi, w_lo0 + kb + w2_off, idesc2, true);
-            }
-            __syncwarp();
             next_stage(st, ph);
+          }
+          tc_fence_after();
+          if (has2) {
+            st = stage;
+            uint64_t kb = 0;
+            for (int s = 0; s < sa; ++s, kb += 16) {
+              const uint64_t h_hi = h_desc(st), h_lo = h_hi + uint64_t((kStageBytes / 2) >> 4);
+              if (elect_one()) {
+                mma_bf16<2>(d2, h_hi, w_hi2 + kb, idesc2, s > 0);
+                mma_bf16<2>(d2, h_lo, w_hi2 + kb, idesc2, true);
+                mma_bf16<2>(d2, h_hi, w_lo0 + kb + w2_off, idesc2, true);
+              }
+              __syncwarp();
+              if (++st == uint32_t(nst)) st = 0;
+            }
           }
         }
         // ---- pass 2: D1 half a (needs the first half of the previous drain) ---------------------------------
@@ -2130,6 +2147,10 @@ struct PreparedFc {
   bool tc = false;
   TcShape t{};
   Temp img, bias_pad;
+  // a [k, n] weight whose resident image exceeds shared memory (k = 512: the ped pooling output layer) is applied
+  // as column blocks, each a tensor-core layer of its own writing its slice of the output row
+  std::vector<PreparedFc> blocks;
+  int col0 = 0;
 };
 
 int prepare_fc(PreparedFc& f, const float* w, int ld_src, const float* bias, int k, int n_src, int n, bool want_tc,
@@ -2143,6 +2164,22 @@ int prepare_fc(PreparedFc& f, const float* w, int ld_src, const float* bias, int
   f.t = tc_shape(k, n);
   // narrow / shallow layers (N < 8, K < 64: the 64->3, 64->4, 64->7 heads) stay on the fp32 FFMA kernel
   f.tc = want_tc && f.t.ok && (k & 3) == 0;
+  f.blocks.clear();
+  if (!f.tc && want_tc && pg_tc_available() && (k & 3) == 0 && n == n_src && n >= 64) {
+    // too large for one resident image: 2 or 4 column blocks (multiples of 16 columns)
+    for (int nb = 2; nb <= 4 && f.blocks.empty(); nb *= 2) {
+      const int w0 = ((n + nb - 1) / nb + 15) / 16 * 16;
+      if (!tc_shape(k, w0).ok) continue;
+      for (int c0 = 0; c0 < n; c0 += w0) {
+        f.blocks.emplace_back();
+        PreparedFc& b = f.blocks.back();
+        const int wn = std::min(w0, n - c0);
+        if (int rc = prepare_fc(b, w + c0, ld_src, bias + c0, k, wn, wn, true, s)) return rc;
+        b.col0 = c0;
+        if (!b.tc) { f.blocks.clear(); break; }
+      }
+    }
+  }
   if (!f.tc) return PG_OK;
   PG_CUDA_OK(f.bias_pad.alloc(sizeof(float) * f.t.np, s));
   pad_rows_kernel<<<2, 256, 0, s>>>(bias, 1, n_src, f.t.np, f.bias_pad.as<float>());
@@ -2185,6 +2222,22 @@ int launch_row_gemm(TcParams& p, const TcShape& t, int n, const uint8_t* img, co
 int apply_fc(const PreparedFc& f, const float* x, int64_t m, int act, const float* residual, float* out, int ldo,
              cudaStream_t s) {
   if (m == 0) return PG_OK;
+  if (!f.tc && !f.blocks.empty()) {
+    for (const PreparedFc& b : f.blocks) {
+      TcParams p{};
+      p.P = x;
+      p.ldp = b.k;
+      p.k_real = b.k;
+      p.num_rows = m;
+      p.out = out + b.col0;
+      p.ldo = ldo;
+      p.act = act;
+      p.residual = residual ? residual + b.col0 : nullptr;
+      p.ldr = f.n;
+      if (int rc = launch_row_gemm<PROD_ROWS, EPI_STORE>(p, b.t, b.n, b.img.as<uint8_t>(), b.bias_pad.as<float>(), s)) return rc;
+    }
+    return PG_OK;
+  }
   if (!f.tc) {
     PG_REQUIRE(f.ld_src == f.n_src, "FFMA dense layer needs a contiguous weight matrix");
     PG_REQUIRE(f.n == f.n_src || ldo == f.n, "FFMA dense layer: padded width %d needs ldo == n", f.n);

@@ -62,7 +62,7 @@ def test_fully_connected_vs_oracle(precision):
     tol = 1e-4 if precision == 'fp32' else 3e-4
     dense0 = _lib.tc_launch_count(1)
     for m, k, n in ((1, 1, 1), (257, 300, 300), (1000, 303, 300), (77, 64, 3), (513, 4, 32), (130, 512, 256),
-                    (64, 300, 7), (255, 256, 256), (256, 300, 64), (4099, 300, 320), (33, 128, 300)):
+                    (64, 300, 7), (255, 256, 256), (256, 300, 64), (4099, 300, 320), (33, 128, 300), (700, 512, 300)):
         x = rng.standard_normal((m, k)).astype(np.float32)
         w = (rng.standard_normal((k, n)) / np.sqrt(k)).astype(np.float32)
         b = rng.standard_normal(n).astype(np.float32)
@@ -79,8 +79,9 @@ def test_fully_connected_vs_oracle(precision):
                 assert got.shape == want.shape and np.abs(got - want).max() < tol, (m, k, n, relu)
     if precision == 'bf16x3':
         # (257,300,300), (255,256,256), (256,300,64), (33,128,300) x 4 bias/residual combinations; the others are
-        # K % 4 != 0, K < 64, N < 8 or too wide for resident weights and take the FFMA kernel
-        assert _lib.tc_launch_count(1) - dense0 >= 4 * 4
+        # K % 4 != 0, K < 64 or N < 8 and take the FFMA kernel; (130,512,256) and (700,512,300) exceed one resident
+        # weight image and run as two column blocks (2 launches per call)
+        assert _lib.tc_launch_count(1) - dense0 >= 4 * 4 + 2 * 4 * 2
     pointgnn_b200.set_precision('fp32')
 
 
