@@ -888,11 +888,12 @@ __device__ __forceinline__ void segmax_prepare(const TcParams& p, const int (&id
 template <int kBlocks>
 __device__ __forceinline__ void segmax_d1_transposed(const TcParams& p, uint32_t tmem, uint32_t d1_col, uint32_t rank,
                                                      int quarter, int lane, int blk0, const SegRuns<kBlocks>& runs,
-                                                     int f0 = 0) {
+                                                     float bias_f, int f0 = 0) {
+  // bias_f = bias of this thread's feature, loaded ONCE per kernel by the caller (a global load per call sat on the
+  // drain's critical path: 21 % of the half-a drain's stall samples were the first flush waiting for it)
   const uint32_t lane_base = uint32_t(quarter * 32) << 16;
   const int f = f0 + int(rank) * 128 + quarter * 32 + lane;   // f0: first output feature of this M = 256 block
   const bool f_ok = f < p.n;
-  const float bias_f = f_ok ? __ldg(p.bias + f) : 0.0f;
   auto flush = [&](int cur, float m) {
     if (cur >= 0 && f_ok && m > -FLT_MAX)
       atomicMax(reinterpret_cast<int*>(p.out + int64_t(cur) * p.n + f), __float_as_int(fmaxf(m + bias_f, 0.0f)));
@@ -1484,6 +1485,8 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kSegThreads, 1) seg_
     // tile (rows 0..63 of CTA 0 and of CTA 1), half b = edges 64..127 and 192..255; d2 = destination of the edge in
     // this thread's D2 lane.  Loaded one tile ahead (while D2 of the previous tile is drained).
     int ids_a[4], ids_b[4], d2 = -1;
+    const int f_mine = int(rank) * 128 + quarter * 32 + lane;
+    const float bias_mine = f_mine < p.n ? __ldg(p.bias + f_mine) : 0.0f;   // this thread's D1 feature, once per kernel
     auto load_ids = [&](int64_t tile) {
 #pragma unroll
       for (int c = 0; c < 4; ++c) {
@@ -1506,11 +1509,11 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kSegThreads, 1) seg_
       mbar_wait(sm.bar_tmem_full, tile_iter & 1u);
       if (warp == kSegEpiWarp0 && lane == 0) PG_TRACE(3 + 2 * rank, tile_iter, 1);
       tc_fence_after();
-      segmax_d1_transposed<4>(p, tmem, 0u, rank, quarter, lane, 0, runs_a);
+      segmax_d1_transposed<4>(p, tmem, 0u, rank, quarter, lane, 0, runs_a, bias_mine);
       tc_fence_before();
       __syncwarp();
       if (lane == 0) mbar_arrive_cluster_relaxed(&sm.bar_d1_empty[0], 0);
-      segmax_d1_transposed<4>(p, tmem, 0u, rank, quarter, lane, 4, runs_b);
+      segmax_d1_transposed<4>(p, tmem, 0u, rank, quarter, lane, 4, runs_b, bias_mine);
       tc_fence_before();
       __syncwarp();
       if (lane == 0) mbar_arrive_cluster_relaxed(&sm.bar_d1_empty[1], 0);
@@ -1838,6 +1841,8 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kChainThreads, 1) ml
     const float* w = sm.first;            // [4][k0]
     const float* b = sm.first + 4 * k0;   // [k0]
     const uint32_t d_last = cp.ph[P - 1].d_col;
+    const int f_mine = int(rank) * 128 + quarter * 32 + lane;
+    const float bias_mine = (!store && f_mine < p.n) ? __ldg(p.bias + f_mine) : 0.0f;
     auto produce = [&](int64_t tile, uint32_t tile_iter) {
       const int64_t row = tile * 256 + int64_t(rank) * kTileRows + r;
       int sidx = 0, didx = 0;
@@ -1881,7 +1886,7 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kChainThreads, 1) ml
       segmax_prepare<8>(p, ids, lane, runs);
       mbar_wait(&sm.bar_d_full[P - 1], tile_iter & 1u);
       tc_fence_after();
-      segmax_d1_transposed<8>(p, tmem, d_last, rank, quarter, lane, 0, runs);
+      segmax_d1_transposed<8>(p, tmem, d_last, rank, quarter, lane, 0, runs, bias_mine);
       if (p.n2 > 0)
         segmax_d2_rowmajor(p, tmem, d_last + 256u, quarter, lane,
                            segmax_d2_load(p, tile * 256 + int64_t(rank) * kTileRows + quarter * 32 + lane));
@@ -2078,6 +2083,8 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kLastThreads, 1) poo
     // =================================== epilogue warps =======================================
     cluster_sync();   // [sync A]
     const int quarter = warp;
+    const int f_mine = half * 256 + int(rank) * 128 + quarter * 32 + lane;
+    const float bias_mine = f_mine < p.n ? __ldg(p.bias + f_mine) : 0.0f;
     uint32_t tile_iter = 0;
     for (int64_t tile = tile0; tile < p.num_pair_tiles; tile += tstride, ++tile_iter) {
       const uint32_t buf = tile_iter & 1u, use = tile_iter >> 1;
@@ -2087,7 +2094,7 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kLastThreads, 1) poo
       segmax_prepare<8>(p, ids, lane, runs);
       mbar_wait(&sm.bar_d_full[buf], use & 1u);
       tc_fence_after();
-      segmax_d1_transposed<8>(p, tmem, buf * 256u, rank, quarter, lane, 0, runs, half * 256);
+      segmax_d1_transposed<8>(p, tmem, buf * 256u, rank, quarter, lane, 0, runs, bias_mine, half * 256);
       tc_fence_before();
       __syncwarp();
       if (lane == 0) mbar_arrive_cluster_relaxed(&sm.bar_d_empty[buf], 0);
