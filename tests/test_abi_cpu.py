@@ -120,3 +120,13 @@ def test_training_only_paths_raise():
         pytest.skip('argument checks below are reached before any device work only on CPU boxes')
     with pytest.raises((NotImplementedError, RuntimeError)):
         graph_gen.gen_multi_level_local_graph_v3(np.zeros((4, 3), np.float32), 0.8, [], downsample_method='random')
+
+
+def test_prefetcher_has_no_cpu_path():
+    """utils/prefetch.py overlaps GPU work with GPU work; without a CUDA device it must refuse, not fall back."""
+    import torch
+    if torch.cuda.is_available():
+        pytest.skip('CUDA present')
+    from pointgnn_b200.utils.prefetch import GraphPrefetcher
+    with pytest.raises(RuntimeError):
+        GraphPrefetcher(lambda *a, **k: None, {})
