@@ -1106,8 +1106,10 @@ __device__ __forceinline__ void seg_producer(const TcParams& p, const SegSmem& s
                                              int64_t cluster_id, int64_t num_clusters) {
   const int g = pt >> 7, wg = (pt >> 5) & 3;
   const int r = pt & 127;                     // the row whose per-tile context this thread computes
+// Measured (profiles/r2_seg_prologue_depth.txt): the conflict-free store mapping (1) is 1.2 % SLOWER than the natural one
+// (0) - the 2-way store conflict costs less than the changed order of the gather's lanes.  Default: natural.
 #ifndef PG_SEG_LANEMAP
-#define PG_SEG_LANEMAP 1
+#define PG_SEG_LANEMAP 0
 #endif
 #ifndef PG_SEG_PREFETCH
 #define PG_SEG_PREFETCH 2      // own-iterations between the request of a P slice and its use (register buffers)

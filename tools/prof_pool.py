@@ -15,8 +15,9 @@ from pointgnn_b200.models import graph_gen  # noqa: E402
 frames = int(sys.argv[1]) if len(sys.argv) > 1 else 8
 reps = int(sys.argv[2]) if len(sys.argv) > 2 else 3
 prec = int(sys.argv[3]) if len(sys.argv) > 3 else 1
-cfg = json.load(open(os.path.join(ROOT, 'tests/golden/config_car_auto_T3_train.json')))
-w = dict(np.load(os.path.join(ROOT, 'tests/golden/weights_car_auto_T3_train.npz')))
+name = sys.argv[4] if len(sys.argv) > 4 else 'car_auto_T3_train'       # or ped_cyl_auto_T3_trainval (chain store mode + pool_last)
+cfg = json.load(open(os.path.join(ROOT, 'tests/golden/config_%s.json' % name)))
+w = dict(np.load(os.path.join(ROOT, 'tests/golden/weights_%s.npz' % name)))
 fr = [synth.lidar_frame(i, 20000) for i in range(frames)]
 pts = torch.from_numpy(np.vstack([f[0] for f in fr])).cuda()
 inten = torch.from_numpy(np.vstack([f[1] for f in fr])).cuda()
@@ -24,7 +25,7 @@ fp = torch.arange(frames + 1, dtype=torch.int32, device='cuda') * 20000
 coords, kp, edges = graph_gen.gen_multi_level_local_graph_v3(pts, frame_ptr=fp, **cfg['runtime_graph_gen_kwargs'])
 k = coords[1].shape[0]
 s = 'layer1/extract_vertex_features/fully_connected'
-names = [s, s + '_1', s + '_2', s + '_3']
+names = [s] + [s + '_%d' % i for i in range(1, 8) if (s + '_%d/weights' % i) in w]
 ws = [torch.from_numpy(w[n + '/weights']).cuda() for n in names]
 bs = [torch.from_numpy(w[n + '/biases']).cuda() for n in names]
 src, dst = edges[0][:, 0].contiguous(), edges[0][:, 1].contiguous()
