@@ -228,6 +228,17 @@ PG_API int pg_cap_neighbors(const int32_t* row_ptr, const int32_t* src, int64_t 
 PG_API int pg_scatter_max(const float* features, const int32_t* centers, int64_t num_edges,
                    int32_t num_channels, int64_t num_centers, float* out, void* stream);
 
+/*
+ * graph_scatter_sum_fn / graph_scatter_mean_fn (gnn.py:111-119) = tf.math.unsorted_segment_sum / unsorted_segment_mean
+ * (the aggregation plug-ins no shipped config selects): out[k,c] = sum (mean) over edges e with centers[e]==k of
+ * features[e,c]; an empty segment gives 0 for both (the mean divides by max(count, 1)).  fp32 accumulation, partial sums
+ * combined with atomics (order not fixed, as in TF's GPU kernel).  Ids outside [0, num_centers) are dropped, as TF does.
+ */
+PG_API int pg_scatter_sum(const float* features, const int32_t* centers, int64_t num_edges,
+                   int32_t num_channels, int64_t num_centers, float* out, void* stream);
+PG_API int pg_scatter_mean(const float* features, const int32_t* centers, int64_t num_edges,
+                    int32_t num_channels, int64_t num_centers, float* out, void* stream);
+
 /* tf.gather(params, indices) for [R,C] fp32 rows (gnn.py:256-262,338-348). */
 PG_API int pg_gather_rows(const float* params, int64_t num_rows, int32_t num_channels,
                    const int32_t* indices, int64_t num_indices, float* out, void* stream);

@@ -51,6 +51,8 @@ SIGNATURES = {
     'pg_cap_neighbors': (ctypes.c_int, [c_i32p, c_i32p, c_i64, c_i32, ctypes.c_uint32, c_i32p, c_i32p, c_i32p, c_i64,
                                         ctypes.POINTER(c_i64), ctypes.c_void_p]),
     'pg_scatter_max': (ctypes.c_int, [c_f32p, c_i32p, c_i64, c_i32, c_i64, c_f32p, ctypes.c_void_p]),
+    'pg_scatter_sum': (ctypes.c_int, [c_f32p, c_i32p, c_i64, c_i32, c_i64, c_f32p, ctypes.c_void_p]),
+    'pg_scatter_mean': (ctypes.c_int, [c_f32p, c_i32p, c_i64, c_i32, c_i64, c_f32p, ctypes.c_void_p]),
     'pg_gather_rows': (ctypes.c_int, [c_f32p, c_i64, c_i32, c_i32p, c_i64, c_f32p, ctypes.c_void_p]),
     'pg_fully_connected': (ctypes.c_int, [c_f32p, c_i64, c_i32, c_f32p, c_f32p, c_i32, c_i32, c_f32p, c_f32p,
                                           c_i32, ctypes.c_void_p]),
@@ -349,6 +351,16 @@ def scatter_max(features, centers, num_centers):
     out = torch.empty((int(num_centers), c), dtype=torch.float32, device=features.device)
     _check(lib.pg_scatter_max(_ptr(features, torch.float32, 'features'), _ptr(centers, torch.int32, 'centers'), e, c,
                               int(num_centers), _ptr(out, torch.float32, 'out'), _stream()))
+    return out
+
+
+def scatter_sum(features, centers, num_centers, mean=False):
+    lib = load()
+    e, c = features.shape
+    out = torch.empty((int(num_centers), c), dtype=torch.float32, device=features.device)
+    fn = lib.pg_scatter_mean if mean else lib.pg_scatter_sum
+    _check(fn(_ptr(features, torch.float32, 'features'), _ptr(centers, torch.int32, 'centers'), e, c,
+              int(num_centers), _ptr(out, torch.float32, 'out'), _stream()))
     return out
 
 

@@ -116,6 +116,48 @@ __global__ void __launch_bounds__(256) scatter_max_vec4_kernel(const float4* __r
   }
 }
 
+// ---- graph_scatter_sum_fn / graph_scatter_mean_fn (gnn.py:111-119): tf.math.unsorted_segment_sum / _mean ----------
+// Same streaming structure as the max: a thread walks a chunk of consecutive edges with a running partial sum per
+// destination run and flushes it with one atomicAdd per (run, channel); sorted or unsorted ids both work (unsorted ids
+// just flush every edge).  fp32 accumulation; the order of the partial sums is not fixed (atomics), as TF's GPU kernel.
+__global__ void scatter_sum_kernel(const float* __restrict__ feat, const int32_t* __restrict__ centers, int64_t num_edges,
+                                   int num_channels, int64_t num_centers, float* __restrict__ out,
+                                   float* __restrict__ count) {
+  const int c = blockIdx.x * blockDim.x + threadIdx.x;
+  if (c >= num_channels) return;
+  const int64_t num_chunks = (num_edges + kScatterChunk - 1) / kScatterChunk;
+  for (int64_t chunk = blockIdx.y; chunk < num_chunks; chunk += gridDim.y) {
+    const int64_t e0 = chunk * kScatterChunk, e1 = min(e0 + kScatterChunk, num_edges);
+    int cur = -1;
+    float acc = 0.0f, n = 0.0f;
+    for (int64_t e = e0; e < e1; ++e) {
+      const int d = __ldg(centers + e);
+      if (d != cur) {
+        if (cur >= 0 && cur < num_centers) {
+          atomicAdd(out + int64_t(cur) * num_channels + c, acc);
+          if (count != nullptr && c == 0) atomicAdd(count + cur, n);
+        }
+        cur = d;
+        acc = 0.0f;
+        n = 0.0f;
+      }
+      acc += __ldg(feat + e * num_channels + c);
+      n += 1.0f;
+    }
+    if (cur >= 0 && cur < num_centers) {
+      atomicAdd(out + int64_t(cur) * num_channels + c, acc);
+      if (count != nullptr && c == 0) atomicAdd(count + cur, n);
+    }
+  }
+}
+
+__global__ void divide_rows_kernel(float* __restrict__ out, const float* __restrict__ count, int64_t num_centers,
+                                   int num_channels) {
+  const int64_t total = num_centers * num_channels;
+  for (int64_t i = int64_t(blockIdx.x) * blockDim.x + threadIdx.x; i < total; i += int64_t(gridDim.x) * blockDim.x)
+    out[i] = out[i] / fmaxf(count[i / num_channels], 1.0f);      // unsorted_segment_mean: empty segment -> 0
+}
+
 __global__ void gather_rows_kernel(const float* __restrict__ params, int64_t num_rows, int num_channels,
                                    const int32_t* __restrict__ indices, int64_t num_indices,
                                    float* __restrict__ out, int* __restrict__ err) {
@@ -251,6 +293,45 @@ extern "C" int pg_scatter_max(const float* features, const int32_t* centers, int
   scatter_max_kernel<<<grid, threads, 0, s>>>(features, centers, num_edges, num_channels, num_centers, out);
   PG_LAUNCH_CHECK();
   return PG_OK;
+}
+
+static int scatter_sum_impl(const float* features, const int32_t* centers, int64_t num_edges, int32_t num_channels,
+                            int64_t num_centers, float* out, bool mean, cudaStream_t s) {
+  PG_REQUIRE(out != nullptr || num_centers == 0, "pg_scatter_sum: out is null");
+  PG_REQUIRE(num_channels >= 1 && num_edges >= 0 && num_centers >= 0, "pg_scatter_sum: bad sizes");
+  if (num_centers == 0) return PG_OK;
+  PG_CUDA_OK(cudaMemsetAsync(out, 0, sizeof(float) * num_centers * num_channels, s));
+  if (num_edges == 0) return PG_OK;
+  PG_REQUIRE(features && centers, "pg_scatter_sum: null input");
+  Temp count;
+  if (mean) {
+    PG_CUDA_OK(count.alloc(sizeof(float) * num_centers, s));
+    PG_CUDA_OK(cudaMemsetAsync(count.ptr, 0, sizeof(float) * num_centers, s));
+  }
+  const int64_t chunks = ceil_div(num_edges, kScatterChunk);
+  const int threads = num_channels >= 256 ? 256 : (num_channels >= 128 ? 128 : (num_channels >= 64 ? 64 : 32));
+  dim3 grid(ceil_div(num_channels, threads), int(std::min<int64_t>(chunks, 65535)));
+  scatter_sum_kernel<<<grid, threads, 0, s>>>(features, centers, num_edges, num_channels, num_centers, out,
+                                              mean ? count.as<float>() : nullptr);
+  PG_LAUNCH_CHECK();
+  if (mean) {
+    const int blocks = int(std::min<int64_t>(ceil_div(num_centers * num_channels, 256), int64_t(num_sms()) * 8));
+    divide_rows_kernel<<<blocks, 256, 0, s>>>(out, count.as<float>(), num_centers, num_channels);
+    PG_LAUNCH_CHECK();
+  }
+  return PG_OK;
+}
+
+extern "C" int pg_scatter_sum(const float* features, const int32_t* centers, int64_t num_edges, int32_t num_channels,
+                              int64_t num_centers, float* out, void* stream) {
+  return scatter_sum_impl(features, centers, num_edges, num_channels, num_centers, out, false,
+                          static_cast<cudaStream_t>(stream));
+}
+
+extern "C" int pg_scatter_mean(const float* features, const int32_t* centers, int64_t num_edges, int32_t num_channels,
+                               int64_t num_centers, float* out, void* stream) {
+  return scatter_sum_impl(features, centers, num_edges, num_channels, num_centers, out, true,
+                          static_cast<cudaStream_t>(stream));
 }
 
 extern "C" int pg_gather_rows(const float* params, int64_t num_rows, int32_t num_channels, const int32_t* indices,

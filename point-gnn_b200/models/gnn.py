@@ -186,13 +186,16 @@ def graph_scatter_max_fn(point_features, point_centers, num_centers):
 
 
 def graph_scatter_sum_fn(point_features, point_centers, num_centers):
-    """gnn.py:111-114 - not used by any shipped config."""
-    raise NotImplementedError('scatter_sum aggregation is unused by the shipped configs')
+    """gnn.py:111-114 (tf.math.unsorted_segment_sum; empty segment -> 0).  No shipped config selects it; as an
+    ``aggregation_fn`` plug-in it runs the layer op by op (the fused kernels implement the max)."""
+    centers = point_centers.reshape(-1).to(torch.int32).contiguous()
+    return _lib.scatter_sum(point_features.contiguous(), centers, int(num_centers))
 
 
 def graph_scatter_mean_fn(point_features, point_centers, num_centers):
-    """gnn.py:116-119 - not used by any shipped config."""
-    raise NotImplementedError('scatter_mean aggregation is unused by the shipped configs')
+    """gnn.py:116-119 (tf.math.unsorted_segment_mean; empty segment -> 0)."""
+    centers = point_centers.reshape(-1).to(torch.int32).contiguous()
+    return _lib.scatter_sum(point_features.contiguous(), centers, int(num_centers), mean=True)
 
 
 def _i32(t):

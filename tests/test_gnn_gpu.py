@@ -492,3 +492,43 @@ def test_tc_pool_chain_shapes_and_tails(dims):
         scale = max(1.0, float(np.abs(want[~empty]).max())) if (~empty).any() else 1.0
         err = np.abs(got - want)[~empty].max() if (~empty).any() else 0.0
         assert err < 1e-3 * scale, (dims, case, err, scale)
+
+
+def test_scatter_sum_and_mean_vs_numpy(car):
+    """graph_scatter_sum_fn / graph_scatter_mean_fn (gnn.py:111-119: unsorted_segment_sum / _mean; no shipped config
+    selects them) against NumPy, sorted and unsorted ids, empty segments -> 0; and as the aggregation plug-in of a
+    pooling layer (op-by-op path) against the same composition in NumPy."""
+    from pointgnn_b200.models import gnn
+    rng = np.random.default_rng(3)
+    for e, k, c, sort in ((1, 3, 1, True), (5000, 300, 300, True), (7001, 41, 19, False), (260, 9000, 64, True)):
+        feats = rng.standard_normal((e, c)).astype(np.float32)
+        ids = rng.integers(0, k, e)
+        if sort:
+            ids = np.sort(ids)
+        want = np.zeros((k, c), np.float64)
+        np.add.at(want, ids, feats.astype(np.float64))
+        cnt = np.bincount(ids, minlength=k).astype(np.float64)
+        got = gnn.graph_scatter_sum_fn(_cuda(feats), _cuda(ids.astype(np.int32)), k).cpu().numpy()
+        assert got.shape == (k, c) and np.abs(got - want).max() < 1e-4 * max(1.0, np.abs(want).max())
+        gotm = gnn.graph_scatter_mean_fn(_cuda(feats), _cuda(ids.astype(np.int32)), k).cpu().numpy()
+        wantm = want / np.maximum(cnt, 1.0)[:, None]
+        assert np.abs(gotm - wantm).max() < 1e-5 * max(1.0, np.abs(wantm).max())
+        assert np.all(gotm[cnt == 0] == 0.0) and np.all(got[cnt == 0] == 0.0)
+    # as a layer plug-in
+    lc, feats, xyz, kp, ed = _edge_case(car, 'layer1', 'pool')
+    store = gnn.VariableStore(car.weights)
+    with gnn.variable_session(store), gnn.variable_scope('layer1'):
+        got = gnn.PointSetPooling(aggregation_fn=gnn.graph_scatter_mean_fn).apply_regular(
+            _cuda(feats), _cuda(xyz), _cuda(kp, torch.int32), _cuda(ed, torch.int32), **lc['kwargs']).cpu().numpy()
+    w = car.weights
+    src, dst = ed[:, 0], ed[:, 1]
+    h = np.concatenate([feats[src], xyz[src] - xyz[kp[dst, 0]]], axis=1).astype(np.float64)
+    names = ['layer1/extract_vertex_features/fully_connected' + s for s in ('', '_1', '_2', '_3')]
+    for n in names:
+        h = np.maximum(h @ w[n + '/weights'] + w[n + '/biases'], 0)
+    agg = np.zeros((len(kp), h.shape[1]))
+    np.add.at(agg, dst, h)
+    agg /= np.maximum(np.bincount(dst, minlength=len(kp)), 1)[:, None]
+    for n in ('layer1/combined_features/fully_connected', 'layer1/combined_features/fully_connected_1'):
+        agg = np.maximum(agg @ w[n + '/weights'] + w[n + '/biases'], 0)
+    assert np.abs(got - agg).max() < 1e-3 * max(1.0, np.abs(agg).max())
