@@ -1592,7 +1592,10 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kSegThreads, 1) seg_
 // One ring of kChainStages A stages carries the k-steps of ALL phases in MMA issue order
 // (iteration it = tile * its_per_tile + phase offset + k-step); its writers are the producer
 // warps (phase 0) or the mid-stage warps of one chunk parity (4 warps x 2 CTAs = 8 arrivals either way).
-constexpr int kChainStages = 4;      // power of two: stage = it & 3, parity = (it >> 2) & 1
+#ifndef PG_CHAIN_STAGES
+#define PG_CHAIN_STAGES 4
+#endif
+constexpr int kChainStages = PG_CHAIN_STAGES;      // power of two: stage = it & (n - 1), parity = (it / n) & 1
 constexpr int kChainMaxPhases = 4;
 constexpr int kChainProdWarps = 4;
 constexpr int kChainThreads = (kEpiWarps + 1 + kChainProdWarps) * 32;   // 416

@@ -10,6 +10,8 @@ ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 sys.path.insert(0, ROOT)
 from oracle import synth  # noqa: E402
 from pointgnn_b200 import _lib  # noqa: E402
+if os.environ.get('PG_LIB_VARIANT'):      # experiment builds (tools/build_variant.sh NAME -DFLAG...): lab/<NAME>.so
+    _lib.LIB_PATH = os.path.join(ROOT, 'lab', os.environ['PG_LIB_VARIANT'] + '.so')
 from pointgnn_b200.models import graph_gen  # noqa: E402
 
 frames = int(sys.argv[1]) if len(sys.argv) > 1 else 8
@@ -31,15 +33,24 @@ bs = [torch.from_numpy(w[n + '/biases']).cuda() for n in names]
 src, dst = edges[0][:, 0].contiguous(), edges[0][:, 1].contiguous()
 kpi = kp[0].reshape(-1).contiguous()
 print('K', k, 'E0', src.numel())
+dims = [4] + [int(x.shape[1]) for x in ws]
+layer = _lib.PreparedLayer(_lib.PG_LAYER_EDGE_POOL, ws, bs, dims, prec)     # weights packed once, as the model does
+flop_per_edge = sum(2 * dims[i] * dims[i + 1] for i in range(len(dims) - 1))
+if prec == 1:
+    ref = _lib.PreparedLayer(_lib.PG_LAYER_EDGE_POOL, ws, bs, dims, 0).edge_mlp_max(inten, pts, pts, kpi, src, dst, k, trusted=True)
+    got = layer.edge_mlp_max(inten, pts, pts, kpi, src, dst, k, trusted=True)
+    print('max |tensor-core - fp32 FFMA| = %.3g (empty segments equal: %s)' % (
+        float((got - ref).abs()[ref > -1e30].max()), bool(((got < -1e30) == (ref < -1e30)).all())))
 for _ in range(2):
-    _lib.edge_mlp_max(0, inten, pts, pts, kpi, src, dst, k, ws, bs, precision=prec)
+    layer.edge_mlp_max(inten, pts, pts, kpi, src, dst, k, trusted=True)
 torch.cuda.synchronize()
 a = torch.cuda.Event(enable_timing=True)
 b = torch.cuda.Event(enable_timing=True)
 a.record()
 for _ in range(reps):
-    _lib.edge_mlp_max(0, inten, pts, pts, kpi, src, dst, k, ws, bs, precision=prec)
+    layer.edge_mlp_max(inten, pts, pts, kpi, src, dst, k, trusted=True)
 b.record()
 b.synchronize()
 ms = a.elapsed_time(b) / reps
-print('pool edge_mlp_max precision %d: %.3f ms per call, %.1f algorithmic TFLOP/s' % (prec, ms, src.numel() * 97536 / ms / 1e9))
+print('pool edge_mlp_max (prepared layer, %s) precision %d: %.3f ms per call, %.1f algorithmic TFLOP/s'
+      % ('x'.join(str(d) for d in dims), prec, ms, src.numel() * flop_per_edge / ms / 1e9))
