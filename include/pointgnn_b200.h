@@ -169,6 +169,18 @@ PG_API int pg_radius_graph(const float* points, const int32_t* point_frame_ptr, 
                     int32_t* out_dst, int64_t capacity, int64_t* out_num_edges_host, void* stream);
 
 /*
+ * pg_radius_graph with the per-axis `scale` argument of gen_disjointed_rnn_local_graph_v3 (graph_gen.py:203-206:
+ * points_xyz / np.array(scale), center_xyz / np.array(scale) - a float64 division of the float32 coordinates - before
+ * the ball tree is built).  scale_host = (host) [3] positive divisors, NULL = no scaling (= pg_radius_graph); the
+ * division is done in float64 inside the kernels, the predicate is evaluated on the quotients exactly as above.
+ */
+PG_API int pg_radius_graph_scaled(const float* points, const int32_t* point_frame_ptr, const float* centers,
+                           const int32_t* center_frame_ptr, int32_t num_frames, int64_t num_points,
+                           int64_t num_centers, double radius, const double* scale_host, int32_t* out_row_ptr,
+                           int32_t* out_src, int32_t* out_dst, int64_t capacity, int64_t* out_num_edges_host,
+                           void* stream);
+
+/*
  * gen_multi_level_local_graph_v3 (graph_gen.py:155-195) for the two-level structure of every shipped
  * config - level 0: original cloud -> keypoints of ONE voxel scale (radius0), level 1: those keypoints
  * -> themselves (radius1; equal consecutive scales, graph_gen.py:76-81) - as ONE call with ONE host

@@ -41,6 +41,9 @@ SIGNATURES = {
                                             ctypes.c_double, c_i32p, c_i64, c_i32p, c_i32p, ctypes.c_void_p]),
     'pg_radius_graph': (ctypes.c_int, [c_f32p, c_i32p, c_f32p, c_i32p, c_i32, c_i64, c_i64, ctypes.c_double,
                                        c_i32p, c_i32p, c_i32p, c_i64, ctypes.POINTER(c_i64), ctypes.c_void_p]),
+    'pg_radius_graph_scaled': (ctypes.c_int, [c_f32p, c_i32p, c_f32p, c_i32p, c_i32, c_i64, c_i64, ctypes.c_double,
+                                              ctypes.POINTER(ctypes.c_double), c_i32p, c_i32p, c_i32p, c_i64,
+                                              ctypes.POINTER(c_i64), ctypes.c_void_p]),
     'pg_multi_level_graph': (ctypes.c_int, [c_f32p, c_i32p, c_i32, c_i64, ctypes.POINTER(ctypes.c_double),
                                             ctypes.c_double, ctypes.c_double, c_i32p, c_i64, c_i32p, c_f32p,
                                             c_i32p, c_i32p, c_i32p, c_i64, c_i32p, c_i32p, c_i32p, c_i64,
@@ -246,24 +249,26 @@ def cap_neighbors(row_ptr, edges, num_neighbors, seed):
 _edge_capacity = {}
 
 
-def radius_graph(points, point_frame_ptr, centers, center_frame_ptr, radius):
-    """-> (row_ptr [K+1] int32, edges [2,E] int32 with row 0 = src, row 1 = dst)."""
+def radius_graph(points, point_frame_ptr, centers, center_frame_ptr, radius, scale=None):
+    """-> (row_ptr [K+1] int32, edges [2,E] int32 with row 0 = src, row 1 = dst).  scale: None or 3 positive
+    per-axis divisors (graph_gen.py:203-206, float64 division inside the kernels)."""
     lib = load()
+    sc = None if scale is None else (ctypes.c_double * 3)(*[float(v) for v in scale])
     p, k = points.shape[0], centers.shape[0]
     num_frames = point_frame_ptr.numel() - 1
     row_ptr = torch.empty(k + 1, dtype=torch.int32, device=points.device)
-    key = (points.device.index, float(radius))
+    key = (points.device.index, float(radius), None if scale is None else tuple(float(v) for v in scale))
     cap = max(_edge_capacity.get(key, 0), 64 * k, 1 << 16)
     e = c_i64(0)
     while True:
         buf = torch.empty((2, cap), dtype=torch.int32, device=points.device)
-        code = lib.pg_radius_graph(_ptr(points, torch.float32, 'points'),
-                                   _ptr(point_frame_ptr, torch.int32, 'point_frame_ptr'),
-                                   _ptr(centers, torch.float32, 'centers'),
-                                   _ptr(center_frame_ptr, torch.int32, 'center_frame_ptr'), num_frames, p, k,
-                                   float(radius), _ptr(row_ptr, torch.int32, 'row_ptr'),
-                                   ctypes.c_void_p(buf[0].data_ptr()), ctypes.c_void_p(buf[1].data_ptr()), cap,
-                                   ctypes.byref(e), _stream())
+        code = lib.pg_radius_graph_scaled(_ptr(points, torch.float32, 'points'),
+                                          _ptr(point_frame_ptr, torch.int32, 'point_frame_ptr'),
+                                          _ptr(centers, torch.float32, 'centers'),
+                                          _ptr(center_frame_ptr, torch.int32, 'center_frame_ptr'), num_frames, p, k,
+                                          float(radius), sc, _ptr(row_ptr, torch.int32, 'row_ptr'),
+                                          ctypes.c_void_p(buf[0].data_ptr()), ctypes.c_void_p(buf[1].data_ptr()), cap,
+                                          ctypes.byref(e), _stream())
         if code == PG_ERR_CAPACITY:
             cap = int(e.value * 1.25) + 1024
             continue

@@ -87,16 +87,25 @@ __global__ void frame_min_kernel(const float* __restrict__ xyz, const int32_t* _
 struct GridSpec {
   double cell[3];     // cell edge per axis
   double origin_off;  // origin = frame_min - cell * origin_off   (0.5 for Open3D voxels, 0 for radius grids)
+  // gen_disjointed_rnn_local_graph_v3's `scale` (graph_gen.py:203-206): every coordinate is DIVIDED by scale[axis] in
+  // float64 before anything else (points_xyz / np.array(scale) -> float64).  scaled == 0: coordinates as they are.
+  int scaled;
+  double scale[3];
 };
+
+// coordinate of axis a as the reference sees it: float32 value -> float64, divided by the scale if there is one
+__device__ __forceinline__ double coord(const GridSpec& g, float v, int a) {
+  return g.scaled ? __ddiv_rn(double(v), g.scale[a]) : double(v);
+}
 
 __device__ inline void cell_of(const GridSpec& g, const uint32_t* __restrict__ bounds, int f, float x,
                                float y, float z, long long* ix, long long* iy, long long* iz) {
-  const double ox = __dsub_rn(double(ordered_to_float(bounds[3 * f + 0])), __dmul_rn(g.cell[0], g.origin_off));
-  const double oy = __dsub_rn(double(ordered_to_float(bounds[3 * f + 1])), __dmul_rn(g.cell[1], g.origin_off));
-  const double oz = __dsub_rn(double(ordered_to_float(bounds[3 * f + 2])), __dmul_rn(g.cell[2], g.origin_off));
-  *ix = (long long)floor(__ddiv_rn(__dsub_rn(double(x), ox), g.cell[0]));
-  *iy = (long long)floor(__ddiv_rn(__dsub_rn(double(y), oy), g.cell[1]));
-  *iz = (long long)floor(__ddiv_rn(__dsub_rn(double(z), oz), g.cell[2]));
+  const double ox = __dsub_rn(coord(g, ordered_to_float(bounds[3 * f + 0]), 0), __dmul_rn(g.cell[0], g.origin_off));
+  const double oy = __dsub_rn(coord(g, ordered_to_float(bounds[3 * f + 1]), 1), __dmul_rn(g.cell[1], g.origin_off));
+  const double oz = __dsub_rn(coord(g, ordered_to_float(bounds[3 * f + 2]), 2), __dmul_rn(g.cell[2], g.origin_off));
+  *ix = (long long)floor(__ddiv_rn(__dsub_rn(coord(g, x, 0), ox), g.cell[0]));
+  *iy = (long long)floor(__ddiv_rn(__dsub_rn(coord(g, y, 1), oy), g.cell[1]));
+  *iz = (long long)floor(__ddiv_rn(__dsub_rn(coord(g, z, 2), oz), g.cell[2]));
 }
 
 // `n_valid` (optional, device): only rows [0, *n_valid) of the n-row buffer hold points (a point set whose size is
@@ -352,7 +361,7 @@ __global__ void __launch_bounds__(256) radius_query_kernel(
     atomicOr(err, kErrCenterPtr);
   const int f = find_frame(center_frame_ptr, num_frames, c);
   const float cxf = centers[3 * c], cyf = centers[3 * c + 1], czf = centers[3 * c + 2];
-  const double cx = double(cxf), cy = double(cyf), cz = double(czf);
+  const double cx = coord(spec, cxf, 0), cy = coord(spec, cyf, 1), cz = coord(spec, czf, 2);
   long long ix, iy, iz;
   cell_of(spec, bounds, f, cxf, cyf, czf, &ix, &iy, &iz);
   const long long x0 = max(ix - 1, 0ll), x1 = min(ix + 1, (long long)kAxisMax);
@@ -371,7 +380,13 @@ __global__ void __launch_bounds__(256) radius_query_kernel(
           int idx = 0;
           if (i < e) {
             const float4 p = g.pts[i];
-            hit = dist2_rn(cx, cy, cz, p.x, p.y, p.z) <= r2;
+            if (spec.scaled) {
+              const double dx = __dsub_rn(cx, coord(spec, p.x, 0)), dy = __dsub_rn(cy, coord(spec, p.y, 1));
+              const double dz = __dsub_rn(cz, coord(spec, p.z, 2));
+              hit = __dadd_rn(__dadd_rn(__dmul_rn(dx, dx), __dmul_rn(dy, dy)), __dmul_rn(dz, dz)) <= r2;
+            } else {
+              hit = dist2_rn(cx, cy, cz, p.x, p.y, p.z) <= r2;
+            }
             idx = __float_as_int(p.w);
           }
           const uint32_t m = __ballot_sync(0xffffffffu, hit);
@@ -660,15 +675,22 @@ int graph_error(int err) {
 
 struct RadiusPlan {
   BuiltGrid grid;
-  GridSpec spec;
+  GridSpec spec{};
   double r2;
 };
 
 int radius_prepare(const float* points, const int32_t* point_frame_ptr, int num_frames, int64_t num_points,
-                   double radius, cudaStream_t s, RadiusPlan* plan) {
+                   double radius, cudaStream_t s, RadiusPlan* plan, const double* scale_host = nullptr) {
   PG_REQUIRE(radius > 0.0, "radius must be positive");
+  plan->spec = GridSpec{};
   plan->spec.cell[0] = plan->spec.cell[1] = plan->spec.cell[2] = radius * kCellSlack;
   plan->spec.origin_off = 0.0;
+  plan->spec.scale[0] = plan->spec.scale[1] = plan->spec.scale[2] = 1.0;
+  if (scale_host != nullptr) {
+    PG_REQUIRE(scale_host[0] > 0 && scale_host[1] > 0 && scale_host[2] > 0, "scale must be positive");
+    plan->spec.scaled = 1;
+    for (int a = 0; a < 3; ++a) plan->spec.scale[a] = scale_host[a];
+  }
   plan->r2 = radius * radius;
   return build_grid(points, point_frame_ptr, num_frames, num_points, plan->spec, s, &plan->grid);
 }
@@ -685,7 +707,7 @@ extern "C" int pg_voxel_keypoints(const float* xyz, const int32_t* frame_ptr, in
   PG_REQUIRE(xyz && frame_ptr && voxel_size_host && out_keypoint_idx && out_kp_frame_ptr && out_num_keypoints_host,
              "pg_voxel_keypoints: null argument");
   PG_REQUIRE(voxel_size_host[0] > 0 && voxel_size_host[1] > 0 && voxel_size_host[2] > 0, "voxel size must be positive");
-  GridSpec spec;
+  GridSpec spec{};
   spec.cell[0] = voxel_size_host[0];
   spec.cell[1] = voxel_size_host[1];
   spec.cell[2] = voxel_size_host[2];
@@ -721,7 +743,7 @@ extern "C" int pg_voxel_centroids(const float* xyz, const int32_t* frame_ptr, in
   PG_REQUIRE(xyz && frame_ptr && voxel_size_host && out_centroids && out_frame_ptr && out_num_host,
              "pg_voxel_centroids: null argument");
   PG_REQUIRE(voxel_size_host[0] > 0 && voxel_size_host[1] > 0 && voxel_size_host[2] > 0, "voxel size must be positive");
-  GridSpec spec;
+  GridSpec spec{};
   spec.cell[0] = voxel_size_host[0];
   spec.cell[1] = voxel_size_host[1];
   spec.cell[2] = voxel_size_host[2];
@@ -758,7 +780,7 @@ extern "C" int pg_voxel_keypoints_select(const float* xyz, const int32_t* frame_
                  out_num_keypoints_host,
              "pg_voxel_keypoints_select: null argument");
   PG_REQUIRE(voxel_size_host[0] > 0 && voxel_size_host[1] > 0 && voxel_size_host[2] > 0, "voxel size must be positive");
-  GridSpec spec;
+  GridSpec spec{};
   spec.cell[0] = voxel_size_host[0];
   spec.cell[1] = voxel_size_host[1];
   spec.cell[2] = voxel_size_host[2];
@@ -880,12 +902,21 @@ extern "C" int pg_radius_graph(const float* points, const int32_t* point_frame_p
                                const int32_t* center_frame_ptr, int32_t num_frames, int64_t num_points,
                                int64_t num_centers, double radius, int32_t* out_row_ptr, int32_t* out_src,
                                int32_t* out_dst, int64_t capacity, int64_t* out_num_edges_host, void* stream) {
+  return pg_radius_graph_scaled(points, point_frame_ptr, centers, center_frame_ptr, num_frames, num_points, num_centers,
+                                radius, nullptr, out_row_ptr, out_src, out_dst, capacity, out_num_edges_host, stream);
+}
+
+extern "C" int pg_radius_graph_scaled(const float* points, const int32_t* point_frame_ptr, const float* centers,
+                                      const int32_t* center_frame_ptr, int32_t num_frames, int64_t num_points,
+                                      int64_t num_centers, double radius, const double* scale_host,
+                                      int32_t* out_row_ptr, int32_t* out_src, int32_t* out_dst, int64_t capacity,
+                                      int64_t* out_num_edges_host, void* stream) {
   cudaStream_t s = static_cast<cudaStream_t>(stream);
   PG_REQUIRE(points && point_frame_ptr && centers && center_frame_ptr && out_row_ptr && out_num_edges_host,
              "pg_radius_graph: null argument");
   PG_REQUIRE(num_centers >= 1 && num_centers < (int64_t(1) << 31) - 1, "num_centers out of range");
   RadiusPlan plan;
-  if (int rc = radius_prepare(points, point_frame_ptr, num_frames, num_points, radius, s, &plan)) return rc;
+  if (int rc = radius_prepare(points, point_frame_ptr, num_frames, num_points, radius, s, &plan, scale_host)) return rc;
   if (int rc = radius_count_impl(plan, centers, center_frame_ptr, num_frames, num_centers, out_row_ptr,
                                  out_num_edges_host, s))
     return rc;
@@ -960,7 +991,7 @@ extern "C" int pg_multi_level_graph(const float* xyz, const int32_t* frame_ptr, 
   PG_REQUIRE(kp_capacity >= 1 && kp_capacity <= num_points, "pg_multi_level_graph: keypoint capacity out of range");
   PG_REQUIRE(voxel_size_host[0] > 0 && voxel_size_host[1] > 0 && voxel_size_host[2] > 0, "voxel size must be positive");
   // ---- keypoints (multi_layer_downsampling_select, graph_gen.py:49-90) ---------------------------
-  GridSpec vspec;
+  GridSpec vspec{};
   vspec.cell[0] = voxel_size_host[0];
   vspec.cell[1] = voxel_size_host[1];
   vspec.cell[2] = voxel_size_host[2];

@@ -197,12 +197,13 @@ def _radius_edges(points, point_fp, centers, center_fp, radius, num_neighbors,
                   neighbors_downsample_method='random', scale=None, cap_seed=None):
     if num_neighbors > 0 and neighbors_downsample_method != 'random':
         raise NotImplementedError('only neighbors_downsample_method="random" exists in the reference (graph_gen.py:211)')
-    if scale is not None and not np.all(np.asarray(scale, dtype=np.float64) == 1.0):
-        # graph_gen.py:203-206 divides in float64 and builds the tree on float64 coordinates; dividing in
-        # float32 here would move boundary edges.  No shipped config passes `scale`.
-        raise NotImplementedError('per-axis `scale` of gen_disjointed_rnn_local_graph_v3 is not built '
-                                  '(unused by every shipped config)')
-    row_ptr, edges = _lib.radius_graph(points, point_fp, centers, center_fp, radius)
+    sc = None
+    if scale is not None:
+        # graph_gen.py:203-206: points_xyz / np.array(scale) is a float64 division; it is done inside the kernels
+        sc = np.broadcast_to(np.asarray(scale, dtype=np.float64), (3,))
+        if np.any(sc <= 0):
+            raise ValueError('scale must be positive')
+    row_ptr, edges = _lib.radius_graph(points, point_fp, centers, center_fp, radius, scale=sc)
     if num_neighbors > 0:
         # graph_gen.py:210-214: rows longer than num_neighbors keep a random subset of that size
         seed = cap_seed if cap_seed is not None else int(torch.randint(0, 2 ** 31 - 1, (1,), generator=_generator(),

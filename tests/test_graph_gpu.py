@@ -135,8 +135,6 @@ def test_per_axis_voxel_and_training_paths_raise(car):
     _check_graph(xyz, kw, got)
     with pytest.raises(NotImplementedError):      # random grid shift with the CENTROID method (graph_gen.py:24-39): not built
         graph_gen.gen_multi_level_local_graph_v3(xyz, 0.8, car.graph_kwargs['level_configs'], add_rnd3d=True)
-    with pytest.raises(NotImplementedError):      # per-axis `scale` (graph_gen.py:203-206): not built
-        graph_gen.gen_disjointed_rnn_local_graph_v3(xyz, xyz[:10], 1.0, -1, scale=[1.0, 2.0, 1.0])
     with pytest.raises(KeyError):
         graph_gen.gen_multi_level_local_graph_v3(xyz, 0.8, car.graph_kwargs['level_configs'], downsample_method='nope')
 
@@ -211,3 +209,30 @@ def test_multiscale_graph_batched_vs_oracle():
     for lvl in range(3):
         assert eo[lvl] == len(edges[lvl])
         assert int(fps[lvl + 1][-1]) == len(coords[lvl + 1])
+
+
+def test_scaled_radius_graph_vs_reference_golden():
+    """gen_disjointed_rnn_local_graph_v3(..., scale=[sx, sy, sz]) (graph_gen.py:203-206: float64 division of both point
+    sets before the ball tree) - bit-exact against the reference's own output, directly and through a level config."""
+    import os
+    from pointgnn_b200.models import graph_gen
+    g = np.load(os.path.join(os.path.dirname(__file__), 'golden', 'graph_scale.npz'))
+    for i in range(3):
+        scale = [float(v) for v in g['scale_%d' % i]]
+        e = graph_gen.gen_disjointed_rnn_local_graph_v3(g['xyz'], g['centers'], float(g['radius']), -1, scale=scale)
+        assert e.dtype == np.int64 and np.array_equal(e, g['edges_%d' % i]), i
+    # unscaled call unchanged, scale of ones identical to it
+    e1 = graph_gen.gen_disjointed_rnn_local_graph_v3(g['xyz'], g['centers'], 1.0, -1)
+    e2 = graph_gen.gen_disjointed_rnn_local_graph_v3(g['xyz'], g['centers'], 1.0, -1, scale=[1.0, 1.0, 1.0])
+    assert np.array_equal(e1, e2) and np.array_equal(e1, graph.gen_disjointed_rnn_local_graph_v3(g['xyz'], g['centers'], 1.0, -1))
+    cfg = [{'graph_gen_kwargs': {'num_neighbors': -1, 'radius': 1.0, 'scale': [1.0, 0.5, 1.0]},
+            'graph_gen_method': 'disjointed_rnn_local_graph_v3', 'graph_level': 0, 'graph_scale': 1},
+           {'graph_gen_kwargs': {'num_neighbors': -1, 'radius': 4.0, 'scale': [1.0, 0.5, 1.0]},
+            'graph_gen_method': 'disjointed_rnn_local_graph_v3', 'graph_level': 1, 'graph_scale': 1}]
+    xyz, _ = synth.lidar_frame(33, 5000)
+    got = graph_gen.gen_multi_level_local_graph_v3(xyz, 0.8, cfg)
+    want = graph.gen_multi_level_local_graph_v3(xyz, 0.8, cfg)
+    for a, b in zip(got[2], want[2]):
+        assert np.array_equal(a, b)
+    with pytest.raises(ValueError):
+        graph_gen.gen_disjointed_rnn_local_graph_v3(g['xyz'], g['centers'], 1.0, -1, scale=[1.0, 0.0, 1.0])

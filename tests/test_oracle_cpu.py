@@ -203,3 +203,14 @@ def test_oracle_multiscale_matches_reference_golden():
         assert np.array_equal(np.asarray(cents[i + 1], dtype=np.float64), g['centroids_%d' % (i + 1)])
     # level 2 repeats level 1's scale: identity (graph_gen.py:76-81)
     assert np.array_equal(kp[2][:, 0], np.arange(len(kp[1])))
+
+
+def test_oracle_scaled_radius_graph_matches_reference_golden():
+    """The per-axis `scale` of gen_disjointed_rnn_local_graph_v3 (graph_gen.py:203-206) against edge lists produced by
+    the reference's own function (tests/golden/graph_scale.npz)."""
+    import os
+    g = np.load(os.path.join(os.path.dirname(__file__), 'golden', 'graph_scale.npz'))
+    for i in range(3):
+        e = graph.gen_disjointed_rnn_local_graph_v3(g['xyz'], g['centers'], float(g['radius']), -1, scale=list(g['scale_%d' % i]))
+        assert np.array_equal(e, g['edges_%d' % i])
+    assert not np.array_equal(g['edges_0'], g['edges_1'])

@@ -284,12 +284,31 @@ def graph_multiscale_goldens():
     np.savez_compressed(os.path.join(GOLDEN, 'graph_multiscale.npz'), **out)
 
 
+def graph_scale_goldens():
+    """tests/golden/graph_scale.npz: the reference's OWN gen_disjointed_rnn_local_graph_v3 with the per-axis `scale`
+    argument (graph_gen.py:203-206; float64 division before the ball tree), rows in canonical order."""
+    ref = reference_graph.load()
+    xyz, _ = synth.lidar_frame(21, 3000)
+    centers = xyz[::7].copy()
+    out = {'xyz': xyz, 'centers': centers, 'radius': np.float64(1.0)}
+    for i, scale in enumerate(([1.0, 0.7, 1.3], [0.3, 1.0, 1.9], [2.0, 2.0, 2.0])):
+        e = ref.gen_disjointed_rnn_local_graph_v3(xyz, centers, 1.0, -1, scale=scale)
+        e = e[np.lexsort((e[:, 0], e[:, 1]))]
+        assert np.array_equal(e, graph.gen_disjointed_rnn_local_graph_v3(xyz, centers, 1.0, -1, scale=scale)), 'oracle != reference'
+        out['scale_%d' % i] = np.asarray(scale, dtype=np.float64)
+        out['edges_%d' % i] = e.astype(np.int32)
+        print('graph_scale', scale, 'edges', len(e))
+    np.savez_compressed(os.path.join(GOLDEN, 'graph_scale.npz'), **out)
+
+
 if __name__ == '__main__':
     which = sys.argv[1] if len(sys.argv) > 1 else 'all'
     if which in ('all', 'graph_random'):
         graph_random_goldens()
     if which in ('all', 'graph_multiscale'):
         graph_multiscale_goldens()
+    if which in ('all', 'graph_scale'):
+        graph_scale_goldens()
     if which in ('all', 'gnn'):
         main()
     if which in ('all', 'post'):
