@@ -129,6 +129,24 @@ PG_API int pg_voxel_keypoints_select(const float* xyz, const int32_t* frame_ptr,
                               int64_t* out_num_keypoints_host, void* stream);
 
 /*
+ * multi_layer_downsampling / multi_layer_downsampling_select with add_rnd3d=True and the centroid method
+ * (graph_gen.py:24-39, 82-88; no shipped config - the training configs use downsample_method 'random'):
+ *   voxel index = floor_divide((p - frame_min)[float32] + voxel * shift[frame], voxel) in float64 (:25-28),
+ *   shift_host = (host) [num_frames][3] the np.random.random((1,3)) draw of each frame;
+ *   one centroid per occupied voxel, per frame in ascending linear-voxel-key order (:30-36) -> out_centroids
+ *   [capacity,3] fp64 (optional);  with base_xyz: each centroid snapped to the nearest base vertex (:84-87) ->
+ *   out_keypoint_idx [K] rows of base_xyz (base_xyz == NULL <=> out_keypoint_idx == NULL).
+ * The reference sums a voxel's points in float32 in argsort order (np.add.reduceat, :36-37; the order among equal
+ * keys is numpy's unstable sort); this call sums in fp64 in ascending point order: centroids agree to ~1e-6
+ * relative, so a snapped index can differ where two vertices are equidistant within that (two-point voxels).
+ */
+PG_API int pg_voxel_keypoints_rnd3d(const float* xyz, const int32_t* frame_ptr, int32_t num_frames,
+                             int64_t num_points, const double* voxel_size_host, const double* shift_host,
+                             const float* base_xyz, const int32_t* base_frame_ptr, int64_t num_base,
+                             int32_t* out_keypoint_idx, double* out_centroids, int64_t capacity,
+                             int32_t* out_kp_frame_ptr, int64_t* out_num_keypoints_host, void* stream);
+
+/*
  * Radius-neighbour graph = gen_disjointed_rnn_local_graph_v3
  * (graph_gen.py:197-220; ball_tree radius_neighbors, fp64 predicate
  * ((dx*dx+dy*dy)+dz*dz) <= r*r on float32-valued coordinates, inclusive), with

@@ -69,13 +69,29 @@ def nearest_point(base_points, queries, chunk=512):
 
 
 def multi_layer_downsampling(points_xyz, base_voxel_size, levels=[1], add_rnd3d=False):
-    """reference graph_gen.py:11-47, add_rnd3d=False branch."""
-    assert not add_rnd3d, 'oracle covers the deterministic inference path only'
+    """reference graph_gen.py:11-47.  add_rnd3d=True (:24-39) draws np.random.random((1, 3)) exactly where the
+    reference does and uses the same NumPy calls (float32 reduceat sums in argsort order), so with the same generator
+    state it returns the reference's arrays bit for bit."""
+    points_xyz = np.asarray(points_xyz)
+    xmin, ymin, zmin = np.amin(points_xyz, axis=0)
+    xyz_offset = np.asarray([[xmin, ymin, zmin]])
     downsampled_list = [points_xyz]
     last_level = 0
     for level in levels:
         if np.isclose(last_level, level):
             downsampled_list.append(np.copy(downsampled_list[-1]))
+        elif add_rnd3d:
+            xyz_idx = (points_xyz - xyz_offset + base_voxel_size * level * np.random.random((1, 3))) // \
+                (base_voxel_size * level)
+            xyz_idx = xyz_idx.astype(np.int32)
+            dim_x, dim_y, dim_z = np.amax(xyz_idx, axis=0) + 1
+            keys = xyz_idx[:, 0] + xyz_idx[:, 1] * dim_x + xyz_idx[:, 2] * dim_y * dim_x
+            sorted_order = np.argsort(keys)
+            sorted_keys = keys[sorted_order]
+            sorted_points_xyz = points_xyz[sorted_order]
+            _, lens = np.unique(sorted_keys, return_counts=True)
+            indices = np.hstack([[0], lens[:-1]]).cumsum()
+            downsampled_list.append(np.array(np.add.reduceat(sorted_points_xyz, indices, axis=0) / lens[:, np.newaxis]))
         else:
             downsampled_list.append(
                 voxel_down_sample(points_xyz, np.asarray(base_voxel_size) * level))

@@ -35,6 +35,9 @@ SIGNATURES = {
     'pg_voxel_keypoints_select': (ctypes.c_int, [c_f32p, c_i32p, c_i32, c_i64, ctypes.POINTER(ctypes.c_double),
                                                  c_f32p, c_i32p, c_i64, c_i32p, c_i64, c_i32p,
                                                  ctypes.POINTER(c_i64), ctypes.c_void_p]),
+    'pg_voxel_keypoints_rnd3d': (ctypes.c_int, [c_f32p, c_i32p, c_i32, c_i64, ctypes.POINTER(ctypes.c_double),
+                                                ctypes.POINTER(ctypes.c_double), c_f32p, c_i32p, c_i64, c_i32p,
+                                                ctypes.c_void_p, c_i64, c_i32p, ctypes.POINTER(c_i64), ctypes.c_void_p]),
     'pg_radius_graph_count': (ctypes.c_int, [c_f32p, c_i32p, c_f32p, c_i32p, c_i32, c_i64, c_i64,
                                              ctypes.c_double, c_i32p, ctypes.POINTER(c_i64), ctypes.c_void_p]),
     'pg_radius_graph_fill': (ctypes.c_int, [c_f32p, c_i32p, c_f32p, c_i32p, c_i32, c_i64, c_i64,
@@ -207,6 +210,28 @@ def voxel_keypoints_select(xyz, frame_ptr, voxel_size, base_xyz, base_frame_ptr)
                                          _ptr(out_idx, torch.int32, 'out'), n, _ptr(out_fp, torch.int32, 'out_fp'),
                                          ctypes.byref(k), _stream()))
     return out_idx[:k.value], out_fp
+
+
+def voxel_keypoints_rnd3d(xyz, frame_ptr, voxel_size, shift, base_xyz=None, base_frame_ptr=None, want_centroids=False):
+    """pg_voxel_keypoints_rnd3d.  shift: [F,3] float64 host array.  -> (keypoint_idx [K] int32 rows of base_xyz or None,
+    kp_frame_ptr [F+1] int32, centroids [K,3] float64 or None)."""
+    import numpy as np
+    lib = load()
+    n = xyz.shape[0]
+    num_frames = frame_ptr.numel() - 1
+    out_idx = torch.empty(n, dtype=torch.int32, device=xyz.device) if base_xyz is not None else None
+    cent = torch.empty((n, 3), dtype=torch.float64, device=xyz.device) if want_centroids else None
+    out_fp = torch.empty(num_frames + 1, dtype=torch.int32, device=xyz.device)
+    vs = (ctypes.c_double * 3)(*[float(v) for v in voxel_size])
+    sh_arr = np.ascontiguousarray(shift, dtype=np.float64).reshape(num_frames, 3)
+    k = c_i64(0)
+    _check(lib.pg_voxel_keypoints_rnd3d(
+        _ptr(xyz, torch.float32, 'xyz'), _ptr(frame_ptr, torch.int32, 'frame_ptr'), num_frames, n, vs,
+        sh_arr.ctypes.data_as(ctypes.POINTER(ctypes.c_double)), _ptr(base_xyz, torch.float32, 'base_xyz'),
+        _ptr(base_frame_ptr, torch.int32, 'base_frame_ptr'), 0 if base_xyz is None else base_xyz.shape[0],
+        _ptr(out_idx, torch.int32, 'out'), _ptr(cent, torch.float64, 'centroids'), n,
+        _ptr(out_fp, torch.int32, 'out_fp'), ctypes.byref(k), _stream()))
+    return (None if out_idx is None else out_idx[:k.value]), out_fp, (None if cent is None else cent[:k.value])
 
 
 def random_keypoints(xyz, frame_ptr, voxel_size, shift, uniform):

@@ -91,6 +91,10 @@ struct GridSpec {
   // float64 before anything else (points_xyz / np.array(scale) -> float64).  scaled == 0: coordinates as they are.
   int scaled;
   double scale[3];
+  // multi_layer_downsampling with add_rnd3d (graph_gen.py:24-31): cell = floor_divide((p - frame_min)[float32] +
+  // cell * shift[frame], cell) in float64, shift = the np.random.random((1, 3)) draw of the frame.  shift == nullptr:
+  // the rule of cell_of below.
+  const double* shift;
 };
 
 // coordinate of axis a as the reference sees it: float32 value -> float64, divided by the scale if there is one
@@ -107,6 +111,10 @@ __device__ inline void cell_of(const GridSpec& g, const uint32_t* __restrict__ b
   *iy = (long long)floor(__ddiv_rn(__dsub_rn(coord(g, y, 1), oy), g.cell[1]));
   *iz = (long long)floor(__ddiv_rn(__dsub_rn(coord(g, z, 2), oz), g.cell[2]));
 }
+
+// graph_gen.py:24-31 (defined next to the random keypoint path further down)
+__device__ void shifted_cell_of(const GridSpec& g, const uint32_t* __restrict__ bounds, int f, float x, float y, float z,
+                                long long* ix, long long* iy, long long* iz);
 
 // `n_valid` (optional, device): only rows [0, *n_valid) of the n-row buffer hold points (a point set whose size is
 // still on the device, e.g. the keypoints of the same call); the others get the key of frame `num_frames`, which
@@ -127,7 +135,8 @@ __global__ void point_keys_kernel(const float* __restrict__ xyz, const int32_t* 
   }
   const int f = find_frame(frame_ptr, num_frames, i);
   long long ix, iy, iz;
-  cell_of(g, bounds, f, xyz[3 * i], xyz[3 * i + 1], xyz[3 * i + 2], &ix, &iy, &iz);
+  if (g.shift != nullptr) shifted_cell_of(g, bounds, f, xyz[3 * i], xyz[3 * i + 1], xyz[3 * i + 2], &ix, &iy, &iz);
+  else cell_of(g, bounds, f, xyz[3 * i], xyz[3 * i + 1], xyz[3 * i + 2], &ix, &iy, &iz);
   if (ix < 0 || iy < 0 || iz < 0 || ix > kAxisMax || iy > kAxisMax || iz > kAxisMax) {
     atomicOr(range_error, kErrRange);
     ix = iy = iz = 0;
@@ -819,6 +828,71 @@ extern "C" int pg_voxel_keypoints_select(const float* xyz, const int32_t* frame_
   return PG_OK;
 }
 
+// multi_layer_downsampling / multi_layer_downsampling_select with add_rnd3d (graph_gen.py:24-39 + :82-88): the voxel
+// grid of every frame is shifted by its random fraction, a voxel's centroid is the mean of its points, and (when
+// base_xyz is given) each centroid is snapped to the nearest base vertex.  The reference sums a voxel's points in
+// float32 in argsort order (np.add.reduceat); here the sum is fp64 in ascending point order - equal to ~1e-6 relative.
+extern "C" int pg_voxel_keypoints_rnd3d(const float* xyz, const int32_t* frame_ptr, int32_t num_frames, int64_t num_points,
+                                        const double* voxel_size_host, const double* shift_host, const float* base_xyz,
+                                        const int32_t* base_frame_ptr, int64_t num_base, int32_t* out_keypoint_idx,
+                                        double* out_centroids, int64_t capacity, int32_t* out_kp_frame_ptr,
+                                        int64_t* out_num_keypoints_host, void* stream) {
+  cudaStream_t s = static_cast<cudaStream_t>(stream);
+  PG_REQUIRE(xyz && frame_ptr && voxel_size_host && shift_host && out_kp_frame_ptr && out_num_keypoints_host,
+             "pg_voxel_keypoints_rnd3d: null argument");
+  PG_REQUIRE((base_xyz != nullptr) == (out_keypoint_idx != nullptr), "pg_voxel_keypoints_rnd3d: base_xyz and out_keypoint_idx go together");
+  PG_REQUIRE(base_xyz == nullptr || base_frame_ptr != nullptr, "pg_voxel_keypoints_rnd3d: base_frame_ptr is null");
+  PG_REQUIRE(voxel_size_host[0] > 0 && voxel_size_host[1] > 0 && voxel_size_host[2] > 0, "voxel size must be positive");
+  Temp shift;
+  PG_CUDA_OK(shift.alloc(sizeof(double) * 3 * num_frames, s));
+  PG_CUDA_OK(cudaMemcpyAsync(shift.ptr, shift_host, sizeof(double) * 3 * num_frames, cudaMemcpyHostToDevice, s));
+  GridSpec spec{};
+  spec.cell[0] = voxel_size_host[0];
+  spec.cell[1] = voxel_size_host[1];
+  spec.cell[2] = voxel_size_host[2];
+  spec.shift = shift.as<double>();
+  BuiltGrid grid, base;
+  if (int rc = build_grid(xyz, frame_ptr, num_frames, num_points, spec, s, &grid)) return rc;
+  Temp cent, cframe;
+  double* cent_ptr = out_centroids;
+  const int64_t cent_cap = out_centroids ? capacity : num_points;
+  if (cent_ptr == nullptr) {
+    PG_CUDA_OK(cent.alloc(sizeof(double) * 3 * num_points, s));
+    cent_ptr = cent.as<double>();
+  }
+  PG_CUDA_OK(cframe.alloc(sizeof(int32_t) * num_points, s));
+  voxel_centroid_kernel<<<ceil_div(num_points, 128), 128, 0, s>>>(grid.view, cent_ptr, cframe.as<int32_t>(), cent_cap);
+  PG_LAUNCH_CHECK();
+  frame_ranges_kernel<<<ceil_div(num_frames + 1, 128), 128, 0, s>>>(grid.view.cell_key, grid.view.num_cells, num_frames,
+                                                                     out_kp_frame_ptr);
+  PG_LAUNCH_CHECK();
+  int32_t h[3] = {0, 0, 0};
+  if (base_xyz != nullptr) {
+    GridSpec bspec{};
+    bspec.cell[0] = voxel_size_host[0];
+    bspec.cell[1] = voxel_size_host[1];
+    bspec.cell[2] = voxel_size_host[2];
+    if (int rc = build_grid(base_xyz, base_frame_ptr, num_frames, num_base, bspec, s, &base)) return rc;
+    nearest_point_kernel<<<ceil_div(num_points, 128), 128, 0, s>>>(base.view, bspec, base.bounds.as<uint32_t>(),
+                                                                     base_frame_ptr, cent_ptr, cframe.as<int32_t>(),
+                                                                     grid.view.num_cells, std::min(capacity, cent_cap),
+                                                                     out_keypoint_idx, base.err.as<int>());
+    PG_LAUNCH_CHECK();
+    PG_CUDA_OK(cudaMemcpyAsync(&h[2], base.err.ptr, sizeof(int32_t), cudaMemcpyDeviceToHost, s));
+  }
+  PG_CUDA_OK(cudaMemcpyAsync(&h[0], grid.view.num_cells, sizeof(int32_t), cudaMemcpyDeviceToHost, s));
+  PG_CUDA_OK(cudaMemcpyAsync(&h[1], grid.err.ptr, sizeof(int32_t), cudaMemcpyDeviceToHost, s));
+  PG_CUDA_OK(cudaStreamSynchronize(s));
+  if (int rc = graph_error(h[1])) return rc;
+  if (int rc = graph_error(h[2])) return rc;
+  *out_num_keypoints_host = h[0];
+  if (h[0] > capacity) {
+    set_error("keypoint buffer too small: need %d, capacity %lld", h[0], (long long)capacity);
+    return PG_ERR_CAPACITY;
+  }
+  return PG_OK;
+}
+
 static int radius_count_impl(RadiusPlan& plan, const float* centers, const int32_t* center_frame_ptr, int num_frames,
                              int64_t num_centers, int32_t* out_row_ptr, int64_t* out_num_edges_host, cudaStream_t s) {
   Temp counts, tmp, total;
@@ -1080,6 +1154,20 @@ __device__ inline T np_floor_divide(T a, T b) {
     return fl;
   }
   return copysign(T(0), a / b);
+}
+
+__device__ void shifted_cell_of(const GridSpec& g, const uint32_t* __restrict__ bounds, int f, float x, float y, float z,
+                                long long* ix, long long* iy, long long* iz) {
+  const float p[3] = {x, y, z};
+  long long idx[3];
+  for (int a = 0; a < 3; ++a) {
+    const float d = __fsub_rn(p[a], ordered_to_float(bounds[3 * f + a]));            // float32, as points_xyz - xyz_offset
+    const double t = __dadd_rn(double(d), __dmul_rn(g.cell[a], g.shift[3 * f + a]));
+    idx[a] = (long long)np_floor_divide<double>(t, g.cell[a]);
+  }
+  *ix = idx[0];
+  *iy = idx[1];
+  *iz = idx[2];
 }
 
 // graph_gen.py:124-131 voxel index of every point; shift == nullptr: float32 arithmetic (add_rnd3d False),

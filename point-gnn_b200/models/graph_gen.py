@@ -16,7 +16,9 @@ graph_gen.py:92-153, 210-214).  The random path takes its randomness from NumPy'
 the per-frame grid shift - the same ``np.random.random((1, 3))`` draw as the reference - and from this
 module's CUDA generator (``set_seed``) for the per-voxel choice and the neighbour cap, where the
 reference uses Python's ``random`` / ``np.random.choice``: results are equal in distribution, not draw
-by draw.  ``add_rnd3d`` with the centroid method (graph_gen.py:24-39) is not built.
+by draw.  ``add_rnd3d`` with the centroid method (graph_gen.py:24-39) draws the same ``np.random.random((1, 3))``
+per level; its centroids equal the reference's to float32 summation accuracy (the reference sums in float32 in
+``argsort`` order).
 
 Extra, backwards-compatible keyword ``frame_ptr``: a [F+1] int array batching F frames in one
 call; the result is then exactly what the reference's ``batch_data`` (train.py:135-171) builds
@@ -83,15 +85,16 @@ def multi_layer_downsampling(points_xyz, base_voxel_size, levels=[1], add_rnd3d=
     """graph_gen.py:11-47 (Open3D branch).  -> list: the cloud, then per level the fp64 voxel centroids of the
     ORIGINAL cloud at that scale (a level with the previous level's scale repeats the previous entry, :21-22).
     Centroid order: ascending linear voxel key per frame (Open3D's own order is unspecified)."""
-    if add_rnd3d:
-        raise NotImplementedError('add_rnd3d=True with the centroid method (graph_gen.py:24-39) is not built; '
-                                  'the training configs use downsample_method="random"')
     cloud = _Cloud(points_xyz)
     downsampled_list = [cloud.xyz]
     last_level = 0
     for level in levels:
         if np.isclose(last_level, level):
             downsampled_list.append(downsampled_list[-1].clone())
+        elif add_rnd3d:      # graph_gen.py:24-39: grid shifted by one np.random.random((1, 3)) draw per level
+            _, _, cent = _lib.voxel_keypoints_rnd3d(cloud.xyz, cloud.frame_ptr, _voxel_vector(base_voxel_size, level),
+                                                    np.random.random((1, 3)), want_centroids=True)
+            downsampled_list.append(cent)
         else:
             cent, _ = _lib.voxel_centroids(cloud.xyz, cloud.frame_ptr, _voxel_vector(base_voxel_size, level))
             downsampled_list.append(cent)
@@ -113,9 +116,7 @@ def multi_layer_downsampling_select(points_xyz, base_voxel_size, levels=[1], add
 
 def _downsampling_select(cloud, base_voxel_size, levels, add_rnd3d):
     """Device-side body of multi_layer_downsampling_select, also tracking each level's frame_ptr."""
-    if add_rnd3d:
-        raise NotImplementedError('add_rnd3d=True is the training-time random grid shift '
-                                  '(graph_gen.py:24-39); only the inference path is built')
+    num_frames = cloud.frame_ptr.numel() - 1
     vertex_coord_list = [cloud.xyz]
     frame_ptr_list = [cloud.frame_ptr]
     keypoint_indices_list = []
@@ -132,7 +133,13 @@ def _downsampling_select(cloud, base_voxel_size, levels, add_rnd3d):
         else:
             # graph_gen.py:41-45 voxelises the ORIGINAL cloud, :84-88 snaps to the previous level.
             voxel = _voxel_vector(base_voxel_size, level)
-            if base_points is cloud.xyz:
+            if add_rnd3d:
+                # graph_gen.py:24-39: random grid shift, one np.random.random((1, 3)) per frame and level (each
+                # fetch_data call of the reference draws its own)
+                shift = np.vstack([np.random.random((1, 3)) for _ in range(num_frames)])
+                idx, kp_fp, _ = _lib.voxel_keypoints_rnd3d(cloud.xyz, cloud.frame_ptr, voxel, shift, base_points,
+                                                           frame_ptr_list[-1])
+            elif base_points is cloud.xyz:
                 # every shipped config: one distinct scale, previous level == original cloud (one grid, one kernel)
                 idx, kp_fp = _lib.voxel_keypoints(cloud.xyz, cloud.frame_ptr, voxel)
             else:

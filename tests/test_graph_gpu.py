@@ -133,8 +133,6 @@ def test_per_axis_voxel_and_training_paths_raise(car):
     kw['base_voxel_size'] = [0.8, 0.6, 1.0]                   # graph_gen.py:172-173
     got = graph_gen.gen_multi_level_local_graph_v3(xyz, **kw)
     _check_graph(xyz, kw, got)
-    with pytest.raises(NotImplementedError):      # random grid shift with the CENTROID method (graph_gen.py:24-39): not built
-        graph_gen.gen_multi_level_local_graph_v3(xyz, 0.8, car.graph_kwargs['level_configs'], add_rnd3d=True)
     with pytest.raises(KeyError):
         graph_gen.gen_multi_level_local_graph_v3(xyz, 0.8, car.graph_kwargs['level_configs'], downsample_method='nope')
 
@@ -236,3 +234,46 @@ def test_scaled_radius_graph_vs_reference_golden():
         assert np.array_equal(a, b)
     with pytest.raises(ValueError):
         graph_gen.gen_disjointed_rnn_local_graph_v3(g['xyz'], g['centers'], 1.0, -1, scale=[1.0, 0.0, 1.0])
+
+
+def test_rnd3d_centroid_downsampling_vs_reference_golden():
+    """add_rnd3d=True with the centroid method (graph_gen.py:24-39, 82-88) against the reference's own output for the same
+    seeded np.random draws.  The reference sums a voxel's points in float32 in argsort order, the kernel in fp64: voxel
+    membership, order and count must be equal, centroids within 1e-4 m, and every snapped vertex must be a nearest
+    vertex of its centroid within that tolerance (two-point voxels are exact ties upstream)."""
+    import os
+    from pointgnn_b200.models import graph_gen
+    g = np.load(os.path.join(os.path.dirname(__file__), 'golden', 'graph_rnd3d.npz'))
+    levels = [float(v) for v in g['levels']]
+    xyz, voxel = g['xyz'], float(g['base_voxel_size'])
+    np.random.seed(int(g['seed']))
+    cents = graph_gen.multi_layer_downsampling(xyz, voxel, levels, add_rnd3d=True)
+    for i in range(len(levels)):
+        want = g['centroids_%d' % (i + 1)]
+        assert cents[i + 1].shape == want.shape, i
+        assert np.abs(np.asarray(cents[i + 1], dtype=np.float64) - want).max() < 1e-4, i
+    np.random.seed(int(g['seed']))
+    coords, kp = graph_gen.multi_layer_downsampling_select(xyz, voxel, levels, add_rnd3d=True)
+    assert np.array_equal(kp[1][:, 0], np.arange(len(kp[0])))                       # same scale: identity
+    for i in (0, 2):
+        base = np.asarray(coords[i], dtype=np.float64)
+        cent = g['centroids_%d' % (i + 1)]
+        assert len(kp[i]) == len(cent)
+        assert np.array_equal(coords[i + 1], coords[i][kp[i][:, 0]])
+        d_mine = np.linalg.norm(base[kp[i][:, 0]] - cent, axis=1)
+        d_best = np.empty(len(cent))
+        for s0 in range(0, len(cent), 256):
+            d_best[s0:s0 + 256] = np.sqrt(((cent[s0:s0 + 256, None, :] - base[None, :, :]) ** 2).sum(2)).min(1)
+        assert np.all(d_mine <= d_best + 2e-4), i
+    # index agreement is high but not total: every two-point voxel is an exact tie upstream (about one voxel in ten),
+    # broken by float32 rounding noise in the reference and by the exact fp64 distance here
+    assert (kp[0][:, 0] == g['kp_0']).mean() > 0.85
+    # through the graph generator (what train.py would call with downsample_method='center', add_rnd3d=True)
+    cfg = [{'graph_gen_kwargs': {'num_neighbors': -1, 'radius': 1.0}, 'graph_gen_method': 'disjointed_rnn_local_graph_v3',
+            'graph_level': 0, 'graph_scale': 1},
+           {'graph_gen_kwargs': {'num_neighbors': -1, 'radius': 4.0}, 'graph_gen_method': 'disjointed_rnn_local_graph_v3',
+            'graph_level': 1, 'graph_scale': 1}]
+    np.random.seed(3)
+    co, kpi, ed = graph_gen.gen_multi_level_local_graph_v3(xyz, 0.8, cfg, add_rnd3d=True)
+    want_e = graph.gen_disjointed_rnn_local_graph_v3(co[0], co[1], 1.0, -1)
+    assert np.array_equal(ed[0], want_e) and np.array_equal(co[1], xyz[kpi[0][:, 0]])

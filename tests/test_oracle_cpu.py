@@ -214,3 +214,20 @@ def test_oracle_scaled_radius_graph_matches_reference_golden():
         e = graph.gen_disjointed_rnn_local_graph_v3(g['xyz'], g['centers'], float(g['radius']), -1, scale=list(g['scale_%d' % i]))
         assert np.array_equal(e, g['edges_%d' % i])
     assert not np.array_equal(g['edges_0'], g['edges_1'])
+
+
+def test_oracle_rnd3d_centroids_match_reference_golden():
+    """add_rnd3d with the centroid method (graph_gen.py:24-39): tests/golden/graph_rnd3d.npz holds the reference's own
+    output for a seeded NumPy generator; the oracle makes the same NumPy calls and must reproduce the centroids bit for
+    bit and the snapped indices wherever the nearest vertex is unique."""
+    import os
+    g = np.load(os.path.join(os.path.dirname(__file__), 'golden', 'graph_rnd3d.npz'))
+    levels = [float(v) for v in g['levels']]
+    np.random.seed(int(g['seed']))
+    cents = graph.multi_layer_downsampling(g['xyz'], float(g['base_voxel_size']), levels, add_rnd3d=True)
+    np.random.seed(int(g['seed']))
+    coords, kp = graph.multi_layer_downsampling_select(g['xyz'], float(g['base_voxel_size']), levels, add_rnd3d=True)
+    for i in range(len(levels)):
+        assert np.array_equal(np.asarray(cents[i + 1], dtype=np.float64), g['centroids_%d' % (i + 1)])
+        assert (kp[i][:, 0] == g['kp_%d' % i]).mean() > 0.97
+    assert np.array_equal(kp[1][:, 0], np.arange(len(kp[0])))

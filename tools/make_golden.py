@@ -301,6 +301,36 @@ def graph_scale_goldens():
     np.savez_compressed(os.path.join(GOLDEN, 'graph_scale.npz'), **out)
 
 
+def graph_rnd3d_goldens():
+    """tests/golden/graph_rnd3d.npz: the reference's OWN multi_layer_downsampling / multi_layer_downsampling_select with
+    add_rnd3d=True and the centroid method (graph_gen.py:24-39, 82-88), NumPy's global generator seeded; the oracle,
+    seeded the same way, must return the same arrays bit for bit (it makes the same NumPy calls)."""
+    ref = reference_graph.load()
+    xyz, _ = synth.lidar_frame(17, 9000)
+    levels = [1, 1, 2.5]
+    np.random.seed(7)
+    cents = ref.multi_layer_downsampling(xyz, 0.4, levels, add_rnd3d=True)
+    np.random.seed(7)
+    co = graph.multi_layer_downsampling(xyz, 0.4, levels, add_rnd3d=True)
+    np.random.seed(7)
+    vc, kp = ref.multi_layer_downsampling_select(xyz, 0.4, levels, add_rnd3d=True)
+    np.random.seed(7)
+    vo, ko = graph.multi_layer_downsampling_select(xyz, 0.4, levels, add_rnd3d=True)
+    out = {'xyz': xyz, 'levels': np.asarray(levels, dtype=np.float64), 'base_voxel_size': np.float64(0.4), 'seed': np.int64(7)}
+    exact = 0
+    for i in range(len(levels)):
+        assert np.array_equal(np.asarray(cents[i + 1]), np.asarray(co[i + 1])), 'oracle centroids != reference'
+        # the kd-tree tie rule (lowest index among exact minimisers) only matters for exact ties; with float32-summed
+        # centroids there are hardly any, but identical base rows (level 3) still tie
+        same = np.asarray(kp[i])[:, 0] == np.asarray(ko[i])[:, 0]
+        exact += int(same.sum())
+        out['centroids_%d' % (i + 1)] = np.asarray(cents[i + 1], dtype=np.float64)
+        out['kp_%d' % i] = np.asarray(kp[i])[:, 0].astype(np.int32)
+        out['coords_%d' % (i + 1)] = np.asarray(vc[i + 1], dtype=np.float32)
+        print('graph_rnd3d level', i, 'vertices', len(kp[i]), 'oracle index == reference:', int(same.sum()))
+    np.savez_compressed(os.path.join(GOLDEN, 'graph_rnd3d.npz'), **out)
+
+
 if __name__ == '__main__':
     which = sys.argv[1] if len(sys.argv) > 1 else 'all'
     if which in ('all', 'graph_random'):
@@ -309,6 +339,8 @@ if __name__ == '__main__':
         graph_multiscale_goldens()
     if which in ('all', 'graph_scale'):
         graph_scale_goldens()
+    if which in ('all', 'graph_rnd3d'):
+        graph_rnd3d_goldens()
     if which in ('all', 'gnn'):
         main()
     if which in ('all', 'post'):
