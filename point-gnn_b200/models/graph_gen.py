@@ -18,7 +18,8 @@ module's CUDA generator (``set_seed``) for the per-voxel choice and the neighbou
 reference uses Python's ``random`` / ``np.random.choice``: results are equal in distribution, not draw
 by draw.  ``add_rnd3d`` with the centroid method (graph_gen.py:24-39) draws the same ``np.random.random((1, 3))``
 per level; its centroids equal the reference's to float32 summation accuracy (the reference sums in float32 in
-``argsort`` order).
+``argsort`` order).  The per-axis ``scale`` of ``gen_disjointed_rnn_local_graph_v3`` (graph_gen.py:203-206) is
+divided in float64 inside the kernels, as ``points_xyz / np.array(scale)`` does.
 
 Extra, backwards-compatible keyword ``frame_ptr``: a [F+1] int array batching F frames in one
 call; the result is then exactly what the reference's ``batch_data`` (train.py:135-171) builds
